@@ -1,0 +1,93 @@
+/*
+ * strom_b200.h -- engine-level C ABI of libstrom_b200.so (beyond the 13 BeagleLib-compatible
+ * calls of strom_beagle.h).  These are the "thin C-ABI layer over CUDA streams" the host
+ * (strom_b200/host/likelihood.hpp, bench.py, tests) uses for:
+ *   - device / stream selection (one instance per GPU, caller-provided stream),
+ *   - byte-coded tip upload (reference path: Likelihood::setTipStates, src/likelihood.hpp:228-247,
+ *     uploads 4-byte ints; at 1000 taxa x 1M patterns the engine takes the 1-byte codes directly),
+ *   - one fused evaluation call replacing the per-call sequence of
+ *     Likelihood::calcLogLikelihood (src/likelihood.hpp:409-447),
+ *   - a non-synchronising variant that leaves the scalar on the device for the cross-GPU sum,
+ *   - buffer read-back for per-buffer parity tests,
+ *   - schedule inspection (host logic, callable without a GPU).
+ * All functions return a BeagleReturnCodes value unless stated otherwise.
+ */
+#ifndef STROM_B200_H
+#define STROM_B200_H
+
+#include "strom_beagle.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Model + tree description of one evaluation; every pointer is caller-owned host memory. */
+typedef struct {
+    const double* stateFrequencies;      /* [4]            src/model.hpp:327-335 */
+    const double* eigenVectors;          /* [16] row-major src/model.hpp:315-325 */
+    const double* inverseEigenVectors;   /* [16] row-major */
+    const double* eigenValues;           /* [4] */
+    const double* categoryRates;         /* [categoryCount] src/model.hpp:337-344 */
+    const double* categoryWeights;       /* [categoryCount] src/model.hpp:346-354 */
+    const int*    matrixIndices;         /* [edgeCount]     src/likelihood.hpp:308-315, :353-354 */
+    const double* edgeLengths;           /* [edgeCount] */
+    int           edgeCount;
+    const BeagleOperation* operations;   /* [operationCount] src/likelihood.hpp:321-347 */
+    int           operationCount;
+    int           rootParentBuffer;      /* preorder[0] number, src/likelihood.hpp:427 */
+    int           rootChildBuffer;       /* root tip number,   src/likelihood.hpp:424 */
+    int           rootMatrix;            /* = rootChildBuffer, src/likelihood.hpp:433 */
+} StromEvalArgs;
+
+/* Library version string (static storage). */
+STROM_API const char* sb200Version(void);
+
+/* CUDA device new instances are created on (default: device 0). */
+STROM_API int sb200SetDevice(int device);
+
+/* Run the instance on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores
+ * the instance's own stream. */
+STROM_API int sb200SetStream(int instance, void* cudaStream);
+
+/* Tip upload from 1-byte codes (0..3, anything else = missing). */
+STROM_API int sb200SetTipStatesU8(int instance, int tipIndex, const unsigned char* inStates);
+
+/* One whole Likelihood::calcLogLikelihood: parameter upload, all transition matrices, all
+ * partials with rescaling, root-edge reduction, scalar back on the host.  Synchronises. */
+STROM_API int sb200Eval(int instance, const StromEvalArgs* args, double* outLogLikelihood);
+
+/* Same work, no host synchronisation: the pattern-weighted log-likelihood of this instance's
+ * pattern slice is left in *deviceOut (a device pointer to one double) in stream order. */
+STROM_API int sb200EvalAsync(int instance, const StromEvalArgs* args, double* deviceOut);
+
+/* Re-run the last evaluation's device work (matrices, partials, root reduction) with the
+ * parameters already resident in HBM; no host->device copy, no synchronisation.  Used by
+ * bench.py for the device-only `value` leg. */
+STROM_API int sb200ReplayAsync(int instance, double* deviceOut);
+
+/* Blocks until the instance's stream is idle. */
+STROM_API int sb200Synchronize(int instance);
+
+/* Read-back for parity tests: partials as [pattern][category][4] doubles (FP32 instances are
+ * widened), cumulative scale buffer as [pattern] log factors, matrix as [category][4][4]. */
+STROM_API int sb200GetPartials(int instance, int bufferIndex, double* out);
+STROM_API int sb200GetScaleFactors(int instance, int scaleIndex, double* out);
+STROM_API int sb200GetTransitionMatrix(int instance, int matrixIndex, double* out);
+
+/* Number of kernels this instance has launched since creation (bench.py's gpu_launches). */
+STROM_API long sb200LaunchCount(int instance);
+
+/* Algorithmic HBM bytes of the last beagleUpdatePartials call per SURVEY.md section 8(d)
+ * (unfused per-operation traffic), and the bytes the chain-fused schedule actually moves. */
+STROM_API int sb200LastTraffic(int instance, double* algorithmicBytes, double* scheduledBytes);
+
+/* Host-only schedule inspection (no GPU needed): builds the chain/level schedule for an
+ * operation list and reports, per operation, its level and chain id.  Returns the number of
+ * levels (>= 0) or a negative error code.  chainOut/levelOut may be NULL. */
+STROM_API int sb200DebugSchedule(const BeagleOperation* operations, int operationCount, int tipCount,
+                                 int partialsBufferCount, int* levelOut, int* chainOut, int* chainCountOut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STROM_B200_H */

@@ -1,0 +1,879 @@
+// engine.cu -- the CUDA engine behind the boundary of include/strom_beagle.h and
+// include/strom_b200.h.  One instance = one GPU, one stream, all buffers resident in HBM:
+// byte-coded tips, every partials buffer, every transition matrix, the cumulative and subtree
+// log-scalers.  There is no CPU fallback: every entry point that computes does so with the
+// kernels of kernels.cuh or fails with a BeagleLib error code.
+//
+// Replaces what strom reaches through Likelihood (reference src/likelihood.hpp:165-448) and
+// Model::setBeagle* (reference src/model.hpp:315-354).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/strom_b200.h"
+#include "kernels.cuh"
+#include "schedule.hpp"
+
+namespace sb200 {
+
+struct CudaFail {
+    cudaError_t err;
+};
+#define CK(x)                                        \
+    do {                                             \
+        cudaError_t _e = (x);                        \
+        if (_e != cudaSuccess) throw CudaFail{_e};   \
+    } while (0)
+
+static int g_device = 0;
+
+// Host image of the per-call parameter block; mirrored 1:1 in HBM and refreshed by ONE copy.
+struct ParamBlockHeader {
+    double rates[kMaxCategories];
+};
+
+struct Engine {
+    int device = 0;
+    bool fp32 = false;
+    int nTips = 0, nPartials = 0, nCompact = 0, P = 0, nEigen = 0, nMat = 0, C = 0, nScale = 0;
+    long long tipStride = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+
+    // HBM
+    uint8_t* dTips = nullptr;
+    void* dPartials = nullptr;
+    void* dMats = nullptr;
+    double* dPatWeights = nullptr;
+    std::vector<double*> dScale;          // cumulative scale buffers, allocated on first use
+    std::vector<char> scaleZeroPending;   // reset requested, memset deferred (may be fused away)
+    double* dSlots = nullptr;
+    size_t slotCapacity = 0;
+    // parameter block: [ParamBlockHeader][DevModel x nEigen][int midx[edgeCap]][double elen[edgeCap]]
+    unsigned char* hBlock = nullptr;      // pinned
+    unsigned char* dBlock = nullptr;
+    size_t blockBytes = 0, modelOff = 0, midxOff = 0, elenOff = 0;
+    int edgeCap = 0, edgeCount = 0;
+    cudaEvent_t blockCopied = nullptr;
+    bool blockInFlight = false;
+    // schedule
+    Schedule sched;
+    uint64_t schedHash = 0;
+    bool schedValid = false;
+    std::vector<BeagleOperation> schedOps;
+    DevOp* dOps = nullptr;
+    DevChain* dChains = nullptr;
+    int* dRootSlots = nullptr;
+    size_t opsCap = 0, chainsCap = 0, rootCap = 0;
+    void* hSchedStage = nullptr;          // pinned staging for schedule uploads
+    size_t schedStageCap = 0;
+    cudaEvent_t schedCopied = nullptr;
+    bool schedInFlight = false;
+    int lastCumIndex = BEAGLE_OP_NONE;
+    // root reduction
+    double* dBlockSums = nullptr;
+    unsigned int* dTicket = nullptr;
+    double* dOut = nullptr;
+    double* hOut = nullptr;               // pinned
+    int rootBlocks = 0;
+    // last root-edge call (for replay)
+    int lastParent = -1, lastChild = -1, lastMatrix = -1, lastWIdx = 0, lastFIdx = 0, lastRootCum = BEAGLE_OP_NONE;
+    std::vector<char> tipSet;
+    long launches = 0;
+    double algBytes = 0, schedBytes = 0;
+
+    size_t realSize() const { return fp32 ? 4 : 8; }
+    ParamBlockHeader* hHeader() { return reinterpret_cast<ParamBlockHeader*>(hBlock); }
+    DevModel* hModel(int i) { return reinterpret_cast<DevModel*>(hBlock + modelOff) + i; }
+    int* hMidx() { return reinterpret_cast<int*>(hBlock + midxOff); }
+    double* hElen() { return reinterpret_cast<double*>(hBlock + elenOff); }
+    const double* dRates() const { return reinterpret_cast<const double*>(dBlock); }
+    const DevModel* dModel(int i) const { return reinterpret_cast<const DevModel*>(dBlock + modelOff) + i; }
+    const int* dMidx() const { return reinterpret_cast<const int*>(dBlock + midxOff); }
+    const double* dElen() const { return reinterpret_cast<const double*>(dBlock + elenOff); }
+
+    ~Engine() { destroy(); }
+
+    void destroy() {
+        cudaSetDevice(device);
+        if (ownStream) cudaStreamSynchronize(ownStream);
+        cudaFree(dTips); cudaFree(dPartials); cudaFree(dMats); cudaFree(dPatWeights);
+        for (double* p : dScale) cudaFree(p);
+        dScale.clear();
+        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dChains); cudaFree(dRootSlots);
+        cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut);
+        if (hBlock) cudaFreeHost(hBlock);
+        if (hSchedStage) cudaFreeHost(hSchedStage);
+        if (hOut) cudaFreeHost(hOut);
+        if (blockCopied) cudaEventDestroy(blockCopied);
+        if (schedCopied) cudaEventDestroy(schedCopied);
+        if (ownStream) cudaStreamDestroy(ownStream);
+        dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr;
+        dBlock = nullptr; dOps = nullptr; dChains = nullptr; dRootSlots = nullptr; dBlockSums = nullptr;
+        dTicket = nullptr; dOut = nullptr; hBlock = nullptr; hSchedStage = nullptr; hOut = nullptr;
+        blockCopied = nullptr; schedCopied = nullptr; ownStream = nullptr; stream = nullptr;
+    }
+
+    void layoutBlock(int cap) {
+        edgeCap = cap;
+        modelOff = sizeof(ParamBlockHeader);
+        midxOff = modelOff + sizeof(DevModel) * static_cast<size_t>(nEigen);
+        midxOff = (midxOff + 15) & ~size_t(15);
+        elenOff = midxOff + sizeof(int) * static_cast<size_t>(cap);
+        elenOff = (elenOff + 15) & ~size_t(15);
+        blockBytes = elenOff + sizeof(double) * static_cast<size_t>(cap);
+    }
+
+    void init() {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+        stream = ownStream;
+        CK(cudaEventCreateWithFlags(&blockCopied, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
+        tipStride = (static_cast<long long>(P) + 127) & ~127LL;
+        if (nTips > 0) {
+            CK(cudaMalloc(&dTips, static_cast<size_t>(nTips) * tipStride));
+            CK(cudaMemsetAsync(dTips, 4, static_cast<size_t>(nTips) * tipStride, stream));
+        }
+        tipSet.assign(nTips, 0);
+        const size_t bufElems = static_cast<size_t>(P) * C * 4;
+        if (nPartials > 0) CK(cudaMalloc(&dPartials, bufElems * nPartials * realSize()));
+        if (nMat > 0) {
+            CK(cudaMalloc(&dMats, static_cast<size_t>(nMat) * C * kMatStride * realSize()));
+            CK(cudaMemsetAsync(dMats, 0, static_cast<size_t>(nMat) * C * kMatStride * realSize(), stream));
+        }
+        CK(cudaMalloc(&dPatWeights, sizeof(double) * P));
+        CK(cudaMemsetAsync(dPatWeights, 0, sizeof(double) * P, stream));
+        dScale.assign(nScale, nullptr);
+        scaleZeroPending.assign(nScale, 0);
+        layoutBlock(nMat > 0 ? nMat : 1);
+        CK(cudaMallocHost(&hBlock, blockBytes));
+        std::memset(hBlock, 0, blockBytes);
+        CK(cudaMalloc(&dBlock, blockBytes));
+        for (int k = 0; k < kMaxCategories; ++k) hHeader()->rates[k] = 1.0;
+        const int perBlock = C <= 2 || C == 4 || C == 8 ? 256 / C : 128;
+        rootBlocks = (P + perBlock - 1) / perBlock;
+        CK(cudaMalloc(&dBlockSums, sizeof(double) * rootBlocks));
+        CK(cudaMalloc(&dTicket, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(dTicket, 0, sizeof(unsigned int), stream));
+        CK(cudaMalloc(&dOut, sizeof(double)));
+        CK(cudaMallocHost(&hOut, sizeof(double)));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    void waitBlockFree() {
+        if (blockInFlight) {
+            CK(cudaEventSynchronize(blockCopied));
+            blockInFlight = false;
+        }
+    }
+
+    double* scaleBuffer(int idx) {
+        if (!dScale[idx]) {
+            CK(cudaMalloc(&dScale[idx], sizeof(double) * P));
+            CK(cudaMemsetAsync(dScale[idx], 0, sizeof(double) * P, stream));
+            scaleZeroPending[idx] = 0;
+        }
+        return dScale[idx];
+    }
+
+    void materializeZero(int idx) {
+        double* b = scaleBuffer(idx);
+        if (scaleZeroPending[idx]) {
+            CK(cudaMemsetAsync(b, 0, sizeof(double) * P, stream));
+            scaleZeroPending[idx] = 0;
+        }
+    }
+
+    // ---- (a) ---------------------------------------------------------------------------
+    void uploadBlock() {
+        CK(cudaMemcpyAsync(dBlock, hBlock, blockBytes, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(blockCopied, stream));
+        blockInFlight = true;
+    }
+
+    void launchMatrices() {
+        if (edgeCount == 0) return;
+        const long long threads = static_cast<long long>(edgeCount) * C * 16;
+        const int blocks = static_cast<int>((threads + 255) / 256);
+        if (fp32)
+            transition_matrices_kernel<float><<<blocks, 256, 0, stream>>>(dModel(0), dRates(), dMidx(), dElen(), edgeCount, C,
+                                                                          static_cast<float*>(dMats));
+        else
+            transition_matrices_kernel<double><<<blocks, 256, 0, stream>>>(dModel(0), dRates(), dMidx(), dElen(), edgeCount,
+                                                                           C, static_cast<double*>(dMats));
+        CK(cudaGetLastError());
+        ++launches;
+    }
+
+    int setEdges(const int* idx, const double* len, int count) {
+        for (int u = 0; u < count; ++u)
+            if (idx[u] < 0 || idx[u] >= nMat) return BEAGLE_ERROR_OUT_OF_RANGE;
+        waitBlockFree();
+        if (count > edgeCap) {
+            // grow the block, preserving the model part
+            std::vector<unsigned char> keep(hBlock, hBlock + midxOff);
+            CK(cudaStreamSynchronize(stream));
+            cudaFreeHost(hBlock); cudaFree(dBlock);
+            hBlock = nullptr; dBlock = nullptr;
+            layoutBlock(count);
+            CK(cudaMallocHost(&hBlock, blockBytes));
+            std::memset(hBlock, 0, blockBytes);
+            std::memcpy(hBlock, keep.data(), keep.size());
+            CK(cudaMalloc(&dBlock, blockBytes));
+        }
+        std::memcpy(hMidx(), idx, sizeof(int) * count);
+        std::memcpy(hElen(), len, sizeof(double) * count);
+        edgeCount = count;
+        return BEAGLE_SUCCESS;
+    }
+
+    // ---- (b) ---------------------------------------------------------------------------
+    template <typename T>
+    static void ensureCap(T*& ptr, size_t& cap, size_t need) {
+        if (need <= cap) return;
+        cudaFree(ptr);
+        ptr = nullptr;
+        cap = need + need / 2 + 16;
+        CK(cudaMalloc(&ptr, sizeof(T) * cap));
+    }
+
+    int prepareSchedule(const BeagleOperation* ops, int count, bool accumulate) {
+        const uint64_t h = hashOps(ops, count, accumulate);
+        if (schedValid && h == schedHash && static_cast<int>(schedOps.size()) == count &&
+            (count == 0 || std::memcmp(schedOps.data(), ops, sizeof(BeagleOperation) * count) == 0))
+            return BEAGLE_SUCCESS;                     // same topology as last call: reuse plan in HBM
+        Schedule s;
+        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, s);
+        if (rc != BEAGLE_SUCCESS) return rc;
+        for (const DevOp& d : s.ops) {
+            if (d.a >= 0 && d.a < nTips && !tipSet[d.a]) return BEAGLE_ERROR_OUT_OF_RANGE;
+            if (d.b < nTips && !tipSet[d.b]) return BEAGLE_ERROR_OUT_OF_RANGE;
+        }
+        schedValid = false;
+        sched = std::move(s);
+        schedOps.assign(ops, ops + count);
+        schedHash = h;
+        // stage + upload
+        const size_t opsB = sizeof(DevOp) * sched.ops.size();
+        const size_t chB = sizeof(DevChain) * sched.chains.size();
+        const size_t rtB = sizeof(int) * sched.rootSlots.size();
+        const size_t total = opsB + chB + rtB;
+        if (schedInFlight) {
+            CK(cudaEventSynchronize(schedCopied));
+            schedInFlight = false;
+        }
+        if (total > schedStageCap) {
+            if (hSchedStage) cudaFreeHost(hSchedStage);
+            hSchedStage = nullptr;
+            schedStageCap = total + total / 2 + 256;
+            CK(cudaMallocHost(&hSchedStage, schedStageCap));
+        }
+        // device arrays may be in use by kernels still queued on the stream: growing them frees
+        // memory, so drain first (rare: only when the operation count grows)
+        if (sched.ops.size() > opsCap || sched.chains.size() > chainsCap || sched.rootSlots.size() > rootCap)
+            CK(cudaStreamSynchronize(stream));
+        ensureCap(dOps, opsCap, sched.ops.size());
+        ensureCap(dChains, chainsCap, sched.chains.size());
+        ensureCap(dRootSlots, rootCap, sched.rootSlots.size());
+        unsigned char* st = static_cast<unsigned char*>(hSchedStage);
+        if (opsB) std::memcpy(st, sched.ops.data(), opsB);
+        if (chB) std::memcpy(st + opsB, sched.chains.data(), chB);
+        if (rtB) std::memcpy(st + opsB + chB, sched.rootSlots.data(), rtB);
+        if (opsB) CK(cudaMemcpyAsync(dOps, st, opsB, cudaMemcpyHostToDevice, stream));
+        if (chB) CK(cudaMemcpyAsync(dChains, st + opsB, chB, cudaMemcpyHostToDevice, stream));
+        if (rtB) CK(cudaMemcpyAsync(dRootSlots, st + opsB + chB, rtB, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(schedCopied, stream));
+        schedInFlight = true;
+        const size_t needSlots = static_cast<size_t>(sched.slotCount) * P;
+        if (needSlots > slotCapacity) {
+            CK(cudaStreamSynchronize(stream));
+            cudaFree(dSlots);
+            dSlots = nullptr;
+            slotCapacity = needSlots + needSlots / 4;
+            CK(cudaMalloc(&dSlots, sizeof(double) * slotCapacity));
+        }
+        // traffic bookkeeping (bytes), SURVEY.md section 8(d)
+        const double b = static_cast<double>(realSize());
+        const double PC = static_cast<double>(P) * C, Pd = static_cast<double>(P);
+        algBytes = sched.nPartialPartial * (3 * 4 * b * PC) + sched.nTipPartial * (2 * 4 * b * PC + Pd) +
+                   sched.nTipTip * (4 * b * PC + 2 * Pd);
+        if (accumulate) algBytes += 16.0 * Pd * count;
+        schedBytes = (sched.partialReads + sched.partialWrites) * 4 * b * PC + sched.tipReads * Pd + sched.scalerRows * 8.0 * Pd;
+        schedValid = true;
+        return BEAGLE_SUCCESS;
+    }
+
+    template <typename real, int CC, int R>
+    void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
+        constexpr int perBlock = (kPruneThreads / CC) * R;
+        dim3 grid((P + perBlock - 1) / perBlock, L.chainCount);
+        prune_chains_kernel<real, CC, R><<<grid, kPruneThreads, 0, stream>>>(a, L.chainStart, cumMode);
+    }
+    template <typename real, int CC>
+    void launchLevelGeneric(const PruneArgs<real>& a, const Level& L, int cumMode) {
+        dim3 grid((P + 127) / 128, L.chainCount);
+        prune_chains_generic_kernel<real, CC><<<grid, 128, 0, stream>>>(a, L.chainStart, cumMode);
+    }
+
+    template <typename real>
+    void launchPartialsT(int cumIdx) {
+        double* cum = nullptr;
+        int cumMode = 0;
+        if (cumIdx != BEAGLE_OP_NONE) {
+            cum = scaleBuffer(cumIdx);
+            const bool singleRootAdd = !sched.sequential && sched.rootSlots.empty() && !sched.chains.empty();
+            if (scaleZeroPending[cumIdx]) {
+                if (singleRootAdd) {
+                    cumMode = 1;                       // the root chain overwrites: reset fused away
+                    scaleZeroPending[cumIdx] = 0;
+                } else {
+                    materializeZero(cumIdx);
+                }
+            }
+        }
+        PruneArgs<real> a;
+        a.partials = static_cast<real*>(dPartials);
+        a.tips = dTips;
+        a.mats = static_cast<const real*>(dMats);
+        a.slots = dSlots;
+        a.cum = cum;
+        a.ops = dOps;
+        a.chains = dChains;
+        a.tipStride = tipStride;
+        a.P = P;
+        a.nTips = nTips;
+        const bool big = static_cast<long long>(P) * C >= (1LL << 18);
+        for (const Level& L : sched.levels) {
+            if (L.chainCount == 0) continue;
+            switch (C) {
+                case 1: big ? launchLevelCG<real, 1, 2>(a, L, cumMode) : launchLevelCG<real, 1, 1>(a, L, cumMode); break;
+                case 2: big ? launchLevelCG<real, 2, 2>(a, L, cumMode) : launchLevelCG<real, 2, 1>(a, L, cumMode); break;
+                case 4: big ? launchLevelCG<real, 4, 2>(a, L, cumMode) : launchLevelCG<real, 4, 1>(a, L, cumMode); break;
+                case 8: big ? launchLevelCG<real, 8, 2>(a, L, cumMode) : launchLevelCG<real, 8, 1>(a, L, cumMode); break;
+                case 3: launchLevelGeneric<real, 3>(a, L, cumMode); break;
+                case 5: launchLevelGeneric<real, 5>(a, L, cumMode); break;
+                case 6: launchLevelGeneric<real, 6>(a, L, cumMode); break;
+                case 7: launchLevelGeneric<real, 7>(a, L, cumMode); break;
+            }
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        if (cum && !sched.rootSlots.empty()) {
+            const int nr = static_cast<int>(sched.rootSlots.size());
+            int mode = 0;
+            if (scaleZeroPending[cumIdx]) { mode = 1; scaleZeroPending[cumIdx] = 0; }
+            fold_roots_kernel<<<(P + 255) / 256, 256, 0, stream>>>(dSlots, dRootSlots, nr, cum, P, mode);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+    }
+
+    void launchPartials(int cumIdx) {
+        lastCumIndex = cumIdx;
+        if (fp32) launchPartialsT<float>(cumIdx);
+        else launchPartialsT<double>(cumIdx);
+    }
+
+    // ---- (c) ---------------------------------------------------------------------------
+    template <typename real>
+    void launchRootT(int parent, int child, int matrix, int wIdx, int fIdx, int cumIdx, double* out) {
+        RootArgs<real> a;
+        a.partials = static_cast<const real*>(dPartials);
+        a.tips = dTips;
+        a.mats = static_cast<const real*>(dMats);
+        a.model = dModel(fIdx);
+        a.catWeights = dModel(wIdx)->weights;
+        a.patWeights = dPatWeights;
+        a.cum = nullptr;
+        if (cumIdx != BEAGLE_OP_NONE) {
+            materializeZero(cumIdx);
+            a.cum = dScale[cumIdx];
+        }
+        a.blockSums = dBlockSums;
+        a.ticket = dTicket;
+        a.out = out;
+        a.tipStride = tipStride;
+        a.P = P;
+        a.nTips = nTips;
+        a.parent = parent;
+        a.child = child;
+        a.matrix = matrix;
+        switch (C) {
+            case 1: root_loglik_kernel<real, 1><<<rootBlocks, 256, 0, stream>>>(a); break;
+            case 2: root_loglik_kernel<real, 2><<<rootBlocks, 256, 0, stream>>>(a); break;
+            case 4: root_loglik_kernel<real, 4><<<rootBlocks, 256, 0, stream>>>(a); break;
+            case 8: root_loglik_kernel<real, 8><<<rootBlocks, 256, 0, stream>>>(a); break;
+            case 3: root_loglik_generic_kernel<real, 3><<<rootBlocks, 128, 0, stream>>>(a); break;
+            case 5: root_loglik_generic_kernel<real, 5><<<rootBlocks, 128, 0, stream>>>(a); break;
+            case 6: root_loglik_generic_kernel<real, 6><<<rootBlocks, 128, 0, stream>>>(a); break;
+            case 7: root_loglik_generic_kernel<real, 7><<<rootBlocks, 128, 0, stream>>>(a); break;
+        }
+        CK(cudaGetLastError());
+        ++launches;
+    }
+
+    int launchRoot(int parent, int child, int matrix, int wIdx, int fIdx, int cumIdx, double* out) {
+        const int nbuf = nTips + nPartials;
+        if (parent < nTips || parent >= nbuf || child < 0 || child >= nbuf || matrix < 0 || matrix >= nMat)
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (child < nTips && !tipSet[child]) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (wIdx < 0 || wIdx >= nEigen || fIdx < 0 || fIdx >= nEigen) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (cumIdx != BEAGLE_OP_NONE && (cumIdx < 0 || cumIdx >= nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        lastParent = parent; lastChild = child; lastMatrix = matrix; lastWIdx = wIdx; lastFIdx = fIdx; lastRootCum = cumIdx;
+        if (fp32) launchRootT<float>(parent, child, matrix, wIdx, fIdx, cumIdx, out);
+        else launchRootT<double>(parent, child, matrix, wIdx, fIdx, cumIdx, out);
+        return BEAGLE_SUCCESS;
+    }
+
+    int readScalar(double* out) {
+        CK(cudaMemcpyAsync(hOut, dOut, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        blockInFlight = false;
+        schedInFlight = false;
+        *out = *hOut;
+        return (*out != *out) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// instance table
+// ---------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::vector<std::unique_ptr<Engine>> g_inst;
+
+static Engine* getEngine(int id) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (id < 0 || id >= static_cast<int>(g_inst.size()) || !g_inst[id]) return nullptr;
+    return g_inst[id].get();
+}
+
+static int mapCuda(cudaError_t e) {
+    if (e == cudaErrorMemoryAllocation) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+        return BEAGLE_ERROR_NO_RESOURCE;
+    std::fprintf(stderr, "strom_b200: CUDA error %d (%s)\n", static_cast<int>(e), cudaGetErrorString(e));
+    return BEAGLE_ERROR_GENERAL;
+}
+
+// Runs `body` on instance `id` with its device current; converts every failure into a code.
+template <typename F>
+static int withEngine(int id, F&& body) {
+    Engine* E = getEngine(id);
+    if (!E) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+    try {
+        cudaError_t e = cudaSetDevice(E->device);
+        if (e != cudaSuccess) return mapCuda(e);
+        return body(*E);
+    } catch (const CudaFail& f) {
+        cudaGetLastError();
+        return mapCuda(f.err);
+    } catch (const std::bad_alloc&) {
+        return BEAGLE_ERROR_OUT_OF_MEMORY;
+    } catch (...) {
+        return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
+    }
+}
+
+static void fillCmat(const double* evec, const double* ivec, double* cmat) {
+    int l = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            for (int x = 0; x < 4; ++x) cmat[l++] = evec[i * 4 + x] * ivec[x * 4 + j];
+}
+
+static int evalCommon(Engine& E, const StromEvalArgs* a, double* deviceOut) {
+    if (!a || a->edgeCount < 0 || a->operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+    int rc = E.setEdges(a->matrixIndices, a->edgeLengths, a->edgeCount);
+    if (rc) return rc;
+    DevModel* m = E.hModel(0);
+    std::memcpy(m->freqs, a->stateFrequencies, sizeof(double) * 4);
+    fillCmat(a->eigenVectors, a->inverseEigenVectors, m->cmat);
+    std::memcpy(m->evals, a->eigenValues, sizeof(double) * 4);
+    std::memcpy(m->weights, a->categoryWeights, sizeof(double) * E.C);
+    std::memcpy(E.hHeader()->rates, a->categoryRates, sizeof(double) * E.C);
+    rc = E.prepareSchedule(a->operations, a->operationCount, true);
+    if (rc) return rc;
+    E.uploadBlock();
+    E.launchMatrices();
+    if (E.nScale < 1) return BEAGLE_ERROR_OUT_OF_RANGE;
+    E.scaleBuffer(0);
+    E.scaleZeroPending[0] = 1;
+    E.launchPartials(0);
+    return E.launchRoot(a->rootParentBuffer, a->rootChildBuffer, a->rootMatrix, 0, 0, 0, deviceOut ? deviceOut : E.dOut);
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+// =============================================================================================
+// The 13 BeagleLib-compatible entry points
+// =============================================================================================
+static char g_resName[256] = "CUDA device";
+static char g_resDesc[256] = "strom_b200 sm_100a engine";
+static BeagleResource g_res[16];
+static BeagleResourceList g_resList = {g_res, 0};
+static char g_resNames[16][256];
+
+extern "C" BeagleResourceList* beagleGetResourceList(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (n > 16) n = 16;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess)
+            std::snprintf(g_resNames[i], sizeof(g_resNames[i]), "%s", prop.name);
+        else
+            std::snprintf(g_resNames[i], sizeof(g_resNames[i]), "%s %d", g_resName, i);
+        g_res[i].name = g_resNames[i];
+        g_res[i].description = g_resDesc;
+        g_res[i].supportFlags = BEAGLE_FLAG_PRECISION_DOUBLE | BEAGLE_FLAG_PRECISION_SINGLE | BEAGLE_FLAG_SCALING_MANUAL |
+                                BEAGLE_FLAG_PROCESSOR_GPU | BEAGLE_FLAG_SCALERS_LOG | BEAGLE_FLAG_EIGEN_REAL;
+        g_res[i].requiredFlags = 0;
+    }
+    g_resList.length = n;
+    return &g_resList;
+}
+
+extern "C" int beagleCreateInstance(int tipCount, int partialsBufferCount, int compactBufferCount, int stateCount,
+                                    int patternCount, int eigenBufferCount, int matrixBufferCount, int categoryCount,
+                                    int scaleBufferCount, int* resourceList, int resourceCount, long preferenceFlags,
+                                    long requirementFlags, BeagleInstanceDetails* returnInfo) {
+    (void)preferenceFlags;   // the reference *prefers* PROCESSOR_CPU (src/likelihood.hpp:193); a preference only
+    if (stateCount != 4) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if (requirementFlags & (BEAGLE_FLAG_PROCESSOR_CPU | BEAGLE_FLAG_SCALING_AUTO | BEAGLE_FLAG_SCALING_ALWAYS |
+                            BEAGLE_FLAG_EIGEN_COMPLEX | BEAGLE_FLAG_SCALERS_RAW | BEAGLE_FLAG_VECTOR_SSE |
+                            BEAGLE_FLAG_THREADING_OPENMP))
+        return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if ((requirementFlags & BEAGLE_FLAG_PRECISION_SINGLE) && (requirementFlags & BEAGLE_FLAG_PRECISION_DOUBLE))
+        return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if (tipCount < 0 || partialsBufferCount < 0 || compactBufferCount < 0 || patternCount < 1 || eigenBufferCount < 1 ||
+        matrixBufferCount < 0 || categoryCount < 1 || scaleBufferCount < 0)
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (categoryCount > kMaxCategories) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if (compactBufferCount < tipCount) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // tips are compact states only
+    int device = g_device;
+    if (resourceList && resourceCount > 0) device = resourceList[0];
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return BEAGLE_ERROR_NO_RESOURCE;
+    }
+    if (device < 0 || device >= ndev) return BEAGLE_ERROR_NO_RESOURCE;
+    std::unique_ptr<Engine> E(new (std::nothrow) Engine());
+    if (!E) return BEAGLE_ERROR_OUT_OF_MEMORY;
+    E->device = device;
+    E->fp32 = (requirementFlags & BEAGLE_FLAG_PRECISION_SINGLE) != 0;
+    E->nTips = tipCount; E->nPartials = partialsBufferCount; E->nCompact = compactBufferCount; E->P = patternCount;
+    E->nEigen = eigenBufferCount; E->nMat = matrixBufferCount; E->C = categoryCount; E->nScale = scaleBufferCount;
+    try {
+        E->init();
+    } catch (const CudaFail& f) {
+        cudaGetLastError();
+        return mapCuda(f.err);
+    } catch (...) {
+        return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
+    }
+    if (returnInfo) {
+        returnInfo->resourceNumber = device;
+        returnInfo->resourceName = g_resName;
+        returnInfo->implName = const_cast<char*>(E->fp32 ? "strom_b200-CUDA-sm100a-4State-Single" : "strom_b200-CUDA-sm100a-4State-Double");
+        returnInfo->implDescription = g_resDesc;
+        returnInfo->flags = (E->fp32 ? BEAGLE_FLAG_PRECISION_SINGLE : BEAGLE_FLAG_PRECISION_DOUBLE) | BEAGLE_FLAG_SCALING_MANUAL |
+                            BEAGLE_FLAG_PROCESSOR_GPU | BEAGLE_FLAG_SCALERS_LOG | BEAGLE_FLAG_EIGEN_REAL;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t i = 0; i < g_inst.size(); ++i)
+        if (!g_inst[i]) {
+            g_inst[i] = std::move(E);
+            return static_cast<int>(i);
+        }
+    g_inst.push_back(std::move(E));
+    return static_cast<int>(g_inst.size()) - 1;
+}
+
+extern "C" int beagleFinalizeInstance(int instance) {
+    std::unique_ptr<Engine> E;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (instance < 0 || instance >= static_cast<int>(g_inst.size()) || !g_inst[instance])
+            return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+        E = std::move(g_inst[instance]);
+    }
+    E.reset();
+    return BEAGLE_SUCCESS;
+}
+
+static int setTipsCommon(Engine& E, int tipIndex, const int* s32, const unsigned char* s8) {
+    if (tipIndex < 0 || tipIndex >= E.nTips || tipIndex >= E.nCompact) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<unsigned char> codes(static_cast<size_t>(E.P));
+    if (s32)
+        for (int j = 0; j < E.P; ++j) codes[j] = (s32[j] >= 0 && s32[j] < 4) ? static_cast<unsigned char>(s32[j]) : 4;
+    else
+        for (int j = 0; j < E.P; ++j) codes[j] = s8[j] < 4 ? s8[j] : 4;
+    CK(cudaMemcpyAsync(E.dTips + static_cast<size_t>(tipIndex) * E.tipStride, codes.data(), static_cast<size_t>(E.P),
+                       cudaMemcpyHostToDevice, E.stream));
+    CK(cudaStreamSynchronize(E.stream));   // pageable source: make the copy's completion explicit
+    E.tipSet[tipIndex] = 1;
+    E.schedValid = false;
+    return BEAGLE_SUCCESS;
+}
+
+extern "C" int beagleSetTipStates(int instance, int tipIndex, const int* inStates) {
+    if (!inStates) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) { return setTipsCommon(E, tipIndex, inStates, nullptr); });
+}
+
+extern "C" int sb200SetTipStatesU8(int instance, int tipIndex, const unsigned char* inStates) {
+    if (!inStates) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) { return setTipsCommon(E, tipIndex, nullptr, inStates); });
+}
+
+extern "C" int beagleSetPatternWeights(int instance, const double* w) {
+    if (!w) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        CK(cudaMemcpyAsync(E.dPatWeights, w, sizeof(double) * E.P, cudaMemcpyHostToDevice, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleSetStateFrequencies(int instance, int idx, const double* f) {
+    if (!f) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (idx < 0 || idx >= E.nEigen) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        E.waitBlockFree();
+        std::memcpy(E.hModel(idx)->freqs, f, sizeof(double) * 4);
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleSetEigenDecomposition(int instance, int idx, const double* evec, const double* ivec,
+                                           const double* eval) {
+    if (!evec || !ivec || !eval) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (idx < 0 || idx >= E.nEigen) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        E.waitBlockFree();
+        fillCmat(evec, ivec, E.hModel(idx)->cmat);
+        std::memcpy(E.hModel(idx)->evals, eval, sizeof(double) * 4);
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleSetCategoryRates(int instance, const double* r) {
+    if (!r) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        E.waitBlockFree();
+        std::memcpy(E.hHeader()->rates, r, sizeof(double) * E.C);
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleSetCategoryWeights(int instance, int idx, const double* w) {
+    if (!w) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (idx < 0 || idx >= E.nEigen) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        E.waitBlockFree();
+        std::memcpy(E.hModel(idx)->weights, w, sizeof(double) * E.C);
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleUpdateTransitionMatrices(int instance, int eigenIndex, const int* probabilityIndices,
+                                              const int* d1, const int* d2, const double* edgeLengths, int count) {
+    if (d1 || d2) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if (count < 0 || (count > 0 && (!probabilityIndices || !edgeLengths))) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (eigenIndex != 0 && (eigenIndex < 0 || eigenIndex >= E.nEigen)) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        if (eigenIndex != 0) return static_cast<int>(BEAGLE_ERROR_NO_IMPLEMENTATION);
+        int rc = E.setEdges(probabilityIndices, edgeLengths, count);
+        if (rc) return rc;
+        E.uploadBlock();
+        E.launchMatrices();
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleResetScaleFactors(int instance, int cumulativeScaleIndex) {
+    return withEngine(instance, [&](Engine& E) {
+        if (cumulativeScaleIndex < 0 || cumulativeScaleIndex >= E.nScale) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        E.scaleBuffer(cumulativeScaleIndex);
+        E.scaleZeroPending[cumulativeScaleIndex] = 1;   // folded into the next partials update when possible
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleUpdatePartials(int instance, const BeagleOperation* operations, int operationCount,
+                                    int cumulativeScaleIndex) {
+    if (operationCount < 0 || (operationCount > 0 && !operations)) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (cumulativeScaleIndex != BEAGLE_OP_NONE && (cumulativeScaleIndex < 0 || cumulativeScaleIndex >= E.nScale))
+            return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        int rc = E.prepareSchedule(operations, operationCount, cumulativeScaleIndex != BEAGLE_OP_NONE);
+        if (rc) return rc;
+        E.launchPartials(cumulativeScaleIndex);
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int beagleCalculateEdgeLogLikelihoods(int instance, const int* parentBufferIndices, const int* childBufferIndices,
+                                                 const int* probabilityIndices, const int* d1, const int* d2,
+                                                 const int* categoryWeightsIndices, const int* stateFrequenciesIndices,
+                                                 const int* cumulativeScaleIndices, int count, double* outSumLogLikelihood,
+                                                 double* outD1, double* outD2) {
+    if (d1 || d2 || outD1 || outD2 || count != 1) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    if (!parentBufferIndices || !childBufferIndices || !probabilityIndices || !categoryWeightsIndices ||
+        !stateFrequenciesIndices || !cumulativeScaleIndices || !outSumLogLikelihood)
+        return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        int rc = E.launchRoot(parentBufferIndices[0], childBufferIndices[0], probabilityIndices[0],
+                              categoryWeightsIndices[0], stateFrequenciesIndices[0], cumulativeScaleIndices[0], E.dOut);
+        if (rc) return rc;
+        return E.readScalar(outSumLogLikelihood);
+    });
+}
+
+// =============================================================================================
+// Engine-level entry points (include/strom_b200.h)
+// =============================================================================================
+extern "C" const char* sb200Version(void) { return "strom_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int sb200SetDevice(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return BEAGLE_ERROR_NO_RESOURCE;
+    }
+    if (device < 0 || device >= n) return BEAGLE_ERROR_NO_RESOURCE;
+    g_device = device;
+    return BEAGLE_SUCCESS;
+}
+
+extern "C" int sb200SetStream(int instance, void* cudaStream) {
+    return withEngine(instance, [&](Engine& E) {
+        CK(cudaStreamSynchronize(E.stream));
+        E.stream = cudaStream ? static_cast<cudaStream_t>(cudaStream) : E.ownStream;
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200Eval(int instance, const StromEvalArgs* args, double* outLogLikelihood) {
+    if (!outLogLikelihood) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        int rc = evalCommon(E, args, nullptr);
+        if (rc) return rc;
+        return E.readScalar(outLogLikelihood);
+    });
+}
+
+extern "C" int sb200EvalAsync(int instance, const StromEvalArgs* args, double* deviceOut) {
+    if (!deviceOut) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) { return evalCommon(E, args, deviceOut); });
+}
+
+extern "C" int sb200ReplayAsync(int instance, double* deviceOut) {
+    return withEngine(instance, [&](Engine& E) {
+        if (!E.schedValid || E.lastParent < 0) return static_cast<int>(BEAGLE_ERROR_GENERAL);
+        E.launchMatrices();
+        if (E.lastCumIndex != BEAGLE_OP_NONE) E.scaleZeroPending[E.lastCumIndex] = 1;
+        E.launchPartials(E.lastCumIndex);
+        return E.launchRoot(E.lastParent, E.lastChild, E.lastMatrix, E.lastWIdx, E.lastFIdx, E.lastRootCum,
+                            deviceOut ? deviceOut : E.dOut);
+    });
+}
+
+extern "C" int sb200Synchronize(int instance) {
+    return withEngine(instance, [&](Engine& E) {
+        CK(cudaStreamSynchronize(E.stream));
+        E.blockInFlight = false;
+        E.schedInFlight = false;
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200GetPartials(int instance, int bufferIndex, double* out) {
+    if (!out) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (bufferIndex < E.nTips || bufferIndex >= E.nTips + E.nPartials) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        const size_t n = static_cast<size_t>(E.P) * E.C * 4;
+        CK(cudaStreamSynchronize(E.stream));
+        if (E.fp32) {
+            std::vector<float> tmp(n);
+            CK(cudaMemcpy(tmp.data(), static_cast<float*>(E.dPartials) + n * (bufferIndex - E.nTips), n * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) out[i] = tmp[i];
+        } else {
+            CK(cudaMemcpy(out, static_cast<double*>(E.dPartials) + n * (bufferIndex - E.nTips), n * 8, cudaMemcpyDeviceToHost));
+        }
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200GetScaleFactors(int instance, int scaleIndex, double* out) {
+    if (!out) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (scaleIndex < 0 || scaleIndex >= E.nScale) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        E.materializeZero(scaleIndex);
+        CK(cudaStreamSynchronize(E.stream));
+        CK(cudaMemcpy(out, E.dScale[scaleIndex], sizeof(double) * E.P, cudaMemcpyDeviceToHost));
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200GetTransitionMatrix(int instance, int matrixIndex, double* out) {
+    if (!out) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (matrixIndex < 0 || matrixIndex >= E.nMat) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        const size_t n = static_cast<size_t>(E.C) * kMatStride;
+        std::vector<double> full(n);
+        CK(cudaStreamSynchronize(E.stream));
+        if (E.fp32) {
+            std::vector<float> tmp(n);
+            CK(cudaMemcpy(tmp.data(), static_cast<float*>(E.dMats) + n * matrixIndex, n * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) full[i] = tmp[i];
+        } else {
+            CK(cudaMemcpy(full.data(), static_cast<double*>(E.dMats) + n * matrixIndex, n * 8, cudaMemcpyDeviceToHost));
+        }
+        for (int k = 0; k < E.C; ++k)
+            for (int e = 0; e < 16; ++e) out[k * 16 + e] = full[static_cast<size_t>(k) * kMatStride + e];
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" long sb200LaunchCount(int instance) {
+    Engine* E = getEngine(instance);
+    return E ? E->launches : -1;
+}
+
+extern "C" int sb200LastTraffic(int instance, double* algorithmicBytes, double* scheduledBytes) {
+    Engine* E = getEngine(instance);
+    if (!E) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+    if (algorithmicBytes) *algorithmicBytes = E->algBytes;
+    if (scheduledBytes) *scheduledBytes = E->schedBytes;
+    return BEAGLE_SUCCESS;
+}
+
+extern "C" int sb200DebugSchedule(const BeagleOperation* operations, int operationCount, int tipCount,
+                                  int partialsBufferCount, int* levelOut, int* chainOut, int* chainCountOut) {
+    try {
+        Schedule s;
+        int rc = buildSchedule(operations, operationCount, tipCount, partialsBufferCount, 1 << 30, 1 << 30, true, s);
+        if (rc) return rc;
+        for (int o = 0; o < operationCount; ++o) {
+            if (levelOut) levelOut[o] = s.opLevel[o];
+            if (chainOut) chainOut[o] = s.opChain[o];
+        }
+        if (chainCountOut) *chainCountOut = static_cast<int>(s.chains.size());
+        return static_cast<int>(s.levels.size());
+    } catch (...) {
+        return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
+    }
+}

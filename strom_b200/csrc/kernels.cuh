@@ -1,0 +1,550 @@
+// kernels.cuh -- the three hand-written sm_100a kernels of the tree-likelihood hot path.
+//
+//   (a) transition_matrices_kernel : BeagleLib beagleUpdateTransitionMatrices
+//                                     (reference call site src/likelihood.hpp:357-370)
+//   (b) prune_chains_kernel         : BeagleLib beagleUpdatePartials incl. per-node rescaling
+//                                     (reference call site src/likelihood.hpp:372-388)
+//   (c) root_loglik_kernel          : BeagleLib beagleCalculateEdgeLogLikelihoods
+//                                     (reference call site src/likelihood.hpp:418-447)
+//
+// HBM layout: partials [buffer][pattern][category][state] (one pattern x category = 4 reals =
+// one 256-bit load for FP64), tips [tip][pattern] 1-byte codes 0..4, matrices
+// [matrix][category][36] = 16 row-major entries + a 5x4 "tip table" T[s][i] = P[i][s] whose row
+// s=4 is all ones (the missing state), log-scalers [slot][pattern] FP64.
+//
+// The work is an HBM-bound 4x4 matrix-vector product (about 0.6 flop/byte): no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "schedule.hpp"
+
+namespace sb200 {
+
+constexpr int kMaxCategories = 8;
+constexpr int kMatStride = 36;      // reals per (matrix, category)
+constexpr int kPruneThreads = 256;
+
+// Per-eigen-index model block, resident in HBM and refreshed once per evaluation.
+struct DevModel {
+    double freqs[4];
+    double cmat[64];                 // cmat[(i*4+j)*4+x] = evec[i][x] * ivec[x][j]
+    double evals[4];
+    double weights[kMaxCategories];
+};
+
+template <typename real>
+struct PruneArgs {
+    real* partials;
+    const uint8_t* tips;
+    const real* mats;
+    double* slots;                   // subtree log-scaler sums [slot][pattern]
+    double* cum;                     // cumulative scale buffer or nullptr
+    const DevOp* ops;
+    const DevChain* chains;
+    long long tipStride;
+    int P;
+    int nTips;
+};
+
+template <typename real>
+struct RootArgs {
+    const real* partials;
+    const uint8_t* tips;
+    const real* mats;
+    const DevModel* model;           // already offset to the frequencies' index
+    const double* catWeights;        // weights of the requested index
+    const double* patWeights;
+    const double* cum;               // or nullptr
+    double* blockSums;
+    unsigned int* ticket;
+    double* out;
+    long long tipStride;
+    int P;
+    int nTips;
+    int parent;                      // buffer index
+    int child;                       // buffer index (tip or partials)
+    int matrix;
+};
+
+// ------------------------------------------------------------------------------------------
+// vector load/store helpers: one (pattern, category) = 4 reals
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
+template <typename real> __device__ __forceinline__ real rmax(real a, real b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+// (a) transition matrices: one thread per (edge, category, matrix entry)
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256)
+transition_matrices_kernel(const DevModel* __restrict__ model, const double* __restrict__ rates,
+                           const int* __restrict__ matrixIndex, const double* __restrict__ edgeLength,
+                           int count, int C, real* __restrict__ mats) {
+    const int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = flat & 15, uk = flat >> 4;
+    if (uk >= count * C) return;
+    const int u = uk / C, k = uk - u * C;
+    const int i = e >> 2, j = e & 3;
+    const double t = edgeLength[u] * rates[k];
+    const double* c = model->cmat + e * 4;
+    double sum = 0.0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) sum += c[x] * exp(model->evals[x] * t);
+    const real v = static_cast<real>(sum > 0.0 ? sum : 0.0);
+    real* base = mats + (static_cast<size_t>(matrixIndex[u]) * C + k) * kMatStride;
+    base[e] = v;                         // row-major P[i][j]
+    base[16 + j * 4 + i] = v;            // tip table T[s=j][i]
+    if (j == 0) base[32 + i] = real(1);  // T[4][i]: missing state
+}
+
+// ------------------------------------------------------------------------------------------
+// (b) pruning, chain-fused with per-node rescaling.
+//     C in {1,2,4,8}: one thread per (pattern, category), R patterns per thread.
+// ------------------------------------------------------------------------------------------
+template <int C> __device__ __forceinline__ int rmIndex(int e, int k) { return (((e >> 1) * C + k) << 1) + (e & 1); }
+
+template <typename real, int C>
+__device__ __forceinline__ void factorPartial(const real* __restrict__ sm, int k, const real (&v)[4], real (&F)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        real s = sm[rmIndex<C>(i * 4 + 0, k)] * v[0];
+        s += sm[rmIndex<C>(i * 4 + 1, k)] * v[1];
+        s += sm[rmIndex<C>(i * 4 + 2, k)] * v[2];
+        s += sm[rmIndex<C>(i * 4 + 3, k)] * v[3];
+        F[i] = s;
+    }
+}
+
+template <typename real, int C>
+__device__ __forceinline__ void factorTip(const real* __restrict__ sm, int k, int state, real (&F)[4]) {
+    const real* T = sm + 16 * C + (k * 5 + state) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) F[i] = T[i];
+}
+
+template <typename real, int C, int R>
+__global__ void __launch_bounds__(kPruneThreads)
+prune_chains_kernel(const PruneArgs<real> A, const int chainBase, const int cumMode) {
+    constexpr int G = kPruneThreads / C;                 // patterns per pass
+    constexpr int MSZ = kMatStride * C;                  // reals per operand
+    constexpr int NST = (2 * MSZ + kPruneThreads - 1) / kPruneThreads;
+    __shared__ __align__(16) real sm[2][2 * MSZ];
+
+    const int tid = threadIdx.x;
+    const int k = tid % C, g = tid / C;
+    const DevChain ch = A.chains[chainBase + blockIdx.y];
+
+    int p[R], pc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        p[r] = (blockIdx.x * R + r) * G + g;
+        pc[r] = p[r] < A.P ? p[r] : A.P - 1;
+    }
+    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
+
+    auto stageLoad = [&](const DevOp& op, real (&st)[NST]) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            const int q = tid + s * kPruneThreads;
+            if (q < 2 * MSZ) {
+                const int o = q / MSZ, w = q - o * MSZ;
+                st[s] = A.mats[static_cast<size_t>(o ? op.mb : op.ma) * MSZ + w];
+            }
+        }
+    };
+    auto stageStore = [&](real* dst, const real (&st)[NST]) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            const int q = tid + s * kPruneThreads;
+            if (q < 2 * MSZ) {
+                const int o = q / MSZ, w = q - o * MSZ;
+                const int kk = w / kMatStride, e = w - kk * kMatStride;
+                const int d = e < 16 ? rmIndex<C>(e, kk) : 16 * C + kk * 20 + (e - 16);
+                dst[o * MSZ + d] = st[s];
+            }
+        }
+    };
+    auto fetch = [&](int src, real (&v)[R][4], int (&state)[R]) {
+        if (src < A.nTips) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) state[r] = A.tips[static_cast<size_t>(src) * A.tipStride + pc[r]];
+        } else {
+            const real* base = A.partials + static_cast<size_t>(src - A.nTips) * bufStride;
+#pragma unroll
+            for (int r = 0; r < R; ++r) ld4(base + (static_cast<size_t>(pc[r]) * C + k) * 4, v[r]);
+        }
+    };
+
+    DevOp op = A.ops[ch.opStart];
+    real X[R][4], Y[R][4];
+    int sX[R], sY[R];
+    double acc[R], prod[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; sX[r] = 0; sY[r] = 0; }
+    {
+        real st[NST];
+        stageLoad(op, st);
+        fetch(op.a, X, sX);
+        fetch(op.b, Y, sY);
+        if (op.sa >= 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] += A.slots[static_cast<size_t>(op.sa) * A.P + pc[r]];
+        }
+        if (op.sb >= 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] += A.slots[static_cast<size_t>(op.sb) * A.P + pc[r]];
+        }
+        stageStore(sm[0], st);
+    }
+    __syncthreads();
+
+    for (int j = 0; j < ch.opCount; ++j) {
+        const bool more = j + 1 < ch.opCount;
+        DevOp nx = op;
+        real stn[NST];
+        real Yn[R][4];
+        int sYn[R];
+        double accn[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { accn[r] = 0.0; sYn[r] = 0; }
+        if (more) {
+            // software pipeline: next operation's matrices and sibling are requested before
+            // this operation's arithmetic so the HBM/L2 latency hides behind it
+            nx = A.ops[ch.opStart + j + 1];
+            stageLoad(nx, stn);
+            fetch(nx.b, Yn, sYn);
+            if (nx.sb >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) accn[r] = A.slots[static_cast<size_t>(nx.sb) * A.P + pc[r]];
+            }
+        }
+
+        const real* sa = sm[j & 1];
+        const real* sb = sa + MSZ;
+        const bool aTip = op.a >= 0 && op.a < A.nTips;
+        const bool bTip = op.b < A.nTips;
+        real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            real FA[4], FB[4], D[4];
+            if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
+            else factorPartial<real, C>(sa, k, X[r], FA);
+            if (bTip) factorTip<real, C>(sb, k, sY[r], FB);
+            else factorPartial<real, C>(sb, k, Y[r], FB);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) D[i] = FA[i] * FB[i];
+            if (op.flags & OP_RESCALE) {
+                real m = rmax(rmax(D[0], D[1]), rmax(D[2], D[3]));
+#pragma unroll
+                for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+                if (m == real(0)) m = real(1);
+                const real inv = real(1) / m;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) D[i] *= inv;
+                // deferred log: keep the product of maxima, fold into the sum before it can underflow
+                const double md = static_cast<double>(m);
+                if (md < 1e-100 || prod[r] < 1e-100) {
+                    acc[r] += log(prod[r]) + log(md);
+                    prod[r] = 1.0;
+                } else {
+                    prod[r] *= md;
+                }
+            }
+            if (p[r] < A.P) st4(dest + (static_cast<size_t>(p[r]) * C + k) * 4, D);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) X[r][i] = D[i];
+        }
+
+        if (more) {
+            stageStore(sm[(j + 1) & 1], stn);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Y[r][i] = Yn[r][i];
+                sY[r] = sYn[r];
+                acc[r] += accn[r];
+            }
+            op = nx;
+        }
+        __syncthreads();
+    }
+
+    if (k == 0 && (ch.sOut >= 0 || ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr))) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (p[r] < A.P) {
+                const double total = acc[r] + log(prod[r]);
+                if (ch.sOut >= 0) A.slots[static_cast<size_t>(ch.sOut) * A.P + p[r]] = total;
+                if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
+                    if (cumMode) A.cum[p[r]] = total;
+                    else A.cum[p[r]] += total;
+                }
+            }
+        }
+    }
+}
+
+// Any other category count (3,5,6,7): one thread per pattern, categories looped in registers.
+template <typename real, int C>
+__global__ void __launch_bounds__(128)
+prune_chains_generic_kernel(const PruneArgs<real> A, const int chainBase, const int cumMode) {
+    constexpr int MSZ = kMatStride * C;
+    __shared__ __align__(16) real sm[2 * MSZ];
+    const int tid = threadIdx.x;
+    const DevChain ch = A.chains[chainBase + blockIdx.y];
+    const int p = blockIdx.x * 128 + tid;
+    const int pc = p < A.P ? p : A.P - 1;
+    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
+    real X[C][4];
+    double acc = 0.0, prod = 1.0;
+
+    for (int j = 0; j < ch.opCount; ++j) {
+        const DevOp op = A.ops[ch.opStart + j];
+        __syncthreads();
+        for (int q = tid; q < 2 * MSZ; q += 128) {
+            const int o = q / MSZ, w = q - o * MSZ;
+            sm[q] = A.mats[static_cast<size_t>(o ? op.mb : op.ma) * MSZ + w];
+        }
+        __syncthreads();
+        if (op.sa >= 0) acc += A.slots[static_cast<size_t>(op.sa) * A.P + pc];
+        if (op.sb >= 0) acc += A.slots[static_cast<size_t>(op.sb) * A.P + pc];
+        const bool aTip = op.a >= 0 && op.a < A.nTips;
+        const bool bTip = op.b < A.nTips;
+        const int sA = aTip ? A.tips[static_cast<size_t>(op.a) * A.tipStride + pc] : 0;
+        const int sB = bTip ? A.tips[static_cast<size_t>(op.b) * A.tipStride + pc] : 0;
+        const real* pa = (op.a >= A.nTips) ? A.partials + static_cast<size_t>(op.a - A.nTips) * bufStride : nullptr;
+        const real* pb = bTip ? nullptr : A.partials + static_cast<size_t>(op.b - A.nTips) * bufStride;
+        real m = real(0);
+#pragma unroll
+        for (int kk = 0; kk < C; ++kk) {
+            const real* ma = sm + kk * kMatStride;
+            const real* mb = sm + MSZ + kk * kMatStride;
+            real FA[4], FB[4], Yv[4];
+            if (aTip) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) FA[i] = ma[16 + sA * 4 + i];
+            } else {
+                if (pa) ld4(pa + (static_cast<size_t>(pc) * C + kk) * 4, X[kk]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    FA[i] = ma[i * 4] * X[kk][0] + ma[i * 4 + 1] * X[kk][1] + ma[i * 4 + 2] * X[kk][2] + ma[i * 4 + 3] * X[kk][3];
+            }
+            if (bTip) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) FB[i] = mb[16 + sB * 4 + i];
+            } else {
+                ld4(pb + (static_cast<size_t>(pc) * C + kk) * 4, Yv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    FB[i] = mb[i * 4] * Yv[0] + mb[i * 4 + 1] * Yv[1] + mb[i * 4 + 2] * Yv[2] + mb[i * 4 + 3] * Yv[3];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                X[kk][i] = FA[i] * FB[i];
+                m = rmax(m, X[kk][i]);
+            }
+        }
+        if (op.flags & OP_RESCALE) {
+            if (m == real(0)) m = real(1);
+            const real inv = real(1) / m;
+#pragma unroll
+            for (int kk = 0; kk < C; ++kk)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) X[kk][i] *= inv;
+            const double md = static_cast<double>(m);
+            if (md < 1e-100 || prod < 1e-100) {
+                acc += log(prod) + log(md);
+                prod = 1.0;
+            } else {
+                prod *= md;
+            }
+        }
+        if (p < A.P) {
+            real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride + static_cast<size_t>(p) * C * 4;
+#pragma unroll
+            for (int kk = 0; kk < C; ++kk) st4(dest + kk * 4, X[kk]);
+        }
+    }
+    if (p < A.P) {
+        const double total = acc + log(prod);
+        if (ch.sOut >= 0) A.slots[static_cast<size_t>(ch.sOut) * A.P + p] = total;
+        if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
+            if (cumMode) A.cum[p] = total;
+            else A.cum[p] += total;
+        }
+    }
+}
+
+// Folds the subtree sums of several forest roots into the cumulative buffer, in list order.
+__global__ void fold_roots_kernel(const double* __restrict__ slots, const int* __restrict__ rootSlots, int nRoots,
+                                  double* __restrict__ cum, int P, int cumMode) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double s = cumMode ? 0.0 : cum[p];
+    for (int r = 0; r < nRoots; ++r) s += slots[static_cast<size_t>(rootSlots[r]) * P + p];
+    cum[p] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// (c) root-edge log-likelihood: site likelihoods, pattern weights, deterministic reduction
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Block-level sum of `v` (fixed order), then the last block to finish adds the per-block sums in
+// index order, so the result does not depend on scheduling.
+template <int THREADS>
+__device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums, unsigned int* ticket, double* out) {
+    __shared__ double warpPart[THREADS / 32];
+    __shared__ bool isLast;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    v = warpSum(v);
+    if (lane == 0) warpPart[w] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; ++i) s += warpPart[i];
+        blockSums[blockIdx.x] = s;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (isLast && w == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int i = lane; i < gridDim.x; i += 32) s += reinterpret_cast<volatile double*>(blockSums)[i];
+        s = warpSum(s);
+        if (lane == 0) {
+            *out = s;
+            *ticket = 0u;
+        }
+    }
+}
+
+template <typename real, int C>
+__global__ void __launch_bounds__(256)
+root_loglik_kernel(const RootArgs<real> A) {
+    constexpr int G = 256 / C;
+    __shared__ double W[C * 20];          // tip child: W[k][s][i] = pi_i * w_k * P_k[i][s]
+    __shared__ double M[C * 16];          // partials child: row-major P_k
+    __shared__ double fw[C * 4];          // pi_i * w_k
+    const int tid = threadIdx.x, k = tid % C, g = tid / C;
+    const bool childTip = A.child < A.nTips;
+    const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
+    for (int q = tid; q < C * 20; q += 256) {
+        const int kk = q / 20, e = q - kk * 20, i = e & 3;
+        W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[kk * kMatStride + 16 + e]);
+    }
+    for (int q = tid; q < C * 16; q += 256) M[q] = static_cast<double>(mat[(q >> 4) * kMatStride + (q & 15)]);
+    for (int q = tid; q < C * 4; q += 256) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
+    __syncthreads();
+
+    const int p = blockIdx.x * G + g;
+    const int pc = p < A.P ? p : A.P - 1;
+    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
+    real par[4];
+    ld4(A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + (static_cast<size_t>(pc) * C + k) * 4, par);
+    double term = 0.0;
+    if (childTip) {
+        const int s = A.tips[static_cast<size_t>(A.child) * A.tipStride + pc];
+        const double* w = W + (k * 5 + s) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) term += static_cast<double>(par[i]) * w[i];
+    } else {
+        real chv[4];
+        ld4(A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + (static_cast<size_t>(pc) * C + k) * 4, chv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double sj = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sj += M[k * 16 + i * 4 + j] * static_cast<double>(chv[j]);
+            term += sj * static_cast<double>(par[i]) * fw[k * 4 + i];
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < C; off <<= 1) term += __shfl_xor_sync(0xffffffffu, term, off);
+    double v = 0.0;
+    if (k == 0 && p < A.P) {
+        double ll = log(term);
+        if (A.cum) ll += A.cum[p];
+        v = ll * A.patWeights[p];
+    }
+    blockReduceAndFinish<256>(v, A.blockSums, A.ticket, A.out);
+}
+
+template <typename real, int C>
+__global__ void __launch_bounds__(128)
+root_loglik_generic_kernel(const RootArgs<real> A) {
+    __shared__ double W[C * 20];
+    __shared__ double M[C * 16];
+    __shared__ double fw[C * 4];
+    const int tid = threadIdx.x;
+    const bool childTip = A.child < A.nTips;
+    const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
+    for (int q = tid; q < C * 20; q += 128) {
+        const int kk = q / 20, e = q - kk * 20, i = e & 3;
+        W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[kk * kMatStride + 16 + e]);
+    }
+    for (int q = tid; q < C * 16; q += 128) M[q] = static_cast<double>(mat[(q >> 4) * kMatStride + (q & 15)]);
+    for (int q = tid; q < C * 4; q += 128) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
+    __syncthreads();
+    const int p = blockIdx.x * 128 + tid;
+    const int pc = p < A.P ? p : A.P - 1;
+    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
+    const real* pp = A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + static_cast<size_t>(pc) * C * 4;
+    const int s = childTip ? A.tips[static_cast<size_t>(A.child) * A.tipStride + pc] : 0;
+    const real* cp = childTip ? nullptr
+                              : A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + static_cast<size_t>(pc) * C * 4;
+    double site = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < C; ++kk) {
+        real par[4];
+        ld4(pp + kk * 4, par);
+        if (childTip) {
+            const double* w = W + (kk * 5 + s) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) site += static_cast<double>(par[i]) * w[i];
+        } else {
+            real chv[4];
+            ld4(cp + kk * 4, chv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double sj = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sj += M[kk * 16 + i * 4 + j] * static_cast<double>(chv[j]);
+                site += sj * static_cast<double>(par[i]) * fw[kk * 4 + i];
+            }
+        }
+    }
+    double v = 0.0;
+    if (p < A.P) {
+        double ll = log(site);
+        if (A.cum) ll += A.cum[p];
+        v = ll * A.patWeights[p];
+    }
+    blockReduceAndFinish<128>(v, A.blockSums, A.ticket, A.out);
+}
+
+}  // namespace sb200

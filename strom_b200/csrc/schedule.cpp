@@ -1,0 +1,196 @@
+// schedule.cpp -- see schedule.hpp.  Pure host code (no CUDA), exercised by the CPU test-suite
+// through sb200DebugSchedule.
+#include "schedule.hpp"
+
+#include <algorithm>
+
+namespace sb200 {
+
+uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate) {
+    uint64_t h = 1469598103934665603ull ^ (accumulate ? 0x9e3779b97f4a7c15ull : 0);
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(ops);
+    const size_t n = sizeof(BeagleOperation) * static_cast<size_t>(count);
+    for (size_t i = 0; i < n; ++i) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
+                  int matrixCount, int scaleCount, bool accumulate, Schedule& out) {
+    out = Schedule();
+    const int nbuf = tipCount + partialsBufferCount;
+    if (count < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+
+    for (int o = 0; o < count; ++o) {
+        const BeagleOperation& op = ops[o];
+        if (op.destinationPartials < tipCount || op.destinationPartials >= nbuf) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (op.child1Partials < 0 || op.child1Partials >= nbuf) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (op.child2Partials < 0 || op.child2Partials >= nbuf) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (op.child1TransitionMatrix < 0 || op.child1TransitionMatrix >= matrixCount) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (op.child2TransitionMatrix < 0 || op.child2TransitionMatrix >= matrixCount) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (op.destinationScaleWrite >= scaleCount) return BEAGLE_ERROR_OUT_OF_RANGE;
+        // Per-node scale buffers are write-only in the reference's usage (scale-read is always
+        // BEAGLE_OP_NONE, src/likelihood.hpp:329) and are not materialised by this engine.
+        if (op.destinationScaleRead != BEAGLE_OP_NONE) return BEAGLE_ERROR_NO_IMPLEMENTATION;
+    }
+
+    // Which operation produces each buffer, and how often each produced buffer is consumed.
+    std::vector<int> producer(nbuf, -1);
+    bool forest = true;
+    for (int o = 0; o < count; ++o) {
+        int d = ops[o].destinationPartials;
+        if (producer[d] >= 0) forest = false;          // written twice
+        producer[d] = o;
+    }
+    std::vector<int> in1(count, -1), in2(count, -1), consumers(count, 0);
+    for (int o = 0; o < count && forest; ++o) {
+        const BeagleOperation& op = ops[o];
+        if (op.child1Partials == op.destinationPartials || op.child2Partials == op.destinationPartials) forest = false;
+        int c[2] = {op.child1Partials, op.child2Partials};
+        for (int s = 0; s < 2; ++s) {
+            int pr = c[s] >= tipCount ? producer[c[s]] : -1;
+            if (pr > o) forest = false;                // reads a buffer a later operation overwrites
+            if (pr >= 0 && pr < o) {
+                (s == 0 ? in1 : in2)[o] = pr;
+                if (++consumers[pr] > 1) forest = false;
+            }
+        }
+        if (in1[o] >= 0 && in1[o] == in2[o]) forest = false;
+    }
+
+    out.opLevel.assign(count, 0);
+    out.opChain.assign(count, 0);
+    out.sequential = !forest;
+
+    auto classify = [&](const BeagleOperation& op) {
+        bool t1 = op.child1Partials < tipCount, t2 = op.child2Partials < tipCount;
+        if (t1 && t2) ++out.nTipTip;
+        else if (t1 || t2) ++out.nTipPartial;
+        else ++out.nPartialPartial;
+    };
+
+    if (!forest) {
+        // Conservative path: the list order is the only safe order; one operation per launch.
+        for (int o = 0; o < count; ++o) {
+            const BeagleOperation& op = ops[o];
+            classify(op);
+            const bool rescale = op.destinationScaleWrite >= 0;
+            DevOp d{op.destinationPartials - tipCount, op.child1Partials, op.child1TransitionMatrix,
+                    op.child2Partials, op.child2TransitionMatrix, -1, -1, rescale ? OP_RESCALE : 0};
+            out.ops.push_back(d);
+            out.chains.push_back(DevChain{o, 1, -1, (accumulate && rescale) ? CHAIN_ADD_TO_CUM : 0});
+            out.levels.push_back(Level{o, 1});
+            out.opLevel[o] = o;
+            out.opChain[o] = o;
+            out.partialReads += (op.child1Partials >= tipCount) + (op.child2Partials >= tipCount);
+            out.tipReads += (op.child1Partials < tipCount) + (op.child2Partials < tipCount);
+            out.partialWrites += 1;
+            if (accumulate && rescale) out.scalerRows += 2;
+        }
+        return BEAGLE_SUCCESS;
+    }
+
+    // Strahler-style levels and chains.
+    std::vector<std::vector<int>> chainOps;          // chain id -> input operation indices, bottom-up
+    std::vector<int> chainLevel;
+    std::vector<int> carriedChild(count, -1);        // which input child (0/1) is carried, -1 none
+    std::vector<char> readFromMemory(count, 0);      // produced buffer is re-read from HBM by its parent
+    for (int o = 0; o < count; ++o) {
+        classify(ops[o]);
+        const int i1 = in1[o], i2 = in2[o];
+        const int l1 = i1 >= 0 ? out.opLevel[i1] : -1;
+        const int l2 = i2 >= 0 ? out.opLevel[i2] : -1;
+        int carry = -1;
+        if (i1 >= 0 && (i2 < 0 || l1 > l2)) carry = 0;
+        else if (i2 >= 0 && (i1 < 0 || l2 > l1)) carry = 1;
+        if (carry >= 0) {
+            const int c = carry == 0 ? i1 : i2;
+            const int other = carry == 0 ? i2 : i1;
+            out.opLevel[o] = out.opLevel[c];
+            out.opChain[o] = out.opChain[c];
+            chainOps[out.opChain[o]].push_back(o);
+            carriedChild[o] = carry;
+            if (other >= 0) readFromMemory[other] = 1;
+        } else {
+            const int lvl = (i1 >= 0) ? l1 + 1 : 0;   // both in-list with equal level, or neither in-list
+            out.opLevel[o] = lvl;
+            out.opChain[o] = static_cast<int>(chainOps.size());
+            chainOps.emplace_back(1, o);
+            chainLevel.push_back(lvl);
+            if (i1 >= 0) readFromMemory[i1] = 1;
+            if (i2 >= 0) readFromMemory[i2] = 1;
+        }
+    }
+
+    // Subtree log-scaler slots: one per chain whose last buffer is re-read from memory by its
+    // parent, or that is a root of the forest when there are several roots.
+    const int nChains = static_cast<int>(chainOps.size());
+    std::vector<int> slotOfChain(nChains, -1);
+    std::vector<int> roots;
+    for (int o = 0; o < count; ++o) if (consumers[o] == 0) roots.push_back(o);
+    if (accumulate) {
+        for (int c = 0; c < nChains; ++c) {
+            const int last = chainOps[c].back();
+            const bool isRoot = consumers[last] == 0;
+            if (readFromMemory[last] || (isRoot && roots.size() > 1)) slotOfChain[c] = out.slotCount++;
+        }
+        if (roots.size() > 1)
+            for (int r : roots) out.rootSlots.push_back(slotOfChain[out.opChain[r]]);
+    }
+
+    // Emit chains level by level, longest first inside a level (they gate the launch's tail).
+    int maxLevel = -1;
+    for (int l : chainLevel) maxLevel = std::max(maxLevel, l);
+    std::vector<int> chainNewId(nChains, -1);
+    for (int lvl = 0; lvl <= maxLevel; ++lvl) {
+        std::vector<int> ids;
+        for (int c = 0; c < nChains; ++c) if (chainLevel[c] == lvl) ids.push_back(c);
+        std::stable_sort(ids.begin(), ids.end(),
+                         [&](int x, int y) { return chainOps[x].size() > chainOps[y].size(); });
+        Level L{static_cast<int>(out.chains.size()), static_cast<int>(ids.size())};
+        for (int c : ids) {
+            DevChain dc{static_cast<int>(out.ops.size()), static_cast<int>(chainOps[c].size()), slotOfChain[c], 0};
+            const int last = chainOps[c].back();
+            if (accumulate && consumers[last] == 0 && roots.size() == 1) {
+                dc.flags |= CHAIN_ADD_TO_CUM;
+                out.scalerRows += 2;
+            }
+            if (dc.sOut >= 0) out.scalerRows += 1;
+            chainNewId[c] = static_cast<int>(out.chains.size());
+            for (size_t j = 0; j < chainOps[c].size(); ++j) {
+                const int o = chainOps[c][j];
+                const BeagleOperation& op = ops[o];
+                const bool rescale = op.destinationScaleWrite >= 0;
+                DevOp d;
+                d.dest = op.destinationPartials - tipCount;
+                d.flags = rescale ? OP_RESCALE : 0;
+                auto slotFor = [&](int inOp) {
+                    return (accumulate && inOp >= 0) ? slotOfChain[out.opChain[inOp]] : -1;
+                };
+                if (carriedChild[o] < 0) {
+                    d.a = op.child1Partials; d.ma = op.child1TransitionMatrix; d.sa = slotFor(in1[o]);
+                    d.b = op.child2Partials; d.mb = op.child2TransitionMatrix; d.sb = slotFor(in2[o]);
+                } else if (carriedChild[o] == 0) {
+                    d.a = -1; d.ma = op.child1TransitionMatrix; d.sa = -1;
+                    d.b = op.child2Partials; d.mb = op.child2TransitionMatrix; d.sb = slotFor(in2[o]);
+                } else {
+                    d.a = -1; d.ma = op.child2TransitionMatrix; d.sa = -1;
+                    d.b = op.child1Partials; d.mb = op.child1TransitionMatrix; d.sb = slotFor(in1[o]);
+                }
+                if (d.a >= 0) (d.a < tipCount ? out.tipReads : out.partialReads) += 1;
+                (d.b < tipCount ? out.tipReads : out.partialReads) += 1;
+                out.scalerRows += (d.sa >= 0) + (d.sb >= 0);
+                out.partialWrites += 1;
+                out.ops.push_back(d);
+            }
+            out.chains.push_back(dc);
+        }
+        out.levels.push_back(L);
+    }
+    for (int o = 0; o < count; ++o) out.opChain[o] = chainNewId[out.opChain[o]];
+    return BEAGLE_SUCCESS;
+}
+
+}  // namespace sb200

@@ -1,0 +1,70 @@
+// schedule.hpp -- host-side planning of one beagleUpdatePartials call.
+//
+// The reference hands BeagleLib its operation list in reverse level-order
+// (Likelihood::defineOperations, reference src/likelihood.hpp:296-355) and BeagleLib executes
+// it one operation at a time, re-reading both children from memory.  On B200 that is (n-2)
+// dependent passes over HBM.  The planner below regroups the very same operations into
+// *chains*: a chain starts at an operation whose children are both already in memory (tips, or
+// partials finished in an earlier launch) and then climbs the tree, each next operation taking
+// the partials just produced straight from registers plus one sibling from memory.  A chain
+// never waits on another chain of the same launch: at a node whose two children sit in chains of
+// equal level both chains end and a new one starts one level up (Strahler numbering), so a tree
+// of n tips needs at most log2(n) launches instead of one per dependency level, and every
+// partials buffer is read from HBM at most once per evaluation.  Every destination buffer is
+// still written, so the buffers hold exactly what the reference's would.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/strom_beagle.h"
+
+namespace sb200 {
+
+// One operation as the pruning kernel consumes it (32 bytes, uploaded as-is).
+struct DevOp {
+    int dest;    // destination partials slot (= buffer index - tipCount)
+    int a;       // operand A: buffer index (tip if < tipCount), or -1 = carried in registers
+    int ma;      // transition matrix of A's edge
+    int b;       // operand B: buffer index (never carried)
+    int mb;      // transition matrix of B's edge
+    int sa;      // subtree log-scaler slot to add for A, or -1
+    int sb;      // subtree log-scaler slot to add for B, or -1
+    int flags;   // OP_RESCALE
+};
+enum { OP_RESCALE = 1 };
+
+struct DevChain {
+    int opStart;   // first DevOp of the chain
+    int opCount;
+    int sOut;      // slot receiving the chain's subtree log-scaler sum, or -1
+    int flags;     // CHAIN_ADD_TO_CUM
+};
+enum { CHAIN_ADD_TO_CUM = 1 };
+
+struct Level {
+    int chainStart;
+    int chainCount;
+};
+
+struct Schedule {
+    std::vector<DevOp> ops;
+    std::vector<DevChain> chains;
+    std::vector<Level> levels;
+    std::vector<int> rootSlots;     // slots of forest roots to fold into the cumulative buffer afterwards
+    int slotCount = 0;              // subtree log-scaler slots needed
+    bool sequential = false;        // true: list was not a forest; one operation per launch
+    // per input operation, for inspection / tests
+    std::vector<int> opLevel, opChain;
+    // traffic accounting, in units of "one partials buffer" / "one tip row" / "one scaler row"
+    long nTipTip = 0, nTipPartial = 0, nPartialPartial = 0;
+    long partialReads = 0, partialWrites = 0, tipReads = 0, scalerRows = 0;
+};
+
+// Returns BEAGLE_SUCCESS or an error code (index out of range, unsupported scale-read).
+int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
+                  int matrixCount, int scaleCount, bool accumulate, Schedule& out);
+
+// FNV-1a over the raw operation list, used to reuse a schedule when the topology is unchanged.
+uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate);
+
+}  // namespace sb200

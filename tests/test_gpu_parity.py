@@ -1,0 +1,180 @@
+"""Parity of the sm_100a engine against the CPU oracle, through the C ABI (include/strom_beagle.h).
+
+Tolerance: the north-star bar is 1e-9 relative on logL for FP64; the kernels differ from the
+oracle only in summation order, FMA contraction and exp/log ULPs, so the tests ask for 1e-11.
+Partials, matrices and cumulative log-scalers are compared buffer by buffer."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import MODEL_NAMES, Extra, full_eval, load_golden, named_model, random_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOGL_RTOL = 1e-11          # FP64 (north-star requirement: 1e-9)
+LOGL_RTOL_FP32 = 2e-5      # FP32 partials/matrices, FP64 scalers and accumulation (stated, measured in test)
+
+
+@pytest.mark.parametrize("key", ["rbcL", "rbcl10", "rbcl738"])
+@pytest.mark.parametrize("model", MODEL_NAMES)
+def test_logl_matches_golden_fixture(engine, key, model):
+    fx = load_golden(key)
+    ll = full_eval(engine, fx, named_model(model))
+    assert rel_err(ll, float(fx["lnL_" + model])) < LOGL_RTOL
+
+
+def test_reference_golden_values_on_gpu(engine):
+    # paup.nex:12 and rbcLjc.tre:57, straight from the engine
+    assert abs(full_eval(engine, load_golden("rbcl738"), named_model("gtr_g4")) - (-144730.8)) < 0.05
+    assert abs(-full_eval(engine, load_golden("rbcL"), named_model("jc")) - 286.9238) < 5e-5
+
+
+@pytest.mark.parametrize("key,model", [("rbcl10", "jc"), ("rbcl10", "gtr_g4"), ("rbcl10", "gtr_i_g4"), ("rbcL", "gtr_g8"),
+                                       ("rbcl738", "gtr_g4"), ("rbcl738", "gtr_g2")])
+def test_every_buffer_matches_oracle(engine, oracle, key, model):
+    fx = load_golden(key)
+    m = named_model(model)
+    n, P = fx["data"].shape
+    Cc = len(m["rates"])
+    ll_o, io = full_eval(oracle, fx, m, keep=True)
+    ll_e, ie = full_eval(engine, fx, m, keep=True)
+    xo, xe = Extra(oracle), Extra(engine)
+    for mi in set(fx["pmatrix_index"].tolist()):
+        assert np.allclose(xe.matrix(ie, mi, Cc), xo.matrix(io, mi, Cc), rtol=1e-12, atol=1e-15)
+    for op in fx["ops"]:
+        a, b = xe.partials(ie, int(op[0]), P, Cc), xo.partials(io, int(op[0]), P, Cc)
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-300), int(op[0])
+    assert np.allclose(xe.scale(ie, 0, P), xo.scale(io, 0, P), rtol=1e-12, atol=1e-12)
+    assert rel_err(ll_e, ll_o) < LOGL_RTOL
+    oracle.finalize(io)
+    engine.finalize(ie)
+
+
+@pytest.mark.parametrize("ntaxa,npat,model,seed", [(4, 1, "jc", 1), (5, 7, "gtr_g4", 2), (33, 129, "gtr_g4", 3),
+                                                   (64, 1000, "gtr_i_g4", 4), (200, 257, "gtr_g8", 5),
+                                                   (17, 63, "gtr_g3", 6), (100, 4097, "jc", 7), (3, 5, "gtr_g2", 8)])
+def test_random_trees_and_ragged_sizes(engine, oracle, ntaxa, npat, model, seed):
+    fx = random_problem(ntaxa, npat, seed, missing_frac=0.05)
+    m = named_model(model)
+    assert rel_err(full_eval(engine, fx, m), full_eval(oracle, fx, m)) < LOGL_RTOL
+
+
+def test_all_missing_column_and_zero_length_edges(engine, oracle):
+    fx = random_problem(12, 40, 11, missing_frac=0.0)
+    fx["data"][:, 3] = 4                      # a pattern with no information: site likelihood 1
+    fx["data"][5, :] = 4                      # a taxon that is all gaps
+    fx["edge_lengths"][::3] = 0.0             # zero-length edges (rbcl738nj.tre has them): P = I
+    fx["edge_lengths"][1] = 1e-12             # Node::_smallest_edge_length
+    m = named_model("gtr_g4")
+    assert rel_err(full_eval(engine, fx, m), full_eval(oracle, fx, m)) < LOGL_RTOL
+
+
+def test_underflow_needs_rescaling(engine, oracle):
+    # long edges on many taxa: unscaled partials would underflow double precision
+    fx = random_problem(600, 64, 12, missing_frac=0.0, mean_edge=1.5)
+    m = named_model("gtr_g4")
+    lo, le = full_eval(oracle, fx, m), full_eval(engine, fx, m)
+    assert np.isfinite(lo) and lo < -700 * 64 / 64
+    assert rel_err(le, lo) < LOGL_RTOL
+
+
+def test_repeat_calls_and_changed_parameters(engine, oracle):
+    # one instance, many calls: new edge lengths, new model, new topology (schedule cache must follow)
+    fx = random_problem(40, 300, 21)
+    fx2 = random_problem(40, 300, 22)
+    fx2["data"], fx2["counts"] = fx["data"], fx["counts"]
+    m1, m2 = named_model("gtr_g4"), named_model("jc_g4")
+    n, P = fx["data"].shape
+    ie, io = engine.create(n, P, 4), oracle.create(n, P, 4)
+    for api, inst in ((engine, ie), (oracle, io)):
+        api.set_data(inst, fx["data"].astype(np.int32), fx["counts"])
+    rng = np.random.default_rng(5)
+    for it in range(6):
+        f = fx if it % 3 != 2 else fx2
+        mm = m1 if it % 2 == 0 else m2
+        el = f["edge_lengths"] * rng.uniform(0.5, 1.5, size=f["edge_lengths"].size)
+        a = engine.calc_log_likelihood(ie, mm, f["ops"], f["pmatrix_index"], el, int(f["parent"]), 0)
+        b = oracle.calc_log_likelihood(io, mm, f["ops"], f["pmatrix_index"], el, int(f["parent"]), 0)
+        assert rel_err(a, b) < LOGL_RTOL, it
+    engine.finalize(ie)
+    oracle.finalize(io)
+
+
+def test_operation_list_in_any_valid_order(engine, oracle):
+    # the reference emits reverse level-order; any children-first order must give the same answer
+    fx = random_problem(30, 50, 31)
+    m = named_model("gtr_g4")
+    base = full_eval(oracle, fx, m)
+    # postorder by destination number is also children-first (internals are numbered in postorder)
+    fx2 = dict(fx)
+    fx2["ops"] = fx["ops"][np.argsort(fx["ops"][:, 0])]
+    assert rel_err(full_eval(engine, fx2, m), base) < LOGL_RTOL
+
+
+def test_non_forest_operation_list_runs_sequentially(engine, oracle):
+    # a buffer recomputed twice in one list is legal BeagleLib usage; the planner must fall back
+    fx = random_problem(10, 33, 41)
+    m = named_model("gtr_g4")
+    fx2 = dict(fx)
+    fx2["ops"] = np.concatenate([fx["ops"][:3], fx["ops"]])
+    assert rel_err(full_eval(engine, fx2, m), full_eval(oracle, fx2, m)) < LOGL_RTOL
+
+
+def test_error_codes(engine):
+    fx = load_golden("rbcl10")
+    n, P = fx["data"].shape
+    m = named_model("jc")
+    assert engine.beagleFinalizeInstance(12345) == -4
+    assert engine.beagleSetPatternWeights(999, fx["counts"].ctypes.data_as(C.POINTER(C.c_double))) == -4
+    inst = engine.create(n, P, 1)
+    row = fx["data"][0].astype(np.int32)
+    assert engine.beagleSetTipStates(inst, n, row.ctypes.data_as(C.POINTER(C.c_int))) == -5
+    # tips not uploaded yet: partials update must refuse
+    ops = np.ascontiguousarray(fx["ops"], dtype=np.int32)
+    assert engine.beagleUpdatePartials(inst, ops.ctypes.data_as(C.POINTER(C.c_int)), 8, 0) == -5
+    engine.set_data(inst, fx["data"].astype(np.int32), fx["counts"])
+    bad = ops.copy()
+    bad[0, 0] = 500
+    assert engine.beagleUpdatePartials(inst, bad.ctypes.data_as(C.POINTER(C.c_int)), 8, 0) == -5
+    bad = ops.copy()
+    bad[0, 2] = 1            # scale-read is not supported (the reference never uses it)
+    assert engine.beagleUpdatePartials(inst, bad.ctypes.data_as(C.POINTER(C.c_int)), 8, 0) == -7
+    # NaN log-likelihood -> -8 (BEAGLE_ERROR_FLOATING_POINT): negative frequencies make the site likelihood negative
+    m_bad = dict(m)
+    m_bad["freqs"] = np.array([-1.0, -1.0, -1.0, -1.0])
+    with pytest.raises(Exception) as ei:
+        engine.calc_log_likelihood(inst, m_bad, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
+    assert getattr(ei.value, "code", None) == -8
+    # and the instance still works afterwards
+    ll = engine.calc_log_likelihood(inst, m, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
+    assert rel_err(ll, float(fx["lnL_jc"])) < LOGL_RTOL
+    engine.finalize(inst)
+    assert engine.beagleFinalizeInstance(inst) == -4
+    # unsupported shapes
+    assert engine.beagleCreateInstance(4, 2, 4, 20, 10, 1, 5, 1, 3, None, 0, 0, 1 << 1 | 1 << 6, None) == -7   # 20 states
+    assert engine.beagleCreateInstance(4, 2, 4, 4, 10, 1, 5, 9, 3, None, 0, 0, 1 << 1 | 1 << 6, None) == -7    # 9 categories
+
+
+@pytest.mark.parametrize("key,model", [("rbcl10", "gtr_g4"), ("rbcl738", "gtr_g4"), ("rbcl738", "gtr_i_g4"), ("rbcL", "jc")])
+def test_fp32_variant_within_stated_tolerance(engine, key, model):
+    fx = load_golden(key)
+    ll = full_eval(engine, fx, named_model(model), single=True)
+    assert rel_err(ll, float(fx["lnL_" + model])) < LOGL_RTOL_FP32
+
+
+def test_many_instances_coexist(engine):
+    # one Likelihood (instance) per chain, reference src/strom.hpp:249
+    fx = load_golden("rbcl10")
+    res = []
+    insts = []
+    for name in ("jc", "jc_g4", "gtr_g4", "gtr_i_g4"):
+        m = named_model(name)
+        ll, inst = full_eval(engine, fx, m, keep=True)
+        insts.append(inst)
+        res.append((name, ll))
+    assert len(set(insts)) == 4
+    for name, ll in res:
+        assert rel_err(ll, float(fx["lnL_" + name])) < LOGL_RTOL
+    for inst in insts:
+        engine.finalize(inst)
