@@ -74,6 +74,11 @@ STROM_API int sb200GetPartials(int instance, int bufferIndex, double* out);
 STROM_API int sb200GetScaleFactors(int instance, int scaleIndex, double* out);
 STROM_API int sb200GetTransitionMatrix(int instance, int matrixIndex, double* out);
 
+/* CUDA-event timing of the pruning launches, on the stream they are launched on: enable, run
+ * evaluations, then read the accumulated milliseconds and the number of timed calls. */
+STROM_API int sb200SetProfiling(int instance, int enabled);
+STROM_API int sb200PartialsTime(int instance, double* totalMs, long* calls);
+
 /* Number of kernels this instance has launched since creation (bench.py's gpu_launches). */
 STROM_API long sb200LaunchCount(int instance);
 

@@ -86,6 +86,12 @@ struct Engine {
     std::vector<char> tipSet;
     long launches = 0;
     double algBytes = 0, schedBytes = 0;
+    // optional CUDA-event timing of the pruning launches (bench.py's roofline leg)
+    bool profiling = false;
+    cudaEvent_t evP0 = nullptr, evP1 = nullptr;
+    double partialsMsSum = 0;
+    long partialsCalls = 0;
+    bool evPending = false;
 
     size_t realSize() const { return fp32 ? 4 : 8; }
     ParamBlockHeader* hHeader() { return reinterpret_cast<ParamBlockHeader*>(hBlock); }
@@ -112,6 +118,9 @@ struct Engine {
         if (hOut) cudaFreeHost(hOut);
         if (blockCopied) cudaEventDestroy(blockCopied);
         if (schedCopied) cudaEventDestroy(schedCopied);
+        if (evP0) cudaEventDestroy(evP0);
+        if (evP1) cudaEventDestroy(evP1);
+        evP0 = evP1 = nullptr;
         if (ownStream) cudaStreamDestroy(ownStream);
         dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr;
         dBlock = nullptr; dOps = nullptr; dChains = nullptr; dRootSlots = nullptr; dBlockSums = nullptr;
@@ -374,10 +383,32 @@ struct Engine {
         }
     }
 
+    void collectProfile() {
+        if (!evPending) return;
+        float ms = 0.f;
+        CK(cudaEventSynchronize(evP1));
+        CK(cudaEventElapsedTime(&ms, evP0, evP1));
+        partialsMsSum += ms;
+        ++partialsCalls;
+        evPending = false;
+    }
+
     void launchPartials(int cumIdx) {
         lastCumIndex = cumIdx;
+        if (profiling) {
+            collectProfile();
+            if (!evP0) {
+                CK(cudaEventCreate(&evP0));
+                CK(cudaEventCreate(&evP1));
+            }
+            CK(cudaEventRecord(evP0, stream));
+        }
         if (fp32) launchPartialsT<float>(cumIdx);
         else launchPartialsT<double>(cumIdx);
+        if (profiling) {
+            CK(cudaEventRecord(evP1, stream));
+            evPending = true;
+        }
     }
 
     // ---- (c) ---------------------------------------------------------------------------
@@ -844,6 +875,25 @@ extern "C" int sb200GetTransitionMatrix(int instance, int matrixIndex, double* o
         }
         for (int k = 0; k < E.C; ++k)
             for (int e = 0; e < 16; ++e) out[k * 16 + e] = full[static_cast<size_t>(k) * kMatStride + e];
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200SetProfiling(int instance, int enabled) {
+    return withEngine(instance, [&](Engine& E) {
+        E.collectProfile();
+        E.profiling = enabled != 0;
+        E.partialsMsSum = 0;
+        E.partialsCalls = 0;
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200PartialsTime(int instance, double* totalMs, long* calls) {
+    return withEngine(instance, [&](Engine& E) {
+        E.collectProfile();
+        if (totalMs) *totalMs = E.partialsMsSum;
+        if (calls) *calls = E.partialsCalls;
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }
