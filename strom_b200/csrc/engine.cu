@@ -42,6 +42,7 @@ struct Engine {
     int device = 0;
     bool fp32 = false;
     int nTips = 0, nPartials = 0, nCompact = 0, P = 0, nEigen = 0, nMat = 0, C = 0, nScale = 0;
+    int Ppad = 0;                         // pattern axis padded to a multiple of 512 in every buffer
     long long tipStride = 0;
     cudaStream_t ownStream = nullptr, stream = nullptr;
 
@@ -144,20 +145,21 @@ struct Engine {
         stream = ownStream;
         CK(cudaEventCreateWithFlags(&blockCopied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
-        tipStride = (static_cast<long long>(P) + 127) & ~127LL;
+        Ppad = (P + 511) & ~511;         // = patterns per block of the widest kernel (C=1, R=2)
+        tipStride = Ppad;
         if (nTips > 0) {
             CK(cudaMalloc(&dTips, static_cast<size_t>(nTips) * tipStride));
             CK(cudaMemsetAsync(dTips, 4, static_cast<size_t>(nTips) * tipStride, stream));
         }
         tipSet.assign(nTips, 0);
-        const size_t bufElems = static_cast<size_t>(P) * C * 4;
+        const size_t bufElems = static_cast<size_t>(Ppad) * C * 4;
         if (nPartials > 0) CK(cudaMalloc(&dPartials, bufElems * nPartials * realSize()));
         if (nMat > 0) {
             CK(cudaMalloc(&dMats, static_cast<size_t>(nMat) * C * kMatStride * realSize()));
             CK(cudaMemsetAsync(dMats, 0, static_cast<size_t>(nMat) * C * kMatStride * realSize(), stream));
         }
-        CK(cudaMalloc(&dPatWeights, sizeof(double) * P));
-        CK(cudaMemsetAsync(dPatWeights, 0, sizeof(double) * P, stream));
+        CK(cudaMalloc(&dPatWeights, sizeof(double) * Ppad));
+        CK(cudaMemsetAsync(dPatWeights, 0, sizeof(double) * Ppad, stream));
         dScale.assign(nScale, nullptr);
         scaleZeroPending.assign(nScale, 0);
         layoutBlock(nMat > 0 ? nMat : 1);
@@ -166,7 +168,7 @@ struct Engine {
         CK(cudaMalloc(&dBlock, blockBytes));
         for (int k = 0; k < kMaxCategories; ++k) hHeader()->rates[k] = 1.0;
         const int perBlock = C <= 2 || C == 4 || C == 8 ? 256 / C : 128;
-        rootBlocks = (P + perBlock - 1) / perBlock;
+        rootBlocks = Ppad / perBlock;
         CK(cudaMalloc(&dBlockSums, sizeof(double) * rootBlocks));
         CK(cudaMalloc(&dTicket, sizeof(unsigned int)));
         CK(cudaMemsetAsync(dTicket, 0, sizeof(unsigned int), stream));
@@ -184,8 +186,8 @@ struct Engine {
 
     double* scaleBuffer(int idx) {
         if (!dScale[idx]) {
-            CK(cudaMalloc(&dScale[idx], sizeof(double) * P));
-            CK(cudaMemsetAsync(dScale[idx], 0, sizeof(double) * P, stream));
+            CK(cudaMalloc(&dScale[idx], sizeof(double) * Ppad));
+            CK(cudaMemsetAsync(dScale[idx], 0, sizeof(double) * Ppad, stream));
             scaleZeroPending[idx] = 0;
         }
         return dScale[idx];
@@ -194,7 +196,7 @@ struct Engine {
     void materializeZero(int idx) {
         double* b = scaleBuffer(idx);
         if (scaleZeroPending[idx]) {
-            CK(cudaMemsetAsync(b, 0, sizeof(double) * P, stream));
+            CK(cudaMemsetAsync(b, 0, sizeof(double) * Ppad, stream));
             scaleZeroPending[idx] = 0;
         }
     }
@@ -299,7 +301,7 @@ struct Engine {
         if (rtB) CK(cudaMemcpyAsync(dRootSlots, st + opsB + chB, rtB, cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(schedCopied, stream));
         schedInFlight = true;
-        const size_t needSlots = static_cast<size_t>(sched.slotCount) * P;
+        const size_t needSlots = static_cast<size_t>(sched.slotCount) * Ppad;
         if (needSlots > slotCapacity) {
             CK(cudaStreamSynchronize(stream));
             cudaFree(dSlots);
@@ -321,12 +323,12 @@ struct Engine {
     template <typename real, int CC, int R>
     void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
         constexpr int perBlock = (kPruneThreads / CC) * R;
-        dim3 grid((P + perBlock - 1) / perBlock, L.chainCount);
+        dim3 grid(Ppad / perBlock, L.chainCount);
         prune_chains_kernel<real, CC, R><<<grid, kPruneThreads, 0, stream>>>(a, L.chainStart, cumMode);
     }
     template <typename real, int CC>
     void launchLevelGeneric(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        dim3 grid((P + 127) / 128, L.chainCount);
+        dim3 grid(Ppad / 128, L.chainCount);
         prune_chains_generic_kernel<real, CC><<<grid, 128, 0, stream>>>(a, L.chainStart, cumMode);
     }
 
@@ -356,6 +358,7 @@ struct Engine {
         a.chains = dChains;
         a.tipStride = tipStride;
         a.P = P;
+        a.Ppad = Ppad;
         a.nTips = nTips;
         const bool big = static_cast<long long>(P) * C >= (1LL << 18);
         for (const Level& L : sched.levels) {
@@ -377,7 +380,7 @@ struct Engine {
             const int nr = static_cast<int>(sched.rootSlots.size());
             int mode = 0;
             if (scaleZeroPending[cumIdx]) { mode = 1; scaleZeroPending[cumIdx] = 0; }
-            fold_roots_kernel<<<(P + 255) / 256, 256, 0, stream>>>(dSlots, dRootSlots, nr, cum, P, mode);
+            fold_roots_kernel<<<(Ppad + 255) / 256, 256, 0, stream>>>(dSlots, dRootSlots, nr, cum, Ppad, mode);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -431,6 +434,7 @@ struct Engine {
         a.out = out;
         a.tipStride = tipStride;
         a.P = P;
+        a.Ppad = Ppad;
         a.nTips = nTips;
         a.parent = parent;
         a.child = child;
@@ -836,13 +840,14 @@ extern "C" int sb200GetPartials(int instance, int bufferIndex, double* out) {
     return withEngine(instance, [&](Engine& E) {
         if (bufferIndex < E.nTips || bufferIndex >= E.nTips + E.nPartials) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
         const size_t n = static_cast<size_t>(E.P) * E.C * 4;
+        const size_t stride = static_cast<size_t>(E.Ppad) * E.C * 4;
         CK(cudaStreamSynchronize(E.stream));
         if (E.fp32) {
             std::vector<float> tmp(n);
-            CK(cudaMemcpy(tmp.data(), static_cast<float*>(E.dPartials) + n * (bufferIndex - E.nTips), n * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(tmp.data(), static_cast<float*>(E.dPartials) + stride * (bufferIndex - E.nTips), n * 4, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < n; ++i) out[i] = tmp[i];
         } else {
-            CK(cudaMemcpy(out, static_cast<double*>(E.dPartials) + n * (bufferIndex - E.nTips), n * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(out, static_cast<double*>(E.dPartials) + stride * (bufferIndex - E.nTips), n * 8, cudaMemcpyDeviceToHost));
         }
         return static_cast<int>(BEAGLE_SUCCESS);
     });
@@ -874,7 +879,7 @@ extern "C" int sb200GetTransitionMatrix(int instance, int matrixIndex, double* o
             CK(cudaMemcpy(full.data(), static_cast<double*>(E.dMats) + n * matrixIndex, n * 8, cudaMemcpyDeviceToHost));
         }
         for (int k = 0; k < E.C; ++k)
-            for (int e = 0; e < 16; ++e) out[k * 16 + e] = full[static_cast<size_t>(k) * kMatStride + e];
+            for (int e = 0; e < 16; ++e) out[k * 16 + e] = full[rmIndex(E.C, k, e)];
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }

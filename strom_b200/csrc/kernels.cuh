@@ -7,10 +7,14 @@
 //   (c) root_loglik_kernel          : BeagleLib beagleCalculateEdgeLogLikelihoods
 //                                     (reference call site src/likelihood.hpp:418-447)
 //
-// HBM layout: partials [buffer][pattern][category][state] (one pattern x category = 4 reals =
-// one 256-bit load for FP64), tips [tip][pattern] 1-byte codes 0..4, matrices
-// [matrix][category][36] = 16 row-major entries + a 5x4 "tip table" T[s][i] = P[i][s] whose row
-// s=4 is all ones (the missing state), log-scalers [slot][pattern] FP64.
+// HBM layout (pattern axis padded to Ppad = 512-multiple, so no kernel needs tail predicates):
+//   partials [buffer][Ppad][category][state]  one pattern x category = 4 reals = one 256-bit load (FP64)
+//   tips     [tip][Ppad]                      1-byte codes 0..4 (4 = missing; padding is 4)
+//   matrices [matrix][36*C]                   already in the shared-memory image the pruning kernel wants:
+//              16*C reals  row-major P_k[i][j], interleaved over categories as [(i*4+j)/2][k][(i*4+j)%2]
+//                          (the C category lanes of a warp read C consecutive 16-byte words: no bank conflict)
+//              20*C reals  tip table T[k][s][i] = P_k[i][s], row s=4 all ones (the missing state)
+//   log-scalers [slot][Ppad] FP64 (cumulative buffers and per-chain subtree sums)
 //
 // The work is an HBM-bound 4x4 matrix-vector product (about 0.6 flop/byte): no tensor cores.
 #pragma once
@@ -44,6 +48,7 @@ struct PruneArgs {
     const DevChain* chains;
     long long tipStride;
     int P;
+    int Ppad;
     int nTips;
 };
 
@@ -61,6 +66,7 @@ struct RootArgs {
     double* out;
     long long tipStride;
     int P;
+    int Ppad;
     int nTips;
     int parent;                      // buffer index
     int child;                       // buffer index (tip or partials)
@@ -90,6 +96,19 @@ __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
 template <typename real> __device__ __forceinline__ real rmax(real a, real b) { return a > b ? a : b; }
 
 // ------------------------------------------------------------------------------------------
+// matrix image indexing (see the layout note at the top of this file)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ constexpr int rmIndex(int C, int k, int e) { return (((e >> 1) * C + k) << 1) + (e & 1); }
+__host__ __device__ __forceinline__ constexpr int tipIndex(int C, int k, int s, int i) { return 16 * C + (k * 5 + s) * 4 + i; }
+
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // (a) transition matrices: one thread per (edge, category, matrix entry)
 // ------------------------------------------------------------------------------------------
 template <typename real>
@@ -108,194 +127,192 @@ transition_matrices_kernel(const DevModel* __restrict__ model, const double* __r
 #pragma unroll
     for (int x = 0; x < 4; ++x) sum += c[x] * exp(model->evals[x] * t);
     const real v = static_cast<real>(sum > 0.0 ? sum : 0.0);
-    real* base = mats + (static_cast<size_t>(matrixIndex[u]) * C + k) * kMatStride;
-    base[e] = v;                         // row-major P[i][j]
-    base[16 + j * 4 + i] = v;            // tip table T[s=j][i]
-    if (j == 0) base[32 + i] = real(1);  // T[4][i]: missing state
+    real* base = mats + static_cast<size_t>(matrixIndex[u]) * C * kMatStride;
+    base[rmIndex(C, k, e)] = v;                            // P_k[i][j]
+    base[tipIndex(C, k, j, i)] = v;                        // T[k][s=j][i]
+    if (j == 0) base[tipIndex(C, k, 4, i)] = real(1);      // missing state
 }
 
 // ------------------------------------------------------------------------------------------
 // (b) pruning, chain-fused with per-node rescaling.
 //     C in {1,2,4,8}: one thread per (pattern, category), R patterns per thread.
+//     Per step a thread reads its category's two 4x4 matrices from shared memory (staged by
+//     cp.async one step ahead), the sibling's 4 partials (256-bit load, requested one step
+//     ahead) or 1-byte tip state, keeps the running partials in registers, rescales with a
+//     C-lane shuffle maximum, and writes the 4 new partials with one 256-bit store.
 // ------------------------------------------------------------------------------------------
-template <int C> __device__ __forceinline__ int rmIndex(int e, int k) { return (((e >> 1) * C + k) << 1) + (e & 1); }
-
 template <typename real, int C>
 __device__ __forceinline__ void factorPartial(const real* __restrict__ sm, int k, const real (&v)[4], real (&F)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        real s = sm[rmIndex<C>(i * 4 + 0, k)] * v[0];
-        s += sm[rmIndex<C>(i * 4 + 1, k)] * v[1];
-        s += sm[rmIndex<C>(i * 4 + 2, k)] * v[2];
-        s += sm[rmIndex<C>(i * 4 + 3, k)] * v[3];
+        real s = sm[rmIndex(C, k, i * 4 + 0)] * v[0];
+        s += sm[rmIndex(C, k, i * 4 + 1)] * v[1];
+        s += sm[rmIndex(C, k, i * 4 + 2)] * v[2];
+        s += sm[rmIndex(C, k, i * 4 + 3)] * v[3];
         F[i] = s;
     }
 }
 
 template <typename real, int C>
 __device__ __forceinline__ void factorTip(const real* __restrict__ sm, int k, int state, real (&F)[4]) {
-    const real* T = sm + 16 * C + (k * 5 + state) * 4;
+    const real* T = sm + tipIndex(C, k, state, 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) F[i] = T[i];
 }
 
+constexpr int kOpSegment = 32;      // operations of a chain staged in shared memory at a time
+
 template <typename real, int C, int R>
-__global__ void __launch_bounds__(kPruneThreads)
+__global__ void __launch_bounds__(kPruneThreads, R == 1 ? 3 : 2)
 prune_chains_kernel(const PruneArgs<real> A, const int chainBase, const int cumMode) {
     constexpr int G = kPruneThreads / C;                 // patterns per pass
-    constexpr int MSZ = kMatStride * C;                  // reals per operand
-    constexpr int NST = (2 * MSZ + kPruneThreads - 1) / kPruneThreads;
+    constexpr int MSZ = kMatStride * C;                  // reals per operand image
+    constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
+    constexpr int NCH = MSZ / CHUNK;                     // 16-byte chunks per operand image
     __shared__ __align__(16) real sm[2][2 * MSZ];
+    __shared__ __align__(16) DevOp sops[kOpSegment];
 
     const int tid = threadIdx.x;
     const int k = tid % C, g = tid / C;
     const DevChain ch = A.chains[chainBase + blockIdx.y];
+    const int p0 = blockIdx.x * (G * R) + g;             // r-th pattern of this thread: p0 + r*G (< Ppad)
+    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
+    real* const pmine = A.partials + (static_cast<size_t>(p0) * C + k) * 4;
+    const uint8_t* const tmine = A.tips + p0;
+    double* const smine = A.slots + p0;
 
-    int p[R], pc[R];
+    auto stage = [&](int buf, int ma, int mb) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        p[r] = (blockIdx.x * R + r) * G + g;
-        pc[r] = p[r] < A.P ? p[r] : A.P - 1;
-    }
-    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
-
-    auto stageLoad = [&](const DevOp& op, real (&st)[NST]) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) {
-            const int q = tid + s * kPruneThreads;
-            if (q < 2 * MSZ) {
-                const int o = q / MSZ, w = q - o * MSZ;
-                st[s] = A.mats[static_cast<size_t>(o ? op.mb : op.ma) * MSZ + w];
-            }
+        for (int c = tid; c < 2 * NCH; c += kPruneThreads) {
+            const int o = c >= NCH ? 1 : 0, cc = c - o * NCH;
+            cpAsync16(&sm[buf][o * MSZ + cc * CHUNK], A.mats + static_cast<size_t>(o ? mb : ma) * MSZ + cc * CHUNK);
         }
-    };
-    auto stageStore = [&](real* dst, const real (&st)[NST]) {
-#pragma unroll
-        for (int s = 0; s < NST; ++s) {
-            const int q = tid + s * kPruneThreads;
-            if (q < 2 * MSZ) {
-                const int o = q / MSZ, w = q - o * MSZ;
-                const int kk = w / kMatStride, e = w - kk * kMatStride;
-                const int d = e < 16 ? rmIndex<C>(e, kk) : 16 * C + kk * 20 + (e - 16);
-                dst[o * MSZ + d] = st[s];
-            }
-        }
+        cpAsyncCommit();
     };
     auto fetch = [&](int src, real (&v)[R][4], int (&state)[R]) {
         if (src < A.nTips) {
+            const uint8_t* t = tmine + static_cast<size_t>(src) * A.tipStride;
 #pragma unroll
-            for (int r = 0; r < R; ++r) state[r] = A.tips[static_cast<size_t>(src) * A.tipStride + pc[r]];
+            for (int r = 0; r < R; ++r) state[r] = t[r * G];
         } else {
-            const real* base = A.partials + static_cast<size_t>(src - A.nTips) * bufStride;
+            const real* base = pmine + static_cast<size_t>(src - A.nTips) * bufStride;
 #pragma unroll
-            for (int r = 0; r < R; ++r) ld4(base + (static_cast<size_t>(pc[r]) * C + k) * 4, v[r]);
+            for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
         }
     };
 
-    DevOp op = A.ops[ch.opStart];
     real X[R][4], Y[R][4];
     int sX[R], sY[R];
     double acc[R], prod[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; sX[r] = 0; sY[r] = 0; }
-    {
-        real st[NST];
-        stageLoad(op, st);
-        fetch(op.a, X, sX);
-        fetch(op.b, Y, sY);
-        if (op.sa >= 0) {
+
+    for (int seg0 = 0; seg0 < ch.opCount; seg0 += kOpSegment) {
+        const int nseg = min(kOpSegment, ch.opCount - seg0);
+        if (seg0 > 0) __syncthreads();
+        if (tid < nseg * 2)
+            reinterpret_cast<int4*>(sops)[tid] = reinterpret_cast<const int4*>(A.ops + ch.opStart + seg0)[tid];
+        __syncthreads();
+
+        DevOp op = sops[0];
+        stage(0, op.ma, op.mb);
+        if (seg0 == 0) {
+            fetch(op.a, X, sX);
+            if (op.sa >= 0) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] += A.slots[static_cast<size_t>(op.sa) * A.P + pc[r]];
+                for (int r = 0; r < R; ++r) acc[r] += smine[static_cast<size_t>(op.sa) * A.Ppad + r * G];
+            }
         }
+        fetch(op.b, Y, sY);
         if (op.sb >= 0) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] += A.slots[static_cast<size_t>(op.sb) * A.P + pc[r]];
+            for (int r = 0; r < R; ++r) acc[r] += smine[static_cast<size_t>(op.sb) * A.Ppad + r * G];
         }
-        stageStore(sm[0], st);
-    }
-    __syncthreads();
+        cpAsyncWaitAll();
+        __syncthreads();
 
-    for (int j = 0; j < ch.opCount; ++j) {
-        const bool more = j + 1 < ch.opCount;
-        DevOp nx = op;
-        real stn[NST];
-        real Yn[R][4];
-        int sYn[R];
-        double accn[R];
+        for (int j = 0; j < nseg; ++j) {
+            const bool more = j + 1 < nseg;
+            DevOp nx = op;
+            real Yn[R][4];
+            int sYn[R];
+            double accn[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { accn[r] = 0.0; sYn[r] = 0; }
-        if (more) {
-            // software pipeline: next operation's matrices and sibling are requested before
-            // this operation's arithmetic so the HBM/L2 latency hides behind it
-            nx = A.ops[ch.opStart + j + 1];
-            stageLoad(nx, stn);
-            fetch(nx.b, Yn, sYn);
-            if (nx.sb >= 0) {
+            for (int r = 0; r < R; ++r) { accn[r] = 0.0; sYn[r] = 0; }
+            if (more) {
+                // software pipeline: the next operation's matrices (cp.async) and sibling partials are
+                // requested before this operation's arithmetic so their latency hides behind it
+                nx = sops[j + 1];
+                stage((j + 1) & 1, nx.ma, nx.mb);
+                fetch(nx.b, Yn, sYn);
+                if (nx.sb >= 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) accn[r] = A.slots[static_cast<size_t>(nx.sb) * A.P + pc[r]];
-            }
-        }
-
-        const real* sa = sm[j & 1];
-        const real* sb = sa + MSZ;
-        const bool aTip = op.a >= 0 && op.a < A.nTips;
-        const bool bTip = op.b < A.nTips;
-        real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            real FA[4], FB[4], D[4];
-            if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
-            else factorPartial<real, C>(sa, k, X[r], FA);
-            if (bTip) factorTip<real, C>(sb, k, sY[r], FB);
-            else factorPartial<real, C>(sb, k, Y[r], FB);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) D[i] = FA[i] * FB[i];
-            if (op.flags & OP_RESCALE) {
-                real m = rmax(rmax(D[0], D[1]), rmax(D[2], D[3]));
-#pragma unroll
-                for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-                if (m == real(0)) m = real(1);
-                const real inv = real(1) / m;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) D[i] *= inv;
-                // deferred log: keep the product of maxima, fold into the sum before it can underflow
-                const double md = static_cast<double>(m);
-                if (md < 1e-100 || prod[r] < 1e-100) {
-                    acc[r] += log(prod[r]) + log(md);
-                    prod[r] = 1.0;
-                } else {
-                    prod[r] *= md;
+                    for (int r = 0; r < R; ++r) accn[r] = smine[static_cast<size_t>(nx.sb) * A.Ppad + r * G];
                 }
             }
-            if (p[r] < A.P) st4(dest + (static_cast<size_t>(p[r]) * C + k) * 4, D);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) X[r][i] = D[i];
-        }
 
-        if (more) {
-            stageStore(sm[(j + 1) & 1], stn);
+            const real* sa = sm[j & 1];
+            const real* sb = sa + MSZ;
+            const bool aTip = op.a >= 0 && op.a < A.nTips;
+            const bool bTip = op.b < A.nTips;
+            real* dest = pmine + static_cast<size_t>(op.dest) * bufStride;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+                real FA[4], FB[4], D[4];
+                if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
+                else factorPartial<real, C>(sa, k, X[r], FA);
+                if (bTip) factorTip<real, C>(sb, k, sY[r], FB);
+                else factorPartial<real, C>(sb, k, Y[r], FB);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) Y[r][i] = Yn[r][i];
-                sY[r] = sYn[r];
-                acc[r] += accn[r];
+                for (int i = 0; i < 4; ++i) D[i] = FA[i] * FB[i];
+                if (op.flags & OP_RESCALE) {
+                    real m = rmax(rmax(D[0], D[1]), rmax(D[2], D[3]));
+#pragma unroll
+                    for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+                    if (m == real(0)) m = real(1);
+                    const real inv = real(1) / m;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) D[i] *= inv;
+                    // deferred log: keep the product of the maxima and fold it into the log sum only
+                    // before it could underflow (also catches a denormal maximum)
+                    const double md = static_cast<double>(m);
+                    const double t = prod[r] * md;
+                    if (t < 1e-200) {
+                        acc[r] += log(prod[r]) + log(md);
+                        prod[r] = 1.0;
+                    } else {
+                        prod[r] = t;
+                    }
+                }
+                st4(dest + r * (G * C * 4), D);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) X[r][i] = D[i];
             }
-            op = nx;
+
+            if (more) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) Y[r][i] = Yn[r][i];
+                    sY[r] = sYn[r];
+                    acc[r] += accn[r];
+                }
+                op = nx;
+                cpAsyncWaitAll();
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     if (k == 0 && (ch.sOut >= 0 || ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr))) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (p[r] < A.P) {
-                const double total = acc[r] + log(prod[r]);
-                if (ch.sOut >= 0) A.slots[static_cast<size_t>(ch.sOut) * A.P + p[r]] = total;
-                if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
-                    if (cumMode) A.cum[p[r]] = total;
-                    else A.cum[p[r]] += total;
-                }
+            const double total = acc[r] + log(prod[r]);
+            if (ch.sOut >= 0) smine[static_cast<size_t>(ch.sOut) * A.Ppad + r * G] = total;
+            if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
+                double* c = A.cum + p0 + r * G;
+                if (cumMode) *c = total;
+                else *c += total;
             }
         }
     }
@@ -309,9 +326,8 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int chainBase, const 
     __shared__ __align__(16) real sm[2 * MSZ];
     const int tid = threadIdx.x;
     const DevChain ch = A.chains[chainBase + blockIdx.y];
-    const int p = blockIdx.x * 128 + tid;
-    const int pc = p < A.P ? p : A.P - 1;
-    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
+    const int p = blockIdx.x * 128 + tid;                 // < Ppad
+    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
     real X[C][4];
     double acc = 0.0, prod = 1.0;
 
@@ -323,37 +339,39 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int chainBase, const 
             sm[q] = A.mats[static_cast<size_t>(o ? op.mb : op.ma) * MSZ + w];
         }
         __syncthreads();
-        if (op.sa >= 0) acc += A.slots[static_cast<size_t>(op.sa) * A.P + pc];
-        if (op.sb >= 0) acc += A.slots[static_cast<size_t>(op.sb) * A.P + pc];
+        if (op.sa >= 0) acc += A.slots[static_cast<size_t>(op.sa) * A.Ppad + p];
+        if (op.sb >= 0) acc += A.slots[static_cast<size_t>(op.sb) * A.Ppad + p];
         const bool aTip = op.a >= 0 && op.a < A.nTips;
         const bool bTip = op.b < A.nTips;
-        const int sA = aTip ? A.tips[static_cast<size_t>(op.a) * A.tipStride + pc] : 0;
-        const int sB = bTip ? A.tips[static_cast<size_t>(op.b) * A.tipStride + pc] : 0;
+        const int sA = aTip ? A.tips[static_cast<size_t>(op.a) * A.tipStride + p] : 0;
+        const int sB = bTip ? A.tips[static_cast<size_t>(op.b) * A.tipStride + p] : 0;
         const real* pa = (op.a >= A.nTips) ? A.partials + static_cast<size_t>(op.a - A.nTips) * bufStride : nullptr;
         const real* pb = bTip ? nullptr : A.partials + static_cast<size_t>(op.b - A.nTips) * bufStride;
         real m = real(0);
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) {
-            const real* ma = sm + kk * kMatStride;
-            const real* mb = sm + MSZ + kk * kMatStride;
+            const real* ma = sm;
+            const real* mb = sm + MSZ;
             real FA[4], FB[4], Yv[4];
             if (aTip) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) FA[i] = ma[16 + sA * 4 + i];
+                for (int i = 0; i < 4; ++i) FA[i] = ma[tipIndex(C, kk, sA, i)];
             } else {
-                if (pa) ld4(pa + (static_cast<size_t>(pc) * C + kk) * 4, X[kk]);
+                if (pa) ld4(pa + (static_cast<size_t>(p) * C + kk) * 4, X[kk]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    FA[i] = ma[i * 4] * X[kk][0] + ma[i * 4 + 1] * X[kk][1] + ma[i * 4 + 2] * X[kk][2] + ma[i * 4 + 3] * X[kk][3];
+                    FA[i] = ma[rmIndex(C, kk, i * 4)] * X[kk][0] + ma[rmIndex(C, kk, i * 4 + 1)] * X[kk][1] +
+                            ma[rmIndex(C, kk, i * 4 + 2)] * X[kk][2] + ma[rmIndex(C, kk, i * 4 + 3)] * X[kk][3];
             }
             if (bTip) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) FB[i] = mb[16 + sB * 4 + i];
+                for (int i = 0; i < 4; ++i) FB[i] = mb[tipIndex(C, kk, sB, i)];
             } else {
-                ld4(pb + (static_cast<size_t>(pc) * C + kk) * 4, Yv);
+                ld4(pb + (static_cast<size_t>(p) * C + kk) * 4, Yv);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    FB[i] = mb[i * 4] * Yv[0] + mb[i * 4 + 1] * Yv[1] + mb[i * 4 + 2] * Yv[2] + mb[i * 4 + 3] * Yv[3];
+                    FB[i] = mb[rmIndex(C, kk, i * 4)] * Yv[0] + mb[rmIndex(C, kk, i * 4 + 1)] * Yv[1] +
+                            mb[rmIndex(C, kk, i * 4 + 2)] * Yv[2] + mb[rmIndex(C, kk, i * 4 + 3)] * Yv[3];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -369,36 +387,33 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int chainBase, const 
 #pragma unroll
                 for (int i = 0; i < 4; ++i) X[kk][i] *= inv;
             const double md = static_cast<double>(m);
-            if (md < 1e-100 || prod < 1e-100) {
+            const double t = prod * md;
+            if (t < 1e-200) {
                 acc += log(prod) + log(md);
                 prod = 1.0;
             } else {
-                prod *= md;
+                prod = t;
             }
         }
-        if (p < A.P) {
-            real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride + static_cast<size_t>(p) * C * 4;
+        real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride + static_cast<size_t>(p) * C * 4;
 #pragma unroll
-            for (int kk = 0; kk < C; ++kk) st4(dest + kk * 4, X[kk]);
-        }
+        for (int kk = 0; kk < C; ++kk) st4(dest + kk * 4, X[kk]);
     }
-    if (p < A.P) {
-        const double total = acc + log(prod);
-        if (ch.sOut >= 0) A.slots[static_cast<size_t>(ch.sOut) * A.P + p] = total;
-        if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
-            if (cumMode) A.cum[p] = total;
-            else A.cum[p] += total;
-        }
+    const double total = acc + log(prod);
+    if (ch.sOut >= 0) A.slots[static_cast<size_t>(ch.sOut) * A.Ppad + p] = total;
+    if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
+        if (cumMode) A.cum[p] = total;
+        else A.cum[p] += total;
     }
 }
 
 // Folds the subtree sums of several forest roots into the cumulative buffer, in list order.
 __global__ void fold_roots_kernel(const double* __restrict__ slots, const int* __restrict__ rootSlots, int nRoots,
-                                  double* __restrict__ cum, int P, int cumMode) {
+                                  double* __restrict__ cum, int Ppad, int cumMode) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+    if (p >= Ppad) return;
     double s = cumMode ? 0.0 : cum[p];
-    for (int r = 0; r < nRoots; ++r) s += slots[static_cast<size_t>(rootSlots[r]) * P + p];
+    for (int r = 0; r < nRoots; ++r) s += slots[static_cast<size_t>(rootSlots[r]) * Ppad + p];
     cum[p] = s;
 }
 
@@ -443,38 +458,45 @@ __device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums
     }
 }
 
+// Shared-memory tables of the root edge: W[k][s][i] = pi_i * w_k * P_k[i][s] (tip child),
+// M[k][i][j] = P_k[i][j] and fw[k][i] = pi_i * w_k (partials child).
+template <typename real, int C, int THREADS>
+__device__ __forceinline__ void loadRootTables(const RootArgs<real>& A, double* W, double* M, double* fw) {
+    const int tid = threadIdx.x;
+    const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
+    for (int q = tid; q < C * 20; q += THREADS) {
+        const int kk = q / 20, e = q - kk * 20, s = e >> 2, i = e & 3;
+        W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[tipIndex(C, kk, s, i)]);
+    }
+    for (int q = tid; q < C * 16; q += THREADS) M[q] = static_cast<double>(mat[rmIndex(C, q >> 4, q & 15)]);
+    for (int q = tid; q < C * 4; q += THREADS) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
+    __syncthreads();
+}
+
 template <typename real, int C>
 __global__ void __launch_bounds__(256)
 root_loglik_kernel(const RootArgs<real> A) {
     constexpr int G = 256 / C;
-    __shared__ double W[C * 20];          // tip child: W[k][s][i] = pi_i * w_k * P_k[i][s]
-    __shared__ double M[C * 16];          // partials child: row-major P_k
-    __shared__ double fw[C * 4];          // pi_i * w_k
+    __shared__ double W[C * 20];
+    __shared__ double M[C * 16];
+    __shared__ double fw[C * 4];
     const int tid = threadIdx.x, k = tid % C, g = tid / C;
     const bool childTip = A.child < A.nTips;
-    const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
-    for (int q = tid; q < C * 20; q += 256) {
-        const int kk = q / 20, e = q - kk * 20, i = e & 3;
-        W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[kk * kMatStride + 16 + e]);
-    }
-    for (int q = tid; q < C * 16; q += 256) M[q] = static_cast<double>(mat[(q >> 4) * kMatStride + (q & 15)]);
-    for (int q = tid; q < C * 4; q += 256) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
-    __syncthreads();
+    loadRootTables<real, C, 256>(A, W, M, fw);
 
-    const int p = blockIdx.x * G + g;
-    const int pc = p < A.P ? p : A.P - 1;
-    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
+    const int p = blockIdx.x * G + g;                     // < Ppad
+    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
     real par[4];
-    ld4(A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + (static_cast<size_t>(pc) * C + k) * 4, par);
+    ld4(A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + (static_cast<size_t>(p) * C + k) * 4, par);
     double term = 0.0;
     if (childTip) {
-        const int s = A.tips[static_cast<size_t>(A.child) * A.tipStride + pc];
+        const int s = A.tips[static_cast<size_t>(A.child) * A.tipStride + p];
         const double* w = W + (k * 5 + s) * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) term += static_cast<double>(par[i]) * w[i];
     } else {
         real chv[4];
-        ld4(A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + (static_cast<size_t>(pc) * C + k) * 4, chv);
+        ld4(A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + (static_cast<size_t>(p) * C + k) * 4, chv);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             double sj = 0.0;
@@ -502,21 +524,13 @@ root_loglik_generic_kernel(const RootArgs<real> A) {
     __shared__ double fw[C * 4];
     const int tid = threadIdx.x;
     const bool childTip = A.child < A.nTips;
-    const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
-    for (int q = tid; q < C * 20; q += 128) {
-        const int kk = q / 20, e = q - kk * 20, i = e & 3;
-        W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[kk * kMatStride + 16 + e]);
-    }
-    for (int q = tid; q < C * 16; q += 128) M[q] = static_cast<double>(mat[(q >> 4) * kMatStride + (q & 15)]);
-    for (int q = tid; q < C * 4; q += 128) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
-    __syncthreads();
-    const int p = blockIdx.x * 128 + tid;
-    const int pc = p < A.P ? p : A.P - 1;
-    const size_t bufStride = static_cast<size_t>(A.P) * C * 4;
-    const real* pp = A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + static_cast<size_t>(pc) * C * 4;
-    const int s = childTip ? A.tips[static_cast<size_t>(A.child) * A.tipStride + pc] : 0;
+    loadRootTables<real, C, 128>(A, W, M, fw);
+    const int p = blockIdx.x * 128 + tid;                 // < Ppad
+    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
+    const real* pp = A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + static_cast<size_t>(p) * C * 4;
+    const int s = childTip ? A.tips[static_cast<size_t>(A.child) * A.tipStride + p] : 0;
     const real* cp = childTip ? nullptr
-                              : A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + static_cast<size_t>(pc) * C * 4;
+                              : A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + static_cast<size_t>(p) * C * 4;
     double site = 0.0;
 #pragma unroll
     for (int kk = 0; kk < C; ++kk) {
