@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ENGINE_LIB = os.path.join(_HERE, "csrc", "libstrom_b200.so")
+ENGINE_LIB = os.environ.get("STROM_B200_LIB") or os.path.join(_HERE, "csrc", "libstrom_b200.so")
 
 BEAGLE_FLAG_PRECISION_SINGLE = 1 << 0
 BEAGLE_FLAG_PRECISION_DOUBLE = 1 << 1

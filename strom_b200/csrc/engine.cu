@@ -8,8 +8,10 @@
 // Model::setBeagle* (reference src/model.hpp:315-354).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -68,9 +70,9 @@ struct Engine {
     bool schedValid = false;
     std::vector<BeagleOperation> schedOps;
     DevOp* dOps = nullptr;
-    DevChain* dChains = nullptr;
+    Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
-    size_t opsCap = 0, chainsCap = 0, rootCap = 0;
+    size_t opsCap = 0, groupsCap = 0, rootCap = 0;
     void* hSchedStage = nullptr;          // pinned staging for schedule uploads
     size_t schedStageCap = 0;
     cudaEvent_t schedCopied = nullptr;
@@ -112,7 +114,7 @@ struct Engine {
         cudaFree(dTips); cudaFree(dPartials); cudaFree(dMats); cudaFree(dPatWeights);
         for (double* p : dScale) cudaFree(p);
         dScale.clear();
-        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dChains); cudaFree(dRootSlots);
+        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dGroups); cudaFree(dRootSlots);
         cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut);
         if (hBlock) cudaFreeHost(hBlock);
         if (hSchedStage) cudaFreeHost(hSchedStage);
@@ -124,7 +126,7 @@ struct Engine {
         evP0 = evP1 = nullptr;
         if (ownStream) cudaStreamDestroy(ownStream);
         dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr;
-        dBlock = nullptr; dOps = nullptr; dChains = nullptr; dRootSlots = nullptr; dBlockSums = nullptr;
+        dBlock = nullptr; dOps = nullptr; dGroups = nullptr; dRootSlots = nullptr; dBlockSums = nullptr;
         dTicket = nullptr; dOut = nullptr; hBlock = nullptr; hSchedStage = nullptr; hOut = nullptr;
         blockCopied = nullptr; schedCopied = nullptr; ownStream = nullptr; stream = nullptr;
     }
@@ -254,13 +256,30 @@ struct Engine {
         CK(cudaMalloc(&ptr, sizeof(T) * cap));
     }
 
+    bool bigTiles() const {
+        bool big = static_cast<long long>(P) * C >= (1LL << 18);
+        if (const char* f = std::getenv("SB200_FORCE_R")) big = (f[0] == '2');   // tuning aid
+        return big;
+    }
+    int patternsPerBlock() const {
+        if (C == 1 || C == 2 || C == 4 || C == 8) return (kPruneThreads / C) * (bigTiles() ? 2 : 1);
+        return 128;
+    }
+    // Enough (tile x group) blocks per launch to fill the 148 SMs several times over, as few groups as
+    // possible otherwise (a group is a serial stream; fewer groups = less per-block set-up).
+    int groupsPerLevel() const {
+        const int tiles = Ppad / patternsPerBlock();
+        const int wantBlocks = 148 * 6;
+        return std::max(1, (wantBlocks + tiles - 1) / tiles);
+    }
+
     int prepareSchedule(const BeagleOperation* ops, int count, bool accumulate) {
         const uint64_t h = hashOps(ops, count, accumulate);
         if (schedValid && h == schedHash && static_cast<int>(schedOps.size()) == count &&
             (count == 0 || std::memcmp(schedOps.data(), ops, sizeof(BeagleOperation) * count) == 0))
             return BEAGLE_SUCCESS;                     // same topology as last call: reuse plan in HBM
         Schedule s;
-        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, s);
+        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s);
         if (rc != BEAGLE_SUCCESS) return rc;
         for (const DevOp& d : s.ops) {
             if (d.a >= 0 && d.a < nTips && !tipSet[d.a]) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -272,7 +291,7 @@ struct Engine {
         schedHash = h;
         // stage + upload
         const size_t opsB = sizeof(DevOp) * sched.ops.size();
-        const size_t chB = sizeof(DevChain) * sched.chains.size();
+        const size_t chB = sizeof(Group) * sched.groups.size();
         const size_t rtB = sizeof(int) * sched.rootSlots.size();
         const size_t total = opsB + chB + rtB;
         if (schedInFlight) {
@@ -287,21 +306,21 @@ struct Engine {
         }
         // device arrays may be in use by kernels still queued on the stream: growing them frees
         // memory, so drain first (rare: only when the operation count grows)
-        if (sched.ops.size() > opsCap || sched.chains.size() > chainsCap || sched.rootSlots.size() > rootCap)
+        if (sched.ops.size() > opsCap || sched.groups.size() > groupsCap || sched.rootSlots.size() > rootCap)
             CK(cudaStreamSynchronize(stream));
         ensureCap(dOps, opsCap, sched.ops.size());
-        ensureCap(dChains, chainsCap, sched.chains.size());
+        ensureCap(dGroups, groupsCap, sched.groups.size());
         ensureCap(dRootSlots, rootCap, sched.rootSlots.size());
         unsigned char* st = static_cast<unsigned char*>(hSchedStage);
         if (opsB) std::memcpy(st, sched.ops.data(), opsB);
-        if (chB) std::memcpy(st + opsB, sched.chains.data(), chB);
+        if (chB) std::memcpy(st + opsB, sched.groups.data(), chB);
         if (rtB) std::memcpy(st + opsB + chB, sched.rootSlots.data(), rtB);
         if (opsB) CK(cudaMemcpyAsync(dOps, st, opsB, cudaMemcpyHostToDevice, stream));
-        if (chB) CK(cudaMemcpyAsync(dChains, st + opsB, chB, cudaMemcpyHostToDevice, stream));
+        if (chB) CK(cudaMemcpyAsync(dGroups, st + opsB, chB, cudaMemcpyHostToDevice, stream));
         if (rtB) CK(cudaMemcpyAsync(dRootSlots, st + opsB + chB, rtB, cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(schedCopied, stream));
         schedInFlight = true;
-        const size_t needSlots = static_cast<size_t>(sched.slotCount) * Ppad;
+        const size_t needSlots = 2 * static_cast<size_t>(sched.slotCount) * Ppad;   // (log sum, product) planes
         if (needSlots > slotCapacity) {
             CK(cudaStreamSynchronize(stream));
             cudaFree(dSlots);
@@ -323,13 +342,13 @@ struct Engine {
     template <typename real, int CC, int R>
     void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
         constexpr int perBlock = (kPruneThreads / CC) * R;
-        dim3 grid(Ppad / perBlock, L.chainCount);
-        prune_chains_kernel<real, CC, R><<<grid, kPruneThreads, 0, stream>>>(a, L.chainStart, cumMode);
+        dim3 grid(Ppad / perBlock, L.groupCount);
+        prune_chains_kernel<real, CC, R><<<grid, kPruneThreads, 0, stream>>>(a, L.groupStart, cumMode);
     }
     template <typename real, int CC>
     void launchLevelGeneric(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        dim3 grid(Ppad / 128, L.chainCount);
-        prune_chains_generic_kernel<real, CC><<<grid, 128, 0, stream>>>(a, L.chainStart, cumMode);
+        dim3 grid(Ppad / 128, L.groupCount);
+        prune_chains_generic_kernel<real, CC><<<grid, 128, 0, stream>>>(a, L.groupStart, cumMode);
     }
 
     template <typename real>
@@ -352,17 +371,18 @@ struct Engine {
         a.partials = static_cast<real*>(dPartials);
         a.tips = dTips;
         a.mats = static_cast<const real*>(dMats);
-        a.slots = dSlots;
+        a.slotAcc = dSlots;
+        a.slotProd = dSlots + static_cast<size_t>(sched.slotCount) * Ppad;
         a.cum = cum;
         a.ops = dOps;
-        a.chains = dChains;
+        a.groups = dGroups;
         a.tipStride = tipStride;
         a.P = P;
         a.Ppad = Ppad;
         a.nTips = nTips;
-        const bool big = static_cast<long long>(P) * C >= (1LL << 18);
+        const bool big = bigTiles();
         for (const Level& L : sched.levels) {
-            if (L.chainCount == 0) continue;
+            if (L.groupCount == 0) continue;
             switch (C) {
                 case 1: big ? launchLevelCG<real, 1, 2>(a, L, cumMode) : launchLevelCG<real, 1, 1>(a, L, cumMode); break;
                 case 2: big ? launchLevelCG<real, 2, 2>(a, L, cumMode) : launchLevelCG<real, 2, 1>(a, L, cumMode); break;
@@ -380,7 +400,7 @@ struct Engine {
             const int nr = static_cast<int>(sched.rootSlots.size());
             int mode = 0;
             if (scaleZeroPending[cumIdx]) { mode = 1; scaleZeroPending[cumIdx] = 0; }
-            fold_roots_kernel<<<(Ppad + 255) / 256, 256, 0, stream>>>(dSlots, dRootSlots, nr, cum, Ppad, mode);
+            fold_roots_kernel<<<(Ppad + 255) / 256, 256, 0, stream>>>(a.slotAcc, a.slotProd, dRootSlots, nr, cum, Ppad, mode);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -920,7 +940,7 @@ extern "C" int sb200DebugSchedule(const BeagleOperation* operations, int operati
                                   int partialsBufferCount, int* levelOut, int* chainOut, int* chainCountOut) {
     try {
         Schedule s;
-        int rc = buildSchedule(operations, operationCount, tipCount, partialsBufferCount, 1 << 30, 1 << 30, true, s);
+        int rc = buildSchedule(operations, operationCount, tipCount, partialsBufferCount, 1 << 30, 1 << 30, true, 1, s);
         if (rc) return rc;
         for (int o = 0; o < operationCount; ++o) {
             if (levelOut) levelOut[o] = s.opLevel[o];

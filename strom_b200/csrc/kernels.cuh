@@ -42,10 +42,11 @@ struct PruneArgs {
     real* partials;
     const uint8_t* tips;
     const real* mats;
-    double* slots;                   // subtree log-scaler sums [slot][pattern]
+    double* slotAcc;                 // subtree log-scaler sums: log part   [slot][Ppad]
+    double* slotProd;                //                          product part [slot][Ppad] (scaler = acc + log(prod))
     double* cum;                     // cumulative scale buffer or nullptr
     const DevOp* ops;
-    const DevChain* chains;
+    const Group* groups;
     long long tipStride;
     int P;
     int Ppad;
@@ -135,11 +136,20 @@ transition_matrices_kernel(const DevModel* __restrict__ model, const double* __r
 
 // ------------------------------------------------------------------------------------------
 // (b) pruning, chain-fused with per-node rescaling.
+//
+// A thread block owns one tile of patterns and one *group* of operations of the current launch
+// and streams through the group as ONE software-pipelined loop.  Per step a thread
+//   - reads its category's two 4x4 matrices from shared memory (image staged by cp.async one
+//     step ahead, one __syncthreads per step),
+//   - takes operand B from registers (256-bit load or 1-byte tip state requested one step ahead),
+//   - takes operand A from the partials it produced in the previous step (still in registers), or,
+//     at the start of a chain, from memory,
+//   - multiplies, rescales by the per-pattern maximum over categories and states (C-lane shuffle),
+//     writes the 4 new partials with one 256-bit store.
+// The log of each rescaling maximum is NOT taken per step: the maxima are multiplied into a running
+// product that is folded into a log sum only before it could underflow, chains hand (log sum,
+// product) pairs to their parents, and only the chain ending at the root takes one log per pattern.
 //     C in {1,2,4,8}: one thread per (pattern, category), R patterns per thread.
-//     Per step a thread reads its category's two 4x4 matrices from shared memory (staged by
-//     cp.async one step ahead), the sibling's 4 partials (256-bit load, requested one step
-//     ahead) or 1-byte tip state, keeps the running partials in registers, rescales with a
-//     C-lane shuffle maximum, and writes the 4 new partials with one 256-bit store.
 // ------------------------------------------------------------------------------------------
 template <typename real, int C>
 __device__ __forceinline__ void factorPartial(const real* __restrict__ sm, int k, const real (&v)[4], real (&F)[4]) {
@@ -160,27 +170,63 @@ __device__ __forceinline__ void factorTip(const real* __restrict__ sm, int k, in
     for (int i = 0; i < 4; ++i) F[i] = T[i];
 }
 
-constexpr int kOpSegment = 32;      // operations of a chain staged in shared memory at a time
+// Rare path of the deferred log: fold the running product (and the factor that would have
+// underflowed it) into the log sum.  Kept out of line so the hot loop carries no log() code.
+__device__ __noinline__ double foldedLog(double prod, double factor) { return log(prod) + log(factor); }
+__device__ __forceinline__ void foldProduct(double& acc, double& prod, double factor) {
+    acc += foldedLog(prod, factor);
+    prod = 1.0;
+}
+__device__ __noinline__ double scalerTotal(double acc, double prod) { return acc + log(prod); }
+
+// (acc, prod) *= factor, keeping prod >= 1e-200.  `factor` may be denormal (then prod*factor
+// rounds to 0 and the fold path takes the logs separately).
+__device__ __forceinline__ void accumulateFactor(double& acc, double& prod, double factor) {
+    const double t = prod * factor;
+    if (t < 1e-200) foldProduct(acc, prod, factor);
+    else prod = t;
+}
+
+constexpr int kOpSegment = 32;                 // operations staged in shared memory at a time (x2 buffers)
+constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
+
+#ifndef SB200_MINBLK_R1
+#define SB200_MINBLK_R1 3
+#endif
+#ifndef SB200_MINBLK_R2
+#define SB200_MINBLK_R2 2
+#endif
 
 template <typename real, int C, int R>
-__global__ void __launch_bounds__(kPruneThreads, R == 1 ? 3 : 2)
-prune_chains_kernel(const PruneArgs<real> A, const int chainBase, const int cumMode) {
+__global__ void __launch_bounds__(kPruneThreads, R == 1 ? SB200_MINBLK_R1 : SB200_MINBLK_R2)
+prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
     constexpr int G = kPruneThreads / C;                 // patterns per pass
     constexpr int MSZ = kMatStride * C;                  // reals per operand image
     constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
     constexpr int NCH = MSZ / CHUNK;                     // 16-byte chunks per operand image
     __shared__ __align__(16) real sm[2][2 * MSZ];
-    __shared__ __align__(16) DevOp sops[kOpSegment];
+    __shared__ int4 sops[2][kOpSegment * kOpWords];
 
     const int tid = threadIdx.x;
     const int k = tid % C, g = tid / C;
-    const DevChain ch = A.chains[chainBase + blockIdx.y];
+    const Group grp = A.groups[groupBase + blockIdx.y];
+    const int nOps = grp.opEnd - grp.opStart;
+    const int4* gops = reinterpret_cast<const int4*>(A.ops + grp.opStart);
+    const int nTips = A.nTips;
+    const int Ppad = A.Ppad;
     const int p0 = blockIdx.x * (G * R) + g;             // r-th pattern of this thread: p0 + r*G (< Ppad)
-    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
+    const size_t bufStride = static_cast<size_t>(Ppad) * C * 4;
     real* const pmine = A.partials + (static_cast<size_t>(p0) * C + k) * 4;
     const uint8_t* const tmine = A.tips + p0;
-    double* const smine = A.slots + p0;
+    double* const accMine = A.slotAcc + p0;
+    double* const prodMine = A.slotProd + p0;
 
+    auto loadSegment = [&](int q) {        // operations [q*SEG, (q+1)*SEG) of the group -> sops[q&1]
+        const int first = q * kOpSegment * kOpWords;
+        const int words = min(kOpSegment, nOps - q * kOpSegment) * kOpWords;
+        if (tid < words) sops[q & 1][tid] = gops[first + tid];
+    };
+    auto opWord = [&](int j, int w) -> int4 { return sops[(j / kOpSegment) & 1][(j % kOpSegment) * kOpWords + w]; };
     auto stage = [&](int buf, int ma, int mb) {
 #pragma unroll
         for (int c = tid; c < 2 * NCH; c += kPruneThreads) {
@@ -190,12 +236,12 @@ prune_chains_kernel(const PruneArgs<real> A, const int chainBase, const int cumM
         cpAsyncCommit();
     };
     auto fetch = [&](int src, real (&v)[R][4], int (&state)[R]) {
-        if (src < A.nTips) {
+        if (src < nTips) {
             const uint8_t* t = tmine + static_cast<size_t>(src) * A.tipStride;
 #pragma unroll
             for (int r = 0; r < R; ++r) state[r] = t[r * G];
         } else {
-            const real* base = pmine + static_cast<size_t>(src - A.nTips) * bufStride;
+            const real* base = pmine + static_cast<size_t>(src - nTips) * bufStride;
 #pragma unroll
             for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
         }
@@ -203,116 +249,132 @@ prune_chains_kernel(const PruneArgs<real> A, const int chainBase, const int cumM
 
     real X[R][4], Y[R][4];
     int sX[R], sY[R];
-    double acc[R], prod[R];
+    double acc[R], prod[R], pendAcc[R], pendProd[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; sX[r] = 0; sY[r] = 0; }
+    for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; pendAcc[r] = 0.0; pendProd[r] = 1.0; sX[r] = 0; sY[r] = 0; }
 
-    for (int seg0 = 0; seg0 < ch.opCount; seg0 += kOpSegment) {
-        const int nseg = min(kOpSegment, ch.opCount - seg0);
-        if (seg0 > 0) __syncthreads();
-        if (tid < nseg * 2)
-            reinterpret_cast<int4*>(sops)[tid] = reinterpret_cast<const int4*>(A.ops + ch.opStart + seg0)[tid];
-        __syncthreads();
-
-        DevOp op = sops[0];
-        stage(0, op.ma, op.mb);
-        if (seg0 == 0) {
-            fetch(op.a, X, sX);
-            if (op.sa >= 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] += smine[static_cast<size_t>(op.sa) * A.Ppad + r * G];
-            }
-        }
-        fetch(op.b, Y, sY);
-        if (op.sb >= 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] += smine[static_cast<size_t>(op.sb) * A.Ppad + r * G];
-        }
-        cpAsyncWaitAll();
-        __syncthreads();
-
-        for (int j = 0; j < nseg; ++j) {
-            const bool more = j + 1 < nseg;
-            DevOp nx = op;
-            real Yn[R][4];
-            int sYn[R];
-            double accn[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) { accn[r] = 0.0; sYn[r] = 0; }
-            if (more) {
-                // software pipeline: the next operation's matrices (cp.async) and sibling partials are
-                // requested before this operation's arithmetic so their latency hides behind it
-                nx = sops[j + 1];
-                stage((j + 1) & 1, nx.ma, nx.mb);
-                fetch(nx.b, Yn, sYn);
-                if (nx.sb >= 0) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) accn[r] = smine[static_cast<size_t>(nx.sb) * A.Ppad + r * G];
-                }
-            }
-
-            const real* sa = sm[j & 1];
-            const real* sb = sa + MSZ;
-            const bool aTip = op.a >= 0 && op.a < A.nTips;
-            const bool bTip = op.b < A.nTips;
-            real* dest = pmine + static_cast<size_t>(op.dest) * bufStride;
+    // ---- prologue: first operation's matrices, operands and sibling scalers
+    loadSegment(0);
+    __syncthreads();
+    {
+        const int4 w0 = opWord(0, 0), w1 = opWord(0, 1);     // {dest,a,ma,b} {mb,sa,sb,flags}
+        stage(0, w0.z, w1.x);
+        fetch(w0.y, X, sX);
+        fetch(w0.w, Y, sY);
+        if (w1.y >= 0) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                real FA[4], FB[4], D[4];
-                if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
-                else factorPartial<real, C>(sa, k, X[r], FA);
-                if (bTip) factorTip<real, C>(sb, k, sY[r], FB);
-                else factorPartial<real, C>(sb, k, Y[r], FB);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) D[i] = FA[i] * FB[i];
-                if (op.flags & OP_RESCALE) {
-                    real m = rmax(rmax(D[0], D[1]), rmax(D[2], D[3]));
-#pragma unroll
-                    for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-                    if (m == real(0)) m = real(1);
-                    const real inv = real(1) / m;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) D[i] *= inv;
-                    // deferred log: keep the product of the maxima and fold it into the log sum only
-                    // before it could underflow (also catches a denormal maximum)
-                    const double md = static_cast<double>(m);
-                    const double t = prod[r] * md;
-                    if (t < 1e-200) {
-                        acc[r] += log(prod[r]) + log(md);
-                        prod[r] = 1.0;
-                    } else {
-                        prod[r] = t;
-                    }
-                }
-                st4(dest + r * (G * C * 4), D);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) X[r][i] = D[i];
+                acc[r] += accMine[static_cast<size_t>(w1.y) * Ppad + r * G];
+                prod[r] = prodMine[static_cast<size_t>(w1.y) * Ppad + r * G];
             }
-
-            if (more) {
+        }
+        if (w1.z >= 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) Y[r][i] = Yn[r][i];
-                    sY[r] = sYn[r];
-                    acc[r] += accn[r];
-                }
-                op = nx;
-                cpAsyncWaitAll();
+            for (int r = 0; r < R; ++r) {
+                pendAcc[r] = accMine[static_cast<size_t>(w1.z) * Ppad + r * G];
+                pendProd[r] = prodMine[static_cast<size_t>(w1.z) * Ppad + r * G];
             }
-            __syncthreads();
         }
     }
 
-    if (k == 0 && (ch.sOut >= 0 || ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr))) {
+    for (int j = 0; j < nOps; ++j) {
+        cpAsyncWaitAll();
+        __syncthreads();          // matrices of step j visible; everyone is done with step j-1's image and op words
+        const bool more = j + 1 < nOps;
+        if ((j % kOpSegment) == 0 && (j / kOpSegment + 1) * kOpSegment < nOps) loadSegment(j / kOpSegment + 1);
+        const int4 w0 = opWord(j, 0), w1 = opWord(j, 1);
+        int4 n0 = w0, n1 = w1;
+        if (more) {
+            n0 = opWord(j + 1, 0);
+            n1 = opWord(j + 1, 1);
+            stage((j + 1) & 1, n0.z, n1.x);
+        }
+        const int flags = w1.w;
+        const real* sa = sm[j & 1];
+        const real* sb = sa + MSZ;
+
+        // operand B -> factor, then its registers are free for the next step's B
+        real FB[R][4];
+        if (w0.w < nTips) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) factorTip<real, C>(sb, k, sY[r], FB[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) factorPartial<real, C>(sb, k, Y[r], FB[r]);
+        }
+        if (w1.z >= 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r] += pendAcc[r];
+                accumulateFactor(acc[r], prod[r], pendProd[r]);
+            }
+        }
+        if (more) {
+            fetch(n0.w, Y, sY);
+            if (n1.z >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    pendAcc[r] = accMine[static_cast<size_t>(n1.z) * Ppad + r * G];
+                    pendProd[r] = prodMine[static_cast<size_t>(n1.z) * Ppad + r * G];
+                }
+            }
+        }
+
+        // operand A -> factor, product, rescale, store
+        const bool aTip = (flags & OP_CHAIN_START) && w0.y < nTips;
+        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const double total = acc[r] + log(prod[r]);
-            if (ch.sOut >= 0) smine[static_cast<size_t>(ch.sOut) * A.Ppad + r * G] = total;
-            if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
-                double* c = A.cum + p0 + r * G;
-                if (cumMode) *c = total;
-                else *c += total;
+            real FA[4];
+            if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
+            else factorPartial<real, C>(sa, k, X[r], FA);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) X[r][i] = FA[i] * FB[r][i];
+            if (flags & OP_RESCALE) {
+                real m = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
+#pragma unroll
+                for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+                if (m == real(0)) m = real(1);
+                const real inv = real(1) / m;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) X[r][i] *= inv;
+                accumulateFactor(acc[r], prod[r], static_cast<double>(m));
+            }
+            st4(dest + r * (G * C * 4), X[r]);
+        }
+
+        if (flags & OP_CHAIN_END) {
+            const int sOut = opWord(j, 2).x;
+            if (sOut >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (prod[r] < 1e-100) foldProduct(acc[r], prod[r], 1.0);   // so a parent's product of two stays normal
+                    if (k == 0) {
+                        accMine[static_cast<size_t>(sOut) * Ppad + r * G] = acc[r];
+                        prodMine[static_cast<size_t>(sOut) * Ppad + r * G] = prod[r];
+                    }
+                }
+            }
+            if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && k == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double total = scalerTotal(acc[r], prod[r]);
+                    double* c = A.cum + p0 + r * G;
+                    if (cumMode) *c = total;
+                    else *c += total;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; }
+        }
+        if (more && (n1.w & OP_CHAIN_START)) {
+            fetch(n0.y, X, sX);
+            if (n1.y >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    acc[r] += accMine[static_cast<size_t>(n1.y) * Ppad + r * G];
+                    prod[r] = prodMine[static_cast<size_t>(n1.y) * Ppad + r * G];
+                }
             }
         }
     }
@@ -321,31 +383,39 @@ prune_chains_kernel(const PruneArgs<real> A, const int chainBase, const int cumM
 // Any other category count (3,5,6,7): one thread per pattern, categories looped in registers.
 template <typename real, int C>
 __global__ void __launch_bounds__(128)
-prune_chains_generic_kernel(const PruneArgs<real> A, const int chainBase, const int cumMode) {
+prune_chains_generic_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
     constexpr int MSZ = kMatStride * C;
     __shared__ __align__(16) real sm[2 * MSZ];
     const int tid = threadIdx.x;
-    const DevChain ch = A.chains[chainBase + blockIdx.y];
+    const Group grp = A.groups[groupBase + blockIdx.y];
     const int p = blockIdx.x * 128 + tid;                 // < Ppad
-    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
+    const int Ppad = A.Ppad;
+    const size_t bufStride = static_cast<size_t>(Ppad) * C * 4;
     real X[C][4];
     double acc = 0.0, prod = 1.0;
 
-    for (int j = 0; j < ch.opCount; ++j) {
-        const DevOp op = A.ops[ch.opStart + j];
+    for (int j = grp.opStart; j < grp.opEnd; ++j) {
+        const DevOp op = A.ops[j];
         __syncthreads();
         for (int q = tid; q < 2 * MSZ; q += 128) {
             const int o = q / MSZ, w = q - o * MSZ;
             sm[q] = A.mats[static_cast<size_t>(o ? op.mb : op.ma) * MSZ + w];
         }
         __syncthreads();
-        if (op.sa >= 0) acc += A.slots[static_cast<size_t>(op.sa) * A.Ppad + p];
-        if (op.sb >= 0) acc += A.slots[static_cast<size_t>(op.sb) * A.Ppad + p];
-        const bool aTip = op.a >= 0 && op.a < A.nTips;
+        if (op.sa >= 0) {
+            acc += A.slotAcc[static_cast<size_t>(op.sa) * Ppad + p];
+            accumulateFactor(acc, prod, A.slotProd[static_cast<size_t>(op.sa) * Ppad + p]);
+        }
+        if (op.sb >= 0) {
+            acc += A.slotAcc[static_cast<size_t>(op.sb) * Ppad + p];
+            accumulateFactor(acc, prod, A.slotProd[static_cast<size_t>(op.sb) * Ppad + p]);
+        }
+        const bool aMem = (op.flags & OP_CHAIN_START) != 0;
+        const bool aTip = aMem && op.a < A.nTips;
         const bool bTip = op.b < A.nTips;
         const int sA = aTip ? A.tips[static_cast<size_t>(op.a) * A.tipStride + p] : 0;
         const int sB = bTip ? A.tips[static_cast<size_t>(op.b) * A.tipStride + p] : 0;
-        const real* pa = (op.a >= A.nTips) ? A.partials + static_cast<size_t>(op.a - A.nTips) * bufStride : nullptr;
+        const real* pa = (aMem && !aTip) ? A.partials + static_cast<size_t>(op.a - A.nTips) * bufStride : nullptr;
         const real* pb = bTip ? nullptr : A.partials + static_cast<size_t>(op.b - A.nTips) * bufStride;
         real m = real(0);
 #pragma unroll
@@ -386,34 +456,39 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int chainBase, const 
             for (int kk = 0; kk < C; ++kk)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) X[kk][i] *= inv;
-            const double md = static_cast<double>(m);
-            const double t = prod * md;
-            if (t < 1e-200) {
-                acc += log(prod) + log(md);
-                prod = 1.0;
-            } else {
-                prod = t;
-            }
+            accumulateFactor(acc, prod, static_cast<double>(m));
         }
         real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride + static_cast<size_t>(p) * C * 4;
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) st4(dest + kk * 4, X[kk]);
-    }
-    const double total = acc + log(prod);
-    if (ch.sOut >= 0) A.slots[static_cast<size_t>(ch.sOut) * A.Ppad + p] = total;
-    if ((ch.flags & CHAIN_ADD_TO_CUM) && A.cum != nullptr) {
-        if (cumMode) A.cum[p] = total;
-        else A.cum[p] += total;
+        if (op.flags & OP_CHAIN_END) {
+            if (op.sOut >= 0) {
+                if (prod < 1e-100) foldProduct(acc, prod, 1.0);
+                A.slotAcc[static_cast<size_t>(op.sOut) * Ppad + p] = acc;
+                A.slotProd[static_cast<size_t>(op.sOut) * Ppad + p] = prod;
+            }
+            if ((op.flags & OP_ADD_TO_CUM) && A.cum != nullptr) {
+                const double total = scalerTotal(acc, prod);
+                if (cumMode) A.cum[p] = total;
+                else A.cum[p] += total;
+            }
+            acc = 0.0;
+            prod = 1.0;
+        }
     }
 }
 
-// Folds the subtree sums of several forest roots into the cumulative buffer, in list order.
-__global__ void fold_roots_kernel(const double* __restrict__ slots, const int* __restrict__ rootSlots, int nRoots,
-                                  double* __restrict__ cum, int Ppad, int cumMode) {
+// Folds the subtree scalers of several forest roots into the cumulative buffer, in list order.
+__global__ void fold_roots_kernel(const double* __restrict__ slotAcc, const double* __restrict__ slotProd,
+                                  const int* __restrict__ rootSlots, int nRoots, double* __restrict__ cum, int Ppad,
+                                  int cumMode) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= Ppad) return;
     double s = cumMode ? 0.0 : cum[p];
-    for (int r = 0; r < nRoots; ++r) s += slots[static_cast<size_t>(rootSlots[r]) * Ppad + p];
+    for (int r = 0; r < nRoots; ++r) {
+        const size_t i = static_cast<size_t>(rootSlots[r]) * Ppad + p;
+        s += slotAcc[i] + log(slotProd[i]);
+    }
     cum[p] = s;
 }
 

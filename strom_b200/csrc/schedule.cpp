@@ -17,8 +17,15 @@ uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate) {
     return h;
 }
 
+static DevOp makeOp(int dest, int a, int ma, int b, int mb, int sa, int sb, int flags, int sOut) {
+    DevOp d;
+    d.dest = dest; d.a = a; d.ma = ma; d.b = b; d.mb = mb; d.sa = sa; d.sb = sb; d.flags = flags; d.sOut = sOut;
+    d.pad[0] = d.pad[1] = d.pad[2] = 0;
+    return d;
+}
+
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
-                  int matrixCount, int scaleCount, bool accumulate, Schedule& out) {
+                  int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out) {
     out = Schedule();
     const int nbuf = tipCount + partialsBufferCount;
     if (count < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -77,11 +84,13 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             const BeagleOperation& op = ops[o];
             classify(op);
             const bool rescale = op.destinationScaleWrite >= 0;
-            DevOp d{op.destinationPartials - tipCount, op.child1Partials, op.child1TransitionMatrix,
-                    op.child2Partials, op.child2TransitionMatrix, -1, -1, rescale ? OP_RESCALE : 0};
-            out.ops.push_back(d);
+            int fl = (rescale ? OP_RESCALE : 0) | OP_CHAIN_START | OP_CHAIN_END;
+            if (accumulate && rescale) fl |= OP_ADD_TO_CUM;
+            out.ops.push_back(makeOp(op.destinationPartials - tipCount, op.child1Partials, op.child1TransitionMatrix,
+                                     op.child2Partials, op.child2TransitionMatrix, -1, -1, fl, -1));
             out.chains.push_back(DevChain{o, 1, -1, (accumulate && rescale) ? CHAIN_ADD_TO_CUM : 0});
-            out.levels.push_back(Level{o, 1});
+            out.levels.push_back(Level{o, 1, o, 1});
+            out.groups.push_back(Group{o, o + 1});
             out.opLevel[o] = o;
             out.opChain[o] = o;
             out.partialReads += (op.child1Partials >= tipCount) + (op.child2Partials >= tipCount);
@@ -140,52 +149,73 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             for (int r : roots) out.rootSlots.push_back(slotOfChain[out.opChain[r]]);
     }
 
-    // Emit chains level by level, longest first inside a level (they gate the launch's tail).
+    // Emit chains level by level.  Inside a level the chains are dealt, longest first, into the
+    // currently lightest of `groupCount` groups (LPT), and each group's operations are laid out
+    // contiguously: a thread block streams through one group.
     int maxLevel = -1;
     for (int l : chainLevel) maxLevel = std::max(maxLevel, l);
     std::vector<int> chainNewId(nChains, -1);
+    if (groupsPerLevel < 1) groupsPerLevel = 1;
     for (int lvl = 0; lvl <= maxLevel; ++lvl) {
         std::vector<int> ids;
         for (int c = 0; c < nChains; ++c) if (chainLevel[c] == lvl) ids.push_back(c);
         std::stable_sort(ids.begin(), ids.end(),
                          [&](int x, int y) { return chainOps[x].size() > chainOps[y].size(); });
-        Level L{static_cast<int>(out.chains.size()), static_cast<int>(ids.size())};
+        const int nGroups = std::max(1, std::min<int>(groupsPerLevel, static_cast<int>(ids.size())));
+        std::vector<std::vector<int>> bins(nGroups);
+        std::vector<size_t> load(nGroups, 0);
         for (int c : ids) {
-            DevChain dc{static_cast<int>(out.ops.size()), static_cast<int>(chainOps[c].size()), slotOfChain[c], 0};
-            const int last = chainOps[c].back();
-            if (accumulate && consumers[last] == 0 && roots.size() == 1) {
-                dc.flags |= CHAIN_ADD_TO_CUM;
-                out.scalerRows += 2;
-            }
-            if (dc.sOut >= 0) out.scalerRows += 1;
-            chainNewId[c] = static_cast<int>(out.chains.size());
-            for (size_t j = 0; j < chainOps[c].size(); ++j) {
-                const int o = chainOps[c][j];
-                const BeagleOperation& op = ops[o];
-                const bool rescale = op.destinationScaleWrite >= 0;
-                DevOp d;
-                d.dest = op.destinationPartials - tipCount;
-                d.flags = rescale ? OP_RESCALE : 0;
-                auto slotFor = [&](int inOp) {
-                    return (accumulate && inOp >= 0) ? slotOfChain[out.opChain[inOp]] : -1;
-                };
-                if (carriedChild[o] < 0) {
-                    d.a = op.child1Partials; d.ma = op.child1TransitionMatrix; d.sa = slotFor(in1[o]);
-                    d.b = op.child2Partials; d.mb = op.child2TransitionMatrix; d.sb = slotFor(in2[o]);
-                } else if (carriedChild[o] == 0) {
-                    d.a = -1; d.ma = op.child1TransitionMatrix; d.sa = -1;
-                    d.b = op.child2Partials; d.mb = op.child2TransitionMatrix; d.sb = slotFor(in2[o]);
-                } else {
-                    d.a = -1; d.ma = op.child2TransitionMatrix; d.sa = -1;
-                    d.b = op.child1Partials; d.mb = op.child1TransitionMatrix; d.sb = slotFor(in1[o]);
+            int best = 0;
+            for (int g = 1; g < nGroups; ++g) if (load[g] < load[best]) best = g;
+            bins[best].push_back(c);
+            load[best] += chainOps[c].size() + 1;     // +1: a chain start costs about one extra step
+        }
+        Level L{static_cast<int>(out.chains.size()), static_cast<int>(ids.size()), static_cast<int>(out.groups.size()), nGroups};
+        for (int g = 0; g < nGroups; ++g) {
+            Group G{static_cast<int>(out.ops.size()), 0};
+            for (int c : bins[g]) {
+                DevChain dc{static_cast<int>(out.ops.size()), static_cast<int>(chainOps[c].size()), slotOfChain[c], 0};
+                const int last = chainOps[c].back();
+                if (accumulate && consumers[last] == 0 && roots.size() == 1) {
+                    dc.flags |= CHAIN_ADD_TO_CUM;
+                    out.scalerRows += 2;
                 }
-                if (d.a >= 0) (d.a < tipCount ? out.tipReads : out.partialReads) += 1;
-                (d.b < tipCount ? out.tipReads : out.partialReads) += 1;
-                out.scalerRows += (d.sa >= 0) + (d.sb >= 0);
-                out.partialWrites += 1;
-                out.ops.push_back(d);
+                if (dc.sOut >= 0) out.scalerRows += 2;
+                chainNewId[c] = static_cast<int>(out.chains.size());
+                for (size_t j = 0; j < chainOps[c].size(); ++j) {
+                    const int o = chainOps[c][j];
+                    const BeagleOperation& op = ops[o];
+                    auto slotFor = [&](int inOp) {
+                        return (accumulate && inOp >= 0) ? slotOfChain[out.opChain[inOp]] : -1;
+                    };
+                    int fl = op.destinationScaleWrite >= 0 ? OP_RESCALE : 0;
+                    if (j == 0) fl |= OP_CHAIN_START;
+                    if (j + 1 == chainOps[c].size()) {
+                        fl |= OP_CHAIN_END;
+                        if (dc.flags & CHAIN_ADD_TO_CUM) fl |= OP_ADD_TO_CUM;
+                    }
+                    const int sOut = (j + 1 == chainOps[c].size()) ? dc.sOut : -1;
+                    const int dest = op.destinationPartials - tipCount;
+                    DevOp d;
+                    if (carriedChild[o] < 0)
+                        d = makeOp(dest, op.child1Partials, op.child1TransitionMatrix, op.child2Partials,
+                                   op.child2TransitionMatrix, slotFor(in1[o]), slotFor(in2[o]), fl, sOut);
+                    else if (carriedChild[o] == 0)
+                        d = makeOp(dest, -1, op.child1TransitionMatrix, op.child2Partials, op.child2TransitionMatrix, -1,
+                                   slotFor(in2[o]), fl, sOut);
+                    else
+                        d = makeOp(dest, -1, op.child2TransitionMatrix, op.child1Partials, op.child1TransitionMatrix, -1,
+                                   slotFor(in1[o]), fl, sOut);
+                    if (d.a >= 0) (d.a < tipCount ? out.tipReads : out.partialReads) += 1;
+                    (d.b < tipCount ? out.tipReads : out.partialReads) += 1;
+                    out.scalerRows += 2 * ((d.sa >= 0) + (d.sb >= 0));
+                    out.partialWrites += 1;
+                    out.ops.push_back(d);
+                }
+                out.chains.push_back(dc);
             }
-            out.chains.push_back(dc);
+            G.opEnd = static_cast<int>(out.ops.size());
+            out.groups.push_back(G);
         }
         out.levels.push_back(L);
     }

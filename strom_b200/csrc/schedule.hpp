@@ -20,7 +20,7 @@
 
 namespace sb200 {
 
-// One operation as the pruning kernel consumes it (32 bytes, uploaded as-is).
+// One operation as the pruning kernel consumes it (48 bytes = three 16-byte words, uploaded as-is).
 struct DevOp {
     int dest;    // destination partials slot (= buffer index - tipCount)
     int a;       // operand A: buffer index (tip if < tipCount), or -1 = carried in registers
@@ -29,27 +29,45 @@ struct DevOp {
     int mb;      // transition matrix of B's edge
     int sa;      // subtree log-scaler slot to add for A, or -1
     int sb;      // subtree log-scaler slot to add for B, or -1
-    int flags;   // OP_RESCALE
+    int flags;   // OP_* bits
+    int sOut;    // OP_CHAIN_END: slot receiving the chain's subtree log-scaler, or -1
+    int pad[3];
 };
-enum { OP_RESCALE = 1 };
+enum {
+    OP_RESCALE = 1,        // destinationScaleWrite >= 0
+    OP_CHAIN_START = 2,    // operand A comes from memory (tips or a finished buffer)
+    OP_CHAIN_END = 4,      // last operation of its chain: emit the subtree log-scaler, reset
+    OP_ADD_TO_CUM = 8      // with OP_CHAIN_END: the chain total goes into the cumulative buffer
+};
 
+// Host-side view of a chain (device code only sees the flags above).
 struct DevChain {
     int opStart;   // first DevOp of the chain
     int opCount;
-    int sOut;      // slot receiving the chain's subtree log-scaler sum, or -1
+    int sOut;
     int flags;     // CHAIN_ADD_TO_CUM
 };
 enum { CHAIN_ADD_TO_CUM = 1 };
 
+// One launch.  Its chains are dealt into `groupCount` groups of similar total length; a thread
+// block runs all operations of one group, [groupStart[g], groupStart[g+1]), as one pipelined loop.
 struct Level {
     int chainStart;
     int chainCount;
+    int groupStart;   // index into Schedule::groups
+    int groupCount;
+};
+
+struct Group {
+    int opStart;
+    int opEnd;
 };
 
 struct Schedule {
     std::vector<DevOp> ops;
     std::vector<DevChain> chains;
     std::vector<Level> levels;
+    std::vector<Group> groups;
     std::vector<int> rootSlots;     // slots of forest roots to fold into the cumulative buffer afterwards
     int slotCount = 0;              // subtree log-scaler slots needed
     bool sequential = false;        // true: list was not a forest; one operation per launch
@@ -61,8 +79,10 @@ struct Schedule {
 };
 
 // Returns BEAGLE_SUCCESS or an error code (index out of range, unsupported scale-read).
+// `groupsPerLevel`: how many thread-block groups a launch should be split into at most (the engine
+// derives it from the pattern-tile count so that every launch has enough blocks to fill the GPU).
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
-                  int matrixCount, int scaleCount, bool accumulate, Schedule& out);
+                  int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out);
 
 // FNV-1a over the raw operation list, used to reuse a schedule when the topology is unchanged.
 uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate);
