@@ -35,6 +35,11 @@ struct CudaFail {
 
 static int g_device = 0;
 
+#ifndef SB200_BIG_R
+#define SB200_BIG_R 4
+#endif
+constexpr int kBigR = SB200_BIG_R;   // patterns per thread of the streaming (large-P) pruning kernel
+
 // Host image of the per-call parameter block; mirrored 1:1 in HBM and refreshed by ONE copy.
 struct ParamBlockHeader {
     double rates[kMaxCategories];
@@ -44,7 +49,7 @@ struct Engine {
     int device = 0;
     bool fp32 = false;
     int nTips = 0, nPartials = 0, nCompact = 0, P = 0, nEigen = 0, nMat = 0, C = 0, nScale = 0;
-    int Ppad = 0;                         // pattern axis padded to a multiple of 512 in every buffer
+    int Ppad = 0;                         // pattern axis padded to a multiple of 1024 in every buffer
     long long tipStride = 0;
     cudaStream_t ownStream = nullptr, stream = nullptr;
 
@@ -72,6 +77,9 @@ struct Engine {
     DevOp* dOps = nullptr;
     Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
+    int* dTTOps = nullptr;                // op index of every tip x tip table
+    void* dTT = nullptr;                  // tip x tip tables
+    size_t ttOpsCap = 0, ttCap = 0;
     size_t opsCap = 0, groupsCap = 0, rootCap = 0;
     void* hSchedStage = nullptr;          // pinned staging for schedule uploads
     size_t schedStageCap = 0;
@@ -114,7 +122,7 @@ struct Engine {
         cudaFree(dTips); cudaFree(dPartials); cudaFree(dMats); cudaFree(dPatWeights);
         for (double* p : dScale) cudaFree(p);
         dScale.clear();
-        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dGroups); cudaFree(dRootSlots);
+        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dGroups); cudaFree(dRootSlots); cudaFree(dTTOps); cudaFree(dTT);
         cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut);
         if (hBlock) cudaFreeHost(hBlock);
         if (hSchedStage) cudaFreeHost(hSchedStage);
@@ -126,7 +134,7 @@ struct Engine {
         evP0 = evP1 = nullptr;
         if (ownStream) cudaStreamDestroy(ownStream);
         dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr;
-        dBlock = nullptr; dOps = nullptr; dGroups = nullptr; dRootSlots = nullptr; dBlockSums = nullptr;
+        dBlock = nullptr; dOps = nullptr; dGroups = nullptr; dRootSlots = nullptr; dTTOps = nullptr; dTT = nullptr; dBlockSums = nullptr;
         dTicket = nullptr; dOut = nullptr; hBlock = nullptr; hSchedStage = nullptr; hOut = nullptr;
         blockCopied = nullptr; schedCopied = nullptr; ownStream = nullptr; stream = nullptr;
     }
@@ -147,7 +155,7 @@ struct Engine {
         stream = ownStream;
         CK(cudaEventCreateWithFlags(&blockCopied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
-        Ppad = (P + 511) & ~511;         // = patterns per block of the widest kernel (C=1, R=2)
+        Ppad = (P + 1023) & ~1023;       // = patterns per block of the widest kernel (C=1, R=4)
         tipStride = Ppad;
         if (nTips > 0) {
             CK(cudaMalloc(&dTips, static_cast<size_t>(nTips) * tipStride));
@@ -262,7 +270,7 @@ struct Engine {
         return big;
     }
     int patternsPerBlock() const {
-        if (C == 1 || C == 2 || C == 4 || C == 8) return (kPruneThreads / C) * (bigTiles() ? 2 : 1);
+        if (C == 1 || C == 2 || C == 4 || C == 8) return (kPruneThreads / C) * (bigTiles() ? kBigR : 1);
         return 128;
     }
     // Enough (tile x group) blocks per launch to fill the 148 SMs several times over, as few groups as
@@ -293,7 +301,11 @@ struct Engine {
         const size_t opsB = sizeof(DevOp) * sched.ops.size();
         const size_t chB = sizeof(Group) * sched.groups.size();
         const size_t rtB = sizeof(int) * sched.rootSlots.size();
-        const size_t total = opsB + chB + rtB;
+        std::vector<int> ttOps(sched.tipTipCount, 0);
+        for (size_t i = 0; i < sched.ops.size(); ++i)
+            if (sched.ops[i].flags & OP_TIPTIP) ttOps[sched.ops[i].tt] = static_cast<int>(i);
+        const size_t ttB = sizeof(int) * ttOps.size();
+        const size_t total = opsB + chB + rtB + ttB;
         if (schedInFlight) {
             CK(cudaEventSynchronize(schedCopied));
             schedInFlight = false;
@@ -306,18 +318,29 @@ struct Engine {
         }
         // device arrays may be in use by kernels still queued on the stream: growing them frees
         // memory, so drain first (rare: only when the operation count grows)
-        if (sched.ops.size() > opsCap || sched.groups.size() > groupsCap || sched.rootSlots.size() > rootCap)
+        const size_t ttNeed = static_cast<size_t>(sched.tipTipCount) * ttStride(C) * realSize();
+        if (sched.ops.size() > opsCap || sched.groups.size() > groupsCap || sched.rootSlots.size() > rootCap ||
+            ttOps.size() > ttOpsCap || ttNeed > ttCap)
             CK(cudaStreamSynchronize(stream));
         ensureCap(dOps, opsCap, sched.ops.size());
         ensureCap(dGroups, groupsCap, sched.groups.size());
         ensureCap(dRootSlots, rootCap, sched.rootSlots.size());
+        ensureCap(dTTOps, ttOpsCap, ttOps.size());
+        if (ttNeed > ttCap) {
+            cudaFree(dTT);
+            dTT = nullptr;
+            ttCap = ttNeed + ttNeed / 2 + 1024;
+            CK(cudaMalloc(&dTT, ttCap));
+        }
         unsigned char* st = static_cast<unsigned char*>(hSchedStage);
         if (opsB) std::memcpy(st, sched.ops.data(), opsB);
         if (chB) std::memcpy(st + opsB, sched.groups.data(), chB);
         if (rtB) std::memcpy(st + opsB + chB, sched.rootSlots.data(), rtB);
+        if (ttB) std::memcpy(st + opsB + chB + rtB, ttOps.data(), ttB);
         if (opsB) CK(cudaMemcpyAsync(dOps, st, opsB, cudaMemcpyHostToDevice, stream));
         if (chB) CK(cudaMemcpyAsync(dGroups, st + opsB, chB, cudaMemcpyHostToDevice, stream));
         if (rtB) CK(cudaMemcpyAsync(dRootSlots, st + opsB + chB, rtB, cudaMemcpyHostToDevice, stream));
+        if (ttB) CK(cudaMemcpyAsync(dTTOps, st + opsB + chB + rtB, ttB, cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(schedCopied, stream));
         schedInFlight = true;
         const size_t needSlots = 2 * static_cast<size_t>(sched.slotCount) * Ppad;   // (log sum, product) planes
@@ -374,20 +397,27 @@ struct Engine {
         a.slotAcc = dSlots;
         a.slotProd = dSlots + static_cast<size_t>(sched.slotCount) * Ppad;
         a.cum = cum;
+        a.ttTables = static_cast<const real*>(dTT);
         a.ops = dOps;
         a.groups = dGroups;
         a.tipStride = tipStride;
         a.P = P;
         a.Ppad = Ppad;
         a.nTips = nTips;
+        if (sched.tipTipCount > 0) {
+            tiptip_tables_kernel<real><<<sched.tipTipCount, 128, 0, stream>>>(dOps, dTTOps, static_cast<const real*>(dMats), C,
+                                                                              static_cast<real*>(dTT));
+            CK(cudaGetLastError());
+            ++launches;
+        }
         const bool big = bigTiles();
         for (const Level& L : sched.levels) {
             if (L.groupCount == 0) continue;
             switch (C) {
-                case 1: big ? launchLevelCG<real, 1, 2>(a, L, cumMode) : launchLevelCG<real, 1, 1>(a, L, cumMode); break;
-                case 2: big ? launchLevelCG<real, 2, 2>(a, L, cumMode) : launchLevelCG<real, 2, 1>(a, L, cumMode); break;
-                case 4: big ? launchLevelCG<real, 4, 2>(a, L, cumMode) : launchLevelCG<real, 4, 1>(a, L, cumMode); break;
-                case 8: big ? launchLevelCG<real, 8, 2>(a, L, cumMode) : launchLevelCG<real, 8, 1>(a, L, cumMode); break;
+                case 1: big ? launchLevelCG<real, 1, kBigR>(a, L, cumMode) : launchLevelCG<real, 1, 1>(a, L, cumMode); break;
+                case 2: big ? launchLevelCG<real, 2, kBigR>(a, L, cumMode) : launchLevelCG<real, 2, 1>(a, L, cumMode); break;
+                case 4: big ? launchLevelCG<real, 4, kBigR>(a, L, cumMode) : launchLevelCG<real, 4, 1>(a, L, cumMode); break;
+                case 8: big ? launchLevelCG<real, 8, kBigR>(a, L, cumMode) : launchLevelCG<real, 8, 1>(a, L, cumMode); break;
                 case 3: launchLevelGeneric<real, 3>(a, L, cumMode); break;
                 case 5: launchLevelGeneric<real, 5>(a, L, cumMode); break;
                 case 6: launchLevelGeneric<real, 6>(a, L, cumMode); break;

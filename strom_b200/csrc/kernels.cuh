@@ -7,7 +7,7 @@
 //   (c) root_loglik_kernel          : BeagleLib beagleCalculateEdgeLogLikelihoods
 //                                     (reference call site src/likelihood.hpp:418-447)
 //
-// HBM layout (pattern axis padded to Ppad = 512-multiple, so no kernel needs tail predicates):
+// HBM layout (pattern axis padded to Ppad = 1024-multiple, so no kernel needs tail predicates):
 //   partials [buffer][Ppad][category][state]  one pattern x category = 4 reals = one 256-bit load (FP64)
 //   tips     [tip][Ppad]                      1-byte codes 0..4 (4 = missing; padding is 4)
 //   matrices [matrix][36*C]                   already in the shared-memory image the pruning kernel wants:
@@ -27,6 +27,9 @@ namespace sb200 {
 
 constexpr int kMaxCategories = 8;
 constexpr int kMatStride = 36;      // reals per (matrix, category)
+// tip x tip table of one operation: 25 (stateA, stateB) combinations x C categories x 4 states of
+// rescaled partials, followed by the 25 rescaling maxima (padded to 32)
+__host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
 constexpr int kPruneThreads = 256;
 
 // Per-eigen-index model block, resident in HBM and refreshed once per evaluation.
@@ -45,6 +48,7 @@ struct PruneArgs {
     double* slotAcc;                 // subtree log-scaler sums: log part   [slot][Ppad]
     double* slotProd;                //                          product part [slot][Ppad] (scaler = acc + log(prod))
     double* cum;                     // cumulative scale buffer or nullptr
+    const real* ttTables;            // [tipTipCount][ttStride(C)]
     const DevOp* ops;
     const Group* groups;
     long long tipStride;
@@ -135,6 +139,48 @@ transition_matrices_kernel(const DevModel* __restrict__ model, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// (a') tip x tip tables: for an operation whose two children are tips, the rescaled partials of a
+//      pattern depend only on the two tip states.  One block per such operation computes all 25
+//      combinations exactly as the per-pattern code would (same products, same maximum, same
+//      reciprocal), so the pruning kernel only copies.
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(128)
+tiptip_tables_kernel(const DevOp* __restrict__ ops, const int* __restrict__ ttOps, const real* __restrict__ mats, int C,
+                     real* __restrict__ tables) {
+    __shared__ real tab[100 * kMaxCategories];
+    __shared__ real mx[32];
+    const DevOp op = ops[ttOps[blockIdx.x]];
+    const real* ma = mats + static_cast<size_t>(op.ma) * C * kMatStride;
+    const real* mb = mats + static_cast<size_t>(op.mb) * C * kMatStride;
+    const int n = 100 * C;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const int combo = q / (4 * C), rem = q - combo * 4 * C, k = rem >> 2, i = rem & 3;
+        const int sA = combo / 5, sB = combo - sA * 5;
+        tab[q] = ma[tipIndex(C, k, sA, i)] * mb[tipIndex(C, k, sB, i)];
+    }
+    __syncthreads();
+    if (threadIdx.x < 25) {
+        real m = real(1);
+        if (op.flags & OP_RESCALE) {
+            m = real(0);
+            for (int e = 0; e < 4 * C; ++e) m = rmax(m, tab[threadIdx.x * 4 * C + e]);
+            if (m == real(0)) m = real(1);
+        }
+        mx[threadIdx.x] = m;
+    }
+    __syncthreads();
+    real* out = tables + static_cast<size_t>(blockIdx.x) * ttStride(C);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const int combo = q / (4 * C);
+        real v = tab[q];
+        if (op.flags & OP_RESCALE) v *= real(1) / mx[combo];
+        out[q] = v;
+    }
+    if (threadIdx.x < 32) out[n + threadIdx.x] = threadIdx.x < 25 ? mx[threadIdx.x] : real(1);
+}
+
+// ------------------------------------------------------------------------------------------
 // (b) pruning, chain-fused with per-node rescaling.
 //
 // A thread block owns one tile of patterns and one *group* of operations of the current launch
@@ -198,14 +244,17 @@ constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 #endif
 
 template <typename real, int C, int R>
-__global__ void __launch_bounds__(kPruneThreads, R == 1 ? SB200_MINBLK_R1 : SB200_MINBLK_R2)
+__global__ void __launch_bounds__(kPruneThreads, R == 1 ? SB200_MINBLK_R1 : 2)
 prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
     constexpr int G = kPruneThreads / C;                 // patterns per pass
     constexpr int MSZ = kMatStride * C;                  // reals per operand image
     constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
     constexpr int NCH = MSZ / CHUNK;                     // 16-byte chunks per operand image
-    __shared__ __align__(16) real sm[2][2 * MSZ];
+    constexpr int TTS = ttStride(C);                     // reals per tip x tip table
+    constexpr int IMG = TTS > 2 * MSZ ? TTS : 2 * MSZ;   // shared image of one step: two matrices OR one table
+    __shared__ __align__(16) real sm[2][IMG];
     __shared__ int4 sops[2][kOpSegment * kOpWords];
+    __shared__ double sAcc[R][kPruneThreads];            // log part of the running scaler (touched rarely)
 
     const int tid = threadIdx.x;
     const int k = tid % C, g = tid / C;
@@ -227,11 +276,17 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         if (tid < words) sops[q & 1][tid] = gops[first + tid];
     };
     auto opWord = [&](int j, int w) -> int4 { return sops[(j / kOpSegment) & 1][(j % kOpSegment) * kOpWords + w]; };
-    auto stage = [&](int buf, int ma, int mb) {
+    auto stage = [&](int buf, int ma, int mb, int tt) {
+        if (tt >= 0) {
+            const real* src = A.ttTables + static_cast<size_t>(tt) * TTS;
 #pragma unroll
-        for (int c = tid; c < 2 * NCH; c += kPruneThreads) {
-            const int o = c >= NCH ? 1 : 0, cc = c - o * NCH;
-            cpAsync16(&sm[buf][o * MSZ + cc * CHUNK], A.mats + static_cast<size_t>(o ? mb : ma) * MSZ + cc * CHUNK);
+            for (int c = tid; c < TTS / CHUNK; c += kPruneThreads) cpAsync16(&sm[buf][c * CHUNK], src + c * CHUNK);
+        } else {
+#pragma unroll
+            for (int c = tid; c < 2 * NCH; c += kPruneThreads) {
+                const int o = c >= NCH ? 1 : 0, cc = c - o * NCH;
+                cpAsync16(&sm[buf][o * MSZ + cc * CHUNK], A.mats + static_cast<size_t>(o ? mb : ma) * MSZ + cc * CHUNK);
+            }
         }
         cpAsyncCommit();
     };
@@ -246,35 +301,31 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
         }
     };
+    // joins the (log sum, product) scaler of a finished child chain (rare: once per joined chain)
+    auto joinSlot = [&](int slot, double (&prod)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double a = sAcc[r][tid] + accMine[static_cast<size_t>(slot) * Ppad + r * G];
+            accumulateFactor(a, prod[r], prodMine[static_cast<size_t>(slot) * Ppad + r * G]);
+            sAcc[r][tid] = a;
+        }
+    };
 
     real X[R][4], Y[R][4];
     int sX[R], sY[R];
-    double acc[R], prod[R], pendAcc[R], pendProd[R];
+    double prod[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; pendAcc[r] = 0.0; pendProd[r] = 1.0; sX[r] = 0; sY[r] = 0; }
+    for (int r = 0; r < R; ++r) { sAcc[r][tid] = 0.0; prod[r] = 1.0; sX[r] = 0; sY[r] = 0; }
 
-    // ---- prologue: first operation's matrices, operands and sibling scalers
+    // ---- prologue: first operation's matrices and operands
     loadSegment(0);
     __syncthreads();
     {
         const int4 w0 = opWord(0, 0), w1 = opWord(0, 1);     // {dest,a,ma,b} {mb,sa,sb,flags}
-        stage(0, w0.z, w1.x);
+        stage(0, w0.z, w1.x, (w1.w & OP_TIPTIP) ? opWord(0, 2).y : -1);
         fetch(w0.y, X, sX);
         fetch(w0.w, Y, sY);
-        if (w1.y >= 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r] += accMine[static_cast<size_t>(w1.y) * Ppad + r * G];
-                prod[r] = prodMine[static_cast<size_t>(w1.y) * Ppad + r * G];
-            }
-        }
-        if (w1.z >= 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                pendAcc[r] = accMine[static_cast<size_t>(w1.z) * Ppad + r * G];
-                pendProd[r] = prodMine[static_cast<size_t>(w1.z) * Ppad + r * G];
-            }
-        }
+        if (w1.y >= 0) joinSlot(w1.y, prod);
     }
 
     for (int j = 0; j < nOps; ++j) {
@@ -287,95 +338,104 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         if (more) {
             n0 = opWord(j + 1, 0);
             n1 = opWord(j + 1, 1);
-            stage((j + 1) & 1, n0.z, n1.x);
+            stage((j + 1) & 1, n0.z, n1.x, (n1.w & OP_TIPTIP) ? opWord(j + 1, 2).y : -1);
         }
         const int flags = w1.w;
         const real* sa = sm[j & 1];
         const real* sb = sa + MSZ;
+        int sYc[R];                                          // this step's B tip states (sY is re-used by the prefetch)
+#pragma unroll
+        for (int r = 0; r < R; ++r) sYc[r] = sY[r];
 
-        // operand B -> factor, then its registers are free for the next step's B
-        real FB[R][4];
-        if (w0.w < nTips) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) factorTip<real, C>(sb, k, sY[r], FB[r]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) factorPartial<real, C>(sb, k, Y[r], FB[r]);
-        }
-        if (w1.z >= 0) {
+        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
+        if (flags & OP_TIPTIP) {
+            // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
+            if (more) fetch(n0.w, Y, sY);                    // sY consumed below via sYc
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                acc[r] += pendAcc[r];
-                accumulateFactor(acc[r], prod[r], pendProd[r]);
-            }
-        }
-        if (more) {
-            fetch(n0.w, Y, sY);
-            if (n1.z >= 0) {
+                const int combo = sX[r] * 5 + sYc[r];
+                const real* T = sa + (combo * C + k) * 4;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    pendAcc[r] = accMine[static_cast<size_t>(n1.z) * Ppad + r * G];
-                    pendProd[r] = prodMine[static_cast<size_t>(n1.z) * Ppad + r * G];
+                for (int i = 0; i < 4; ++i) X[r][i] = T[i];
+                st4(dest + r * (G * C * 4), X[r]);
+                const double m = static_cast<double>(sa[100 * C + combo]);
+                const double t = prod[r] * m;
+                if (t < 1e-200) {
+                    sAcc[r][tid] += foldedLog(prod[r], m);
+                    prod[r] = 1.0;
+                } else {
+                    prod[r] = t;
                 }
             }
-        }
-
-        // operand A -> factor, product, rescale, store
-        const bool aTip = (flags & OP_CHAIN_START) && w0.y < nTips;
-        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
+        } else {
+            // both factors and their product; afterwards X holds the unscaled result and Y is free
+            const bool aTip = (flags & OP_CHAIN_START) && w0.y < nTips;
+            const bool bTip = w0.w < nTips;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            real FA[4];
-            if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
-            else factorPartial<real, C>(sa, k, X[r], FA);
+            for (int r = 0; r < R; ++r) {
+                real FA[4], FB[4];
+                if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
+                else factorPartial<real, C>(sa, k, X[r], FA);
+                if (bTip) factorTip<real, C>(sb, k, sYc[r], FB);
+                else factorPartial<real, C>(sb, k, Y[r], FB);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) X[r][i] = FA[i] * FB[r][i];
-            if (flags & OP_RESCALE) {
-                real m = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
-#pragma unroll
-                for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-                if (m == real(0)) m = real(1);
-                const real inv = real(1) / m;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) X[r][i] *= inv;
-                accumulateFactor(acc[r], prod[r], static_cast<double>(m));
+                for (int i = 0; i < 4; ++i) X[r][i] = FA[i] * FB[i];
             }
-            st4(dest + r * (G * C * 4), X[r]);
+            if (w1.z >= 0) joinSlot(w1.z, prod);
+            // next step's operand B is requested now; the rescaling below hides its latency
+            if (more) fetch(n0.w, Y, sY);
+
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (flags & OP_RESCALE) {
+                    real m = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
+#pragma unroll
+                    for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+                    if (m == real(0)) m = real(1);
+                    const real inv = real(1) / m;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X[r][i] *= inv;
+                    // deferred log: multiply the maxima, fold into the log sum only before an underflow
+                    const double t = prod[r] * static_cast<double>(m);
+                    if (t < 1e-200) {
+                        sAcc[r][tid] += foldedLog(prod[r], static_cast<double>(m));
+                        prod[r] = 1.0;
+                    } else {
+                        prod[r] = t;
+                    }
+                }
+                st4(dest + r * (G * C * 4), X[r]);
+            }
         }
 
         if (flags & OP_CHAIN_END) {
             const int sOut = opWord(j, 2).x;
-            if (sOut >= 0) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (prod[r] < 1e-100) foldProduct(acc[r], prod[r], 1.0);   // so a parent's product of two stays normal
+            for (int r = 0; r < R; ++r) {
+                double a = sAcc[r][tid];
+                if (sOut >= 0) {
+                    if (prod[r] < 1e-100) {                 // keep a parent's product of two stored factors normal
+                        a += foldedLog(prod[r], 1.0);
+                        prod[r] = 1.0;
+                    }
                     if (k == 0) {
-                        accMine[static_cast<size_t>(sOut) * Ppad + r * G] = acc[r];
+                        accMine[static_cast<size_t>(sOut) * Ppad + r * G] = a;
                         prodMine[static_cast<size_t>(sOut) * Ppad + r * G] = prod[r];
                     }
                 }
-            }
-            if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && k == 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const double total = scalerTotal(acc[r], prod[r]);
+                if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && k == 0) {
+                    const double total = scalerTotal(a, prod[r]);
                     double* c = A.cum + p0 + r * G;
                     if (cumMode) *c = total;
                     else *c += total;
                 }
+                sAcc[r][tid] = 0.0;
+                prod[r] = 1.0;
             }
-#pragma unroll
-            for (int r = 0; r < R; ++r) { acc[r] = 0.0; prod[r] = 1.0; }
         }
         if (more && (n1.w & OP_CHAIN_START)) {
             fetch(n0.y, X, sX);
-            if (n1.y >= 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc[r] += accMine[static_cast<size_t>(n1.y) * Ppad + r * G];
-                    prod[r] = prodMine[static_cast<size_t>(n1.y) * Ppad + r * G];
-                }
-            }
+            if (n1.y >= 0) joinSlot(n1.y, prod);
         }
     }
 }

@@ -20,8 +20,20 @@ uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate) {
 static DevOp makeOp(int dest, int a, int ma, int b, int mb, int sa, int sb, int flags, int sOut) {
     DevOp d;
     d.dest = dest; d.a = a; d.ma = ma; d.b = b; d.mb = mb; d.sa = sa; d.sb = sb; d.flags = flags; d.sOut = sOut;
-    d.pad[0] = d.pad[1] = d.pad[2] = 0;
+    d.tt = -1;
+    d.pad[0] = d.pad[1] = 0;
     return d;
+}
+
+// Operations whose two operands are tips produce, per category, one of only 5x5 possible vectors
+// (and rescaling maxima): they get a table computed once per evaluation instead of per pattern.
+static void assignTipTipTables(Schedule& out, int tipCount) {
+    out.tipTipCount = 0;
+    for (DevOp& d : out.ops)
+        if ((d.flags & OP_CHAIN_START) && d.a >= 0 && d.a < tipCount && d.b < tipCount) {
+            d.flags |= OP_TIPTIP;
+            d.tt = out.tipTipCount++;
+        }
 }
 
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
@@ -98,6 +110,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             out.partialWrites += 1;
             if (accumulate && rescale) out.scalerRows += 2;
         }
+        assignTipTipTables(out, tipCount);
         return BEAGLE_SUCCESS;
     }
 
@@ -220,6 +233,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
         out.levels.push_back(L);
     }
     for (int o = 0; o < count; ++o) out.opChain[o] = chainNewId[out.opChain[o]];
+    assignTipTipTables(out, tipCount);
     return BEAGLE_SUCCESS;
 }
 

@@ -31,13 +31,15 @@ struct DevOp {
     int sb;      // subtree log-scaler slot to add for B, or -1
     int flags;   // OP_* bits
     int sOut;    // OP_CHAIN_END: slot receiving the chain's subtree log-scaler, or -1
-    int pad[3];
+    int tt;      // OP_TIPTIP: index of this operation's precomputed (stateA, stateB) table
+    int pad[2];
 };
 enum {
     OP_RESCALE = 1,        // destinationScaleWrite >= 0
     OP_CHAIN_START = 2,    // operand A comes from memory (tips or a finished buffer)
     OP_CHAIN_END = 4,      // last operation of its chain: emit the subtree log-scaler, reset
-    OP_ADD_TO_CUM = 8      // with OP_CHAIN_END: the chain total goes into the cumulative buffer
+    OP_ADD_TO_CUM = 8,     // with OP_CHAIN_END: the chain total goes into the cumulative buffer
+    OP_TIPTIP = 16         // both operands are tips: the result is one of 25 precomputed vectors per category
 };
 
 // Host-side view of a chain (device code only sees the flags above).
@@ -70,6 +72,7 @@ struct Schedule {
     std::vector<Group> groups;
     std::vector<int> rootSlots;     // slots of forest roots to fold into the cumulative buffer afterwards
     int slotCount = 0;              // subtree log-scaler slots needed
+    int tipTipCount = 0;            // operations with OP_TIPTIP (= number of tables)
     bool sequential = false;        // true: list was not a forest; one operation per launch
     // per input operation, for inspection / tests
     std::vector<int> opLevel, opChain;
