@@ -277,7 +277,7 @@ struct Engine {
     // possible otherwise (a group is a serial stream; fewer groups = less per-block set-up).
     int groupsPerLevel() const {
         const int tiles = Ppad / patternsPerBlock();
-        const int wantBlocks = 148 * 6;
+        const int wantBlocks = 148 * 16;      // >= 8 waves of 2 resident blocks per SM: the tail wave costs little
         return std::max(1, (wantBlocks + tiles - 1) / tiles);
     }
 

@@ -216,6 +216,26 @@ __device__ __forceinline__ void factorTip(const real* __restrict__ sm, int k, in
     for (int i = 0; i < 4; ++i) F[i] = T[i];
 }
 
+// Branch-free reciprocal for the rescaling (argument is a normal number in (0, ~1]; the caller routes
+// anything smaller than 1e-290 to an exact division): hardware seed + Newton steps, < 1 ulp error.
+// Branch-free matters: it lets the compiler interleave the R independent rescalings of a thread.
+__device__ __forceinline__ double fastRcp(double m) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(m));
+    double e = fma(-m, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-m, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-m, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ float fastRcp(float m) {
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(m));
+    const float e = fmaf(-m, x, 1.0f);
+    return fmaf(x, e, x);
+}
+
 // Rare path of the deferred log: fold the running product (and the factor that would have
 // underflowed it) into the log sum.  Kept out of line so the hot loop carries no log() code.
 __device__ __noinline__ double foldedLog(double prod, double factor) { return log(prod) + log(factor); }
@@ -348,63 +368,112 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         for (int r = 0; r < R; ++r) sYc[r] = sY[r];
 
         real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
+        double mfac[R];                                      // this step's rescaling maxima (1 when not rescaled)
         if (flags & OP_TIPTIP) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
-            if (more) fetch(n0.w, Y, sY);                    // sY consumed below via sYc
+            if (more) fetch(n0.w, Y, sY);                    // sY was saved in sYc above
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int combo = sX[r] * 5 + sYc[r];
                 const real* T = sa + (combo * C + k) * 4;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) X[r][i] = T[i];
-                st4(dest + r * (G * C * 4), X[r]);
-                const double m = static_cast<double>(sa[100 * C + combo]);
-                const double t = prod[r] * m;
-                if (t < 1e-200) {
-                    sAcc[r][tid] += foldedLog(prod[r], m);
-                    prod[r] = 1.0;
-                } else {
-                    prod[r] = t;
-                }
+                mfac[r] = static_cast<double>(sa[100 * C + combo]);
             }
         } else {
-            // both factors and their product; afterwards X holds the unscaled result and Y is free
-            const bool aTip = (flags & OP_CHAIN_START) && w0.y < nTips;
-            const bool bTip = w0.w < nTips;
+            // factor of operand A (from registers, or tip table at a chain start), then operand B
+            if ((flags & OP_CHAIN_START) && w0.y < nTips) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                real FA[4], FB[4];
-                if (aTip) factorTip<real, C>(sa, k, sX[r], FA);
-                else factorPartial<real, C>(sa, k, X[r], FA);
-                if (bTip) factorTip<real, C>(sb, k, sYc[r], FB);
-                else factorPartial<real, C>(sb, k, Y[r], FB);
+                for (int r = 0; r < R; ++r) factorTip<real, C>(sa, k, sX[r], X[r]);
+            } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) X[r][i] = FA[i] * FB[i];
+                for (int r = 0; r < R; ++r) {
+                    real F[4];
+                    factorPartial<real, C>(sa, k, X[r], F);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X[r][i] = F[i];
+                }
+            }
+            if (w0.w < nTips) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    real F[4];
+                    factorTip<real, C>(sb, k, sYc[r], F);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    real F[4];
+                    factorPartial<real, C>(sb, k, Y[r], F);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
+                }
             }
             if (w1.z >= 0) joinSlot(w1.z, prod);
             // next step's operand B is requested now; the rescaling below hides its latency
             if (more) fetch(n0.w, Y, sY);
 
+            if (flags & OP_RESCALE) {
+                // stage-major over the R patterns: R independent dependency chains, no branch in between
+                real m[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) m[r] = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
+#pragma unroll
+                for (int off = 1; off < C; off <<= 1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_xor_sync(0xffffffffu, m[r], off));
+                }
+                bool tiny = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    m[r] = (m[r] == real(0)) ? real(1) : m[r];
+                    tiny |= m[r] < real(1e-290);
+                }
+                real inv[R];
+                if (!tiny) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) inv[r] = fastRcp(m[r]);
+                } else {                                     // denormal-range maximum: exact division
+#pragma unroll
+                    for (int r = 0; r < R; ++r) inv[r] = real(1) / m[r];
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X[r][i] *= inv[r];
+                    mfac[r] = static_cast<double>(m[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) mfac[r] = 1.0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) st4(dest + r * (G * C * 4), X[r]);
+        {
+            // deferred log: multiply the maxima, fold into the log sum only before an underflow
+            double t[R];
+            bool low = false;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (flags & OP_RESCALE) {
-                    real m = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
+                t[r] = prod[r] * mfac[r];
+                low |= t[r] < 1e-200;
+            }
+            if (!low) {
 #pragma unroll
-                    for (int off = 1; off < C; off <<= 1) m = rmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-                    if (m == real(0)) m = real(1);
-                    const real inv = real(1) / m;
+                for (int r = 0; r < R; ++r) prod[r] = t[r];
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[r][i] *= inv;
-                    // deferred log: multiply the maxima, fold into the log sum only before an underflow
-                    const double t = prod[r] * static_cast<double>(m);
-                    if (t < 1e-200) {
-                        sAcc[r][tid] += foldedLog(prod[r], static_cast<double>(m));
+                for (int r = 0; r < R; ++r) {
+                    if (t[r] < 1e-200) {
+                        sAcc[r][tid] += foldedLog(prod[r], mfac[r]);
                         prod[r] = 1.0;
                     } else {
-                        prod[r] = t;
+                        prod[r] = t[r];
                     }
                 }
-                st4(dest + r * (G * C * 4), X[r]);
             }
         }
 
