@@ -36,7 +36,7 @@ struct CudaFail {
 static int g_device = 0;
 
 #ifndef SB200_BIG_R
-#define SB200_BIG_R 4
+#define SB200_BIG_R 2
 #endif
 constexpr int kBigR = SB200_BIG_R;   // patterns per thread of the streaming (large-P) pruning kernel
 

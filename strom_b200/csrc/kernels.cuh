@@ -260,11 +260,11 @@ constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 #define SB200_MINBLK_R1 3
 #endif
 #ifndef SB200_MINBLK_R2
-#define SB200_MINBLK_R2 2
+#define SB200_MINBLK_R2 3
 #endif
 
 template <typename real, int C, int R>
-__global__ void __launch_bounds__(kPruneThreads, R == 1 ? SB200_MINBLK_R1 : 2)
+__global__ void __launch_bounds__(kPruneThreads, R == 1 ? SB200_MINBLK_R1 : SB200_MINBLK_R2)
 prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
     constexpr int G = kPruneThreads / C;                 // patterns per pass
     constexpr int MSZ = kMatStride * C;                  // reals per operand image
