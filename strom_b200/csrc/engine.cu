@@ -49,7 +49,7 @@ struct Engine {
     int device = 0;
     bool fp32 = false;
     int nTips = 0, nPartials = 0, nCompact = 0, P = 0, nEigen = 0, nMat = 0, C = 0, nScale = 0;
-    int Ppad = 0;                         // pattern axis padded to a multiple of 1024 in every buffer
+    int Ppad = 0;                         // pattern axis padded to whole thread-block tiles in every buffer
     long long tipStride = 0;
     cudaStream_t ownStream = nullptr, stream = nullptr;
 
@@ -155,7 +155,12 @@ struct Engine {
         stream = ownStream;
         CK(cudaEventCreateWithFlags(&blockCopied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
-        Ppad = (P + 1023) & ~1023;       // = patterns per block of the widest kernel (C=1, R=4)
+        // pattern axis padded to a whole number of thread-block tiles of every kernel that walks it
+        // (pruning tile = patternsPerBlock(); generic / root kernels use 128- or 256/C-pattern tiles)
+        {
+            const int unit = std::max(patternsPerBlock(), 128);
+            Ppad = ((P + unit - 1) / unit) * unit;
+        }
         tipStride = Ppad;
         if (nTips > 0) {
             CK(cudaMalloc(&dTips, static_cast<size_t>(nTips) * tipStride));

@@ -7,7 +7,7 @@
 //   (c) root_loglik_kernel          : BeagleLib beagleCalculateEdgeLogLikelihoods
 //                                     (reference call site src/likelihood.hpp:418-447)
 //
-// HBM layout (pattern axis padded to Ppad = 1024-multiple, so no kernel needs tail predicates):
+// HBM layout (pattern axis padded to Ppad = whole thread-block tiles, so no kernel needs tail predicates):
 //   partials [buffer][Ppad][category][state]  one pattern x category = 4 reals = one 256-bit load (FP64)
 //   tips     [tip][Ppad]                      1-byte codes 0..4 (4 = missing; padding is 4)
 //   matrices [matrix][36*C]                   already in the shared-memory image the pruning kernel wants:

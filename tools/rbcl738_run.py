@@ -1,0 +1,31 @@
+"""Runs N evaluations of the rbcl738 fixture on the engine (for ncu launch lists / timing)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+from bench import gtr_gamma_model, PAUP_PI, PAUP_R, PAUP_ALPHA
+from strom_b200.engine import EvalArgs, ShardedLikelihood
+
+n_eval = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+fx = np.load(os.path.join(ROOT, "tests", "golden", "rbcl738.npz"))
+model = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA, 4)
+L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], 4, device=0)
+ea = EvalArgs(model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
+print("logL", L.calc_log_likelihood(ea))
+for _ in range(10):
+    L.replay_async()
+L.stream.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with torch.cuda.stream(L.stream):
+    e0.record()
+    for _ in range(n_eval):
+        L.replay_async()
+    e1.record()
+L.stream.synchronize()
+print("device us/eval", e0.elapsed_time(e1) * 1000 / n_eval)
+t0 = time.perf_counter()
+for _ in range(n_eval):
+    L.calc_log_likelihood(ea)
+print("fused call us/eval", (time.perf_counter() - t0) * 1e6 / n_eval)
+L.close()
