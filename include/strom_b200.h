@@ -57,8 +57,14 @@ STROM_API int sb200SetTipStatesU8(int instance, int tipIndex, const unsigned cha
 STROM_API int sb200Eval(int instance, const StromEvalArgs* args, double* outLogLikelihood);
 
 /* Same work, no host synchronisation: the pattern-weighted log-likelihood of this instance's
- * pattern slice is left in *deviceOut (a device pointer to one double) in stream order. */
+ * pattern slice is left in *deviceOut (a device pointer to one double) in stream order, or, when
+ * deviceOut is NULL, in the instance's own result slot, to be collected with sb200Finish. */
 STROM_API int sb200EvalAsync(int instance, const StromEvalArgs* args, double* deviceOut);
+
+/* Waits for the instance's stream and returns the scalar of the last evaluation that used the
+ * instance's own result slot (BEAGLE_ERROR_FLOATING_POINT if it is NaN).  With one instance per
+ * GPU, a host enqueues sb200EvalAsync on every shard and then collects with sb200Finish. */
+STROM_API int sb200Finish(int instance, double* outLogLikelihood);
 
 /* Re-run the last evaluation's device work (matrices, partials, root reduction) with the
  * parameters already resident in HBM; no host->device copy, no synchronisation.  Used by

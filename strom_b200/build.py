@@ -68,12 +68,54 @@ def build_oracle(force: bool = False) -> str:
     return ORACLE_LIB
 
 
+HOST_DIR = os.path.join(ROOT, "strom_b200", "host")
+HOST_LIB = os.path.join(HOST_DIR, "libstrom_host.so")
+HOST_ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "libstrom_host_oracle.so")
+GXX = "/usr/bin/g++"
+
+
+def host_sources():
+    hdrs = [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith((".hpp", ".cpp"))]
+    return hdrs + [os.path.join(ROOT, "include", f) for f in ("strom_beagle.h", "strom_b200.h")]
+
+
+def build_host(force: bool = False) -> str:
+    """C++ host mirror of the reference's Likelihood/Model/Data/Tree classes, linked to the CUDA engine."""
+    build_engine()
+    if force or _stale(HOST_LIB, host_sources() + [ENGINE_LIB]):
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-DSTROM_B200_ENGINE",
+               "-o", HOST_LIB, os.path.join(HOST_DIR, "capi.cpp"), "-L" + CSRC, "-lstrom_b200", "-Wl,-rpath,$ORIGIN/../csrc"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building libstrom_host.so failed")
+    return HOST_LIB
+
+
+def build_host_oracle(force: bool = False) -> str:
+    """TEST ONLY: the same host classes on the reference's 13-call path, linked to the CPU checker."""
+    build_oracle()
+    if force or _stale(HOST_ORACLE_LIB, host_sources() + [ORACLE_LIB]):
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
+               "-o", HOST_ORACLE_LIB, os.path.join(HOST_DIR, "capi.cpp"), "-L" + os.path.dirname(ORACLE_LIB),
+               "-loracle_beagle", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building the oracle-backed host library failed")
+    return HOST_ORACLE_LIB
+
+
 def build_all(force: bool = False, verbose: bool = False):
     build_engine(force, verbose)
     build_oracle(force)
+    build_host(force)
+    build_host_oracle(force)
 
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(ENGINE_LIB)
     print(ORACLE_LIB)
+    print(HOST_LIB)
+    print(HOST_ORACLE_LIB)

@@ -866,8 +866,12 @@ extern "C" int sb200Eval(int instance, const StromEvalArgs* args, double* outLog
 }
 
 extern "C" int sb200EvalAsync(int instance, const StromEvalArgs* args, double* deviceOut) {
-    if (!deviceOut) return BEAGLE_ERROR_OUT_OF_RANGE;
     return withEngine(instance, [&](Engine& E) { return evalCommon(E, args, deviceOut); });
+}
+
+extern "C" int sb200Finish(int instance, double* outLogLikelihood) {
+    if (!outLogLikelihood) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) { return E.readScalar(outLogLikelihood); });
 }
 
 extern "C" int sb200ReplayAsync(int instance, double* deviceOut) {

@@ -1,0 +1,108 @@
+"""ctypes face of the C++ host library (strom_b200/host/*.hpp): the mirror of the reference's
+Data / TreeManip / Model / Likelihood classes, linked to the CUDA engine (libstrom_host.so)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB = os.path.join(_HERE, "host", "libstrom_host.so")
+
+_IP = C.POINTER(C.c_int)
+_DP = C.POINTER(C.c_double)
+
+
+class HostError(RuntimeError):
+    pass
+
+
+class HostAPI:
+    def __init__(self, path: str = HOST_LIB):
+        if not os.path.exists(path):
+            raise FileNotFoundError("%s not found: run python -m strom_b200.build" % path)
+        self.lib = L = C.CDLL(path, mode=C.RTLD_LOCAL)
+        L.strom_data_from_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.strom_data_from_codes.argtypes = [C.c_int, C.c_int, _IP, C.c_int, C.c_char_p, C.c_int]
+        L.strom_data_dims.argtypes = [C.c_int, _IP, _IP, _IP]
+        L.strom_data_copy.argtypes = [C.c_int, _IP, _DP]
+        L.strom_data_free.argtypes = [C.c_int]
+        L.strom_tree_ops.argtypes = [C.c_char_p, _IP, _IP, _DP, _IP, _IP, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.strom_model_numbers.argtypes = [_DP, _DP, C.c_double, C.c_int, C.c_double, _DP, _DP, _DP, _DP, _DP, _IP, C.c_char_p, C.c_int]
+        L.strom_loglik.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, _IP, C.c_int, C.c_int,
+                                   _DP, _DP, C.c_char_p, C.c_int]
+        self._err = C.create_string_buffer(1024)
+
+    def _check(self, rc):
+        if rc < 0:
+            raise HostError(self._err.value.decode(errors="replace"))
+        return rc
+
+    # ---- Data ----------------------------------------------------------------------------
+    def data_from_file(self, path: str) -> int:
+        return self._check(self.lib.strom_data_from_file(path.encode(), self._err, 1024))
+
+    def data_from_codes(self, codes: np.ndarray, compress: bool = True) -> int:
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        return self._check(self.lib.strom_data_from_codes(codes.shape[0], codes.shape[1], codes.ctypes.data_as(_IP), int(compress),
+                                                          self._err, 1024))
+
+    def data_arrays(self, h: int):
+        n, p, s = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.strom_data_dims(h, C.byref(n), C.byref(p), C.byref(s)))
+        m = np.zeros((n.value, p.value), dtype=np.int32)
+        w = np.zeros(p.value)
+        self._check(self.lib.strom_data_copy(h, m.ctypes.data_as(_IP), w.ctypes.data_as(_DP)))
+        return m, w, s.value
+
+    def data_free(self, h: int):
+        self.lib.strom_data_free(h)
+
+    # ---- Tree / operations -----------------------------------------------------------------
+    def tree_ops(self, newick: str, max_leaves: int = 4096):
+        n = max_leaves
+        ops = np.zeros(7 * (n - 2), dtype=np.int32)
+        pidx = np.zeros(2 * n - 3, dtype=np.int32)
+        elen = np.zeros(2 * n - 3)
+        nl, par = C.c_int(), C.c_int()
+        out = C.create_string_buffer(64 * n)
+        self._check(self.lib.strom_tree_ops(newick.encode(), ops.ctypes.data_as(_IP), pidx.ctypes.data_as(_IP), elen.ctypes.data_as(_DP),
+                                            C.byref(nl), C.byref(par), out, 64 * n, self._err, 1024))
+        n = nl.value
+        return ops[:7 * (n - 2)].reshape(-1, 7).copy(), pidx[:2 * n - 3].copy(), elen[:2 * n - 3].copy(), par.value, out.value.decode()
+
+    # ---- Model -----------------------------------------------------------------------------
+    def model_numbers(self, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0) -> dict:
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        r = np.ascontiguousarray(rmat, dtype=np.float64)
+        evec, ivec, evals = np.zeros((4, 4)), np.zeros((4, 4)), np.zeros(4)
+        rates, probs = np.zeros(ncat + 1), np.zeros(ncat + 1)
+        nt = C.c_int()
+        self._check(self.lib.strom_model_numbers(f.ctypes.data_as(_DP), r.ctypes.data_as(_DP), shape, ncat, pinvar, evec.ctypes.data_as(_DP),
+                                                 ivec.ctypes.data_as(_DP), evals.ctypes.data_as(_DP), rates.ctypes.data_as(_DP),
+                                                 probs.ctypes.data_as(_DP), C.byref(nt), self._err, 1024))
+        return dict(freqs=f, evec=evec, ivec=ivec, evals=evals, rates=rates[:nt.value].copy(), probs=probs[:nt.value].copy())
+
+    # ---- Likelihood --------------------------------------------------------------------------
+    def loglik(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0, devices=(0,),
+               single: bool = False, repeats: int = 1):
+        """Likelihood::calcLogLikelihood through the C++ facade; returns (logL, seconds per evaluation)."""
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        r = np.ascontiguousarray(rmat, dtype=np.float64)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        out, sec = C.c_double(), C.c_double()
+        self._check(self.lib.strom_loglik(data_handle, newick.encode(), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP), shape, ncat, pinvar,
+                                          int(dev.size), dev.ctypes.data_as(_IP), int(single), repeats, C.byref(out), C.byref(sec),
+                                          self._err, 1024))
+        return out.value, sec.value
+
+
+_host = None
+
+
+def host() -> HostAPI:
+    global _host
+    if _host is None:
+        _host = HostAPI()
+    return _host

@@ -1,0 +1,185 @@
+// capi.cpp -- plain C entry points over the host classes, for Python (ctypes) tests and bench.py.
+// Built twice: libstrom_host.so (-DSTROM_B200_ENGINE, linked to libstrom_b200.so: the product) and,
+// for the test-suite only, a variant linked to the CPU checker (same code, 13-call path).
+#include <chrono>
+#include <cstring>
+#include <mutex>
+
+#include "likelihood.hpp"
+#include "tree_manip.hpp"
+
+namespace strom {
+struct LikelihoodInspector {
+    static void operations(Likelihood& L, Tree::SharedPtr t, unsigned ntaxa, std::vector<int>& ops, std::vector<int>& pidx,
+                           std::vector<double>& elen) {
+        L._ntaxa = ntaxa;
+        L.defineOperations(t);
+        ops = L._operations;
+        pidx = L._pmatrix_index;
+        elen = L._edge_lengths;
+    }
+};
+struct ModelInspector {
+    static void eigen(const Model& m, double* evec, double* ivec, double* evals) {
+        std::memcpy(evec, m._eigenvectors, sizeof(double) * 16);
+        std::memcpy(ivec, m._inverse_eigenvectors, sizeof(double) * 16);
+        std::memcpy(evals, m._eigenvalues, sizeof(double) * 4);
+    }
+};
+}  // namespace strom
+
+using namespace strom;
+
+#define HOST_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+std::mutex g_mu;
+std::vector<Data::SharedPtr> g_data;
+
+int fail(const std::exception& e, char* err, int errlen) {
+    if (err && errlen > 0) {
+        std::strncpy(err, e.what(), static_cast<size_t>(errlen) - 1);
+        err[errlen - 1] = 0;
+    }
+    return -1;
+}
+Data::SharedPtr dataOf(int h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h < 0 || h >= static_cast<int>(g_data.size()) || !g_data[h]) throw XStrom("bad data handle");
+    return g_data[h];
+}
+int keep(Data::SharedPtr d) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_data.push_back(d);
+    return static_cast<int>(g_data.size()) - 1;
+}
+Model::SharedPtr makeModel(const double* freqs, const double* rmat, double shape, int ncat, double pinvar) {
+    Model::SharedPtr m(new Model());
+    m->setExchangeabilitiesAndStateFreqs(std::vector<double>(rmat, rmat + 6), std::vector<double>(freqs, freqs + 4));
+    m->setGammaShape(shape);
+    m->setGammaNCateg(static_cast<unsigned>(ncat));
+    if (pinvar > 0.0) m->setPinvar(pinvar);
+    return m;
+}
+}  // namespace
+
+HOST_API int strom_data_from_file(const char* path, char* err, int errlen) {
+    try {
+        Data::SharedPtr d(new Data());
+        d->getDataFromFile(path);
+        return keep(d);
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+// codes: [ntaxa][nsites] ints (0..3, >= 4 missing / ambiguity)
+HOST_API int strom_data_from_codes(int ntaxa, int nsites, const int* codes, int compress, char* err, int errlen) {
+    try {
+        Data::taxon_names_t names;
+        Data::data_matrix_t m(static_cast<size_t>(ntaxa));
+        for (int t = 0; t < ntaxa; ++t) {
+            names.push_back("taxon" + std::to_string(t + 1));
+            m[t].assign(codes + static_cast<size_t>(t) * nsites, codes + static_cast<size_t>(t + 1) * nsites);
+        }
+        Data::SharedPtr d(new Data());
+        d->setDataMatrix(names, m, compress != 0);
+        return keep(d);
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+HOST_API int strom_data_dims(int h, int* ntaxa, int* npatterns, int* nsites) {
+    try {
+        Data::SharedPtr d = dataOf(h);
+        *ntaxa = static_cast<int>(d->getNumTaxa());
+        *npatterns = static_cast<int>(d->getNumPatterns());
+        *nsites = static_cast<int>(d->getSeqLen());
+        return 0;
+    } catch (...) { return -1; }
+}
+
+HOST_API int strom_data_copy(int h, int* matrix, double* counts) {
+    try {
+        Data::SharedPtr d = dataOf(h);
+        const unsigned P = d->getNumPatterns();
+        for (unsigned t = 0; t < d->getNumTaxa(); ++t)
+            std::memcpy(matrix + static_cast<size_t>(t) * P, d->getDataMatrix()[t].data(), sizeof(int) * P);
+        std::memcpy(counts, d->getPatternCounts().data(), sizeof(double) * P);
+        return 0;
+    } catch (...) { return -1; }
+}
+
+HOST_API int strom_data_free(int h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h < 0 || h >= static_cast<int>(g_data.size())) return -1;
+    g_data[h].reset();
+    return 0;
+}
+
+// Operation list, matrix indices and edge lengths Likelihood::defineOperations builds for a newick
+// (ntaxa = number of leaves).  Arrays must hold 7*(n-2), 2n-3 and 2n-3 entries.  newick_out (may be NULL)
+// receives TreeManip::makeNewick(6) of the re-rooted tree.
+HOST_API int strom_tree_ops(const char* newick, int* ops, int* pidx, double* elen, int* nleaves, int* parent, char* newick_out,
+                            int newick_len, char* err, int errlen) {
+    try {
+        TreeManip tm;
+        tm.buildFromNewick(newick, false, false);
+        Tree::SharedPtr t = tm.getTree();
+        Likelihood L;
+        std::vector<int> o, p;
+        std::vector<double> e;
+        LikelihoodInspector::operations(L, t, t->numLeaves(), o, p, e);
+        if (ops) std::memcpy(ops, o.data(), sizeof(int) * o.size());
+        if (pidx) std::memcpy(pidx, p.data(), sizeof(int) * p.size());
+        if (elen) std::memcpy(elen, e.data(), sizeof(double) * e.size());
+        *nleaves = static_cast<int>(t->numLeaves());
+        *parent = 2 * static_cast<int>(t->numLeaves()) - 3;
+        if (newick_out && newick_len > 0) {
+            const std::string s = tm.makeNewick(6);
+            std::strncpy(newick_out, s.c_str(), static_cast<size_t>(newick_len) - 1);
+            newick_out[newick_len - 1] = 0;
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+// Model numbers exactly as the facade uploads them.  rates/probs need ncat (+1 with pinvar > 0) entries.
+HOST_API int strom_model_numbers(const double* freqs, const double* rmat, double shape, int ncat, double pinvar, double* evec, double* ivec,
+                                 double* evals, double* rates, double* probs, int* ncat_total, char* err, int errlen) {
+    try {
+        Model::SharedPtr m = makeModel(freqs, rmat, shape, ncat, pinvar);
+        const std::vector<double> r = m->getDiscreteGammaRelRates(), w = m->getDiscreteGammaRateProbs();
+        *ncat_total = static_cast<int>(r.size());
+        std::memcpy(rates, r.data(), sizeof(double) * r.size());
+        std::memcpy(probs, w.data(), sizeof(double) * w.size());
+        ModelInspector::eigen(*m, evec, ivec, evals);
+        return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+// Builds Data/Tree/Model/Likelihood and evaluates `repeats` times (parameters re-uploaded every time,
+// scalar back on the host every time).  devices: GPUs to shard the patterns over.
+HOST_API int strom_loglik(int data_handle, const char* newick, const double* freqs, const double* rmat, double shape, int ncat,
+                          double pinvar, int ndevices, const int* devices, int single, int repeats, double* logl,
+                          double* seconds_per_eval, char* err, int errlen) {
+    try {
+        Data::SharedPtr d = dataOf(data_handle);
+        TreeManip tm;
+        tm.buildFromNewick(newick, false, false);
+        Likelihood::SharedPtr L(new Likelihood());
+        L->setQuiet(true);
+        L->setData(d);
+        L->setModel(makeModel(freqs, rmat, shape, ncat, pinvar));
+        if (ndevices > 0) L->setDevices(std::vector<int>(devices, devices + ndevices));
+        if (single) L->setSinglePrecision(true);
+        double v = L->calcLogLikelihood(tm.getTree());
+        if (repeats > 1) {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 1; i < repeats; ++i) v = L->calcLogLikelihood(tm.getTree());
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (seconds_per_eval) *seconds_per_eval = dt / (repeats - 1);
+        } else if (seconds_per_eval) {
+            *seconds_per_eval = 0.0;
+        }
+        *logl = v;
+        return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}

@@ -1,0 +1,379 @@
+// likelihood.hpp -- the Likelihood facade Chain and every Updater drive (same class surface as
+// reference src/likelihood.hpp:15-63): setData / setModel / useStoredData / availableResources /
+// calcLogLikelihood(Tree).  Behind it sits any library exporting the 13 BeagleLib-compatible calls
+// of include/strom_beagle.h; the product links libstrom_b200.so (CUDA, no CPU fallback).
+//
+// What changes relative to the reference (BASELINE north-star):
+//   * the instance lives on a GPU: partials, matrices, scalers and byte-coded tips stay in HBM;
+//   * with STROM_B200_ENGINE defined, one evaluation is ONE fused engine call (sb200EvalAsync) per
+//     pattern shard instead of 9 BeagleLib calls, and site patterns can be sharded over several
+//     GPUs (setDevices): every shard holds all partials of its slice and the only exchange is the
+//     sum of one double per shard, added on the host in rank order (deterministic);
+//   * without that macro the facade issues exactly the reference's call sequence
+//     (src/likelihood.hpp:409-447), which is how the tests run it against the CPU checker.
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/strom_beagle.h"
+#ifdef STROM_B200_ENGINE
+#include "../../include/strom_b200.h"
+#endif
+#include "data.hpp"
+#include "model.hpp"
+#include "tree.hpp"
+#include "xstrom.hpp"
+
+namespace strom {
+
+class Likelihood {
+    friend struct LikelihoodInspector;   // test hook: reads the operation list (capi.cpp)
+
+  public:
+    Likelihood();
+    ~Likelihood();
+
+    void useStoredData(bool using_data) { _using_data = using_data; }
+    std::string availableResources();
+    double calcLogLikelihood(Tree::SharedPtr t);
+
+    void setData(Data::SharedPtr d);
+    Data::SharedPtr getData() { return _data; }
+    void setModel(Model::SharedPtr model);
+    Model::SharedPtr getModel() { return _model; }
+
+    // ---- B200 additions -------------------------------------------------------------------
+    // GPUs to shard the site patterns over (default: device 0 only).  Call before the first evaluation.
+    void setDevices(const std::vector<int>& devices);
+    void setSinglePrecision(bool on);         // FP32 partials / matrices variant (scalers stay FP64)
+    void setQuiet(bool quiet) { _quiet = quiet; }
+    unsigned numShards() const { return static_cast<unsigned>(_instances.size()); }
+
+    typedef std::shared_ptr<Likelihood> SharedPtr;
+
+  private:
+    void initBeagleLib();
+    void finalizeInstances();
+    void setTipStates();
+    void setPatternWeights();
+    void setDiscreteGammaShape();
+    void setModelRateMatrix();
+    void defineOperations(Tree::SharedPtr t);
+    void updateTransitionMatrices();
+    void calculatePartials();
+    std::string errorText(int code) const;
+
+    std::vector<int> _instances;       // one engine instance per pattern shard
+    std::vector<int> _devices;
+    std::map<int, std::string> _beagle_error;
+    std::vector<int> _operations;
+    std::vector<int> _pmatrix_index;
+    std::vector<double> _edge_lengths;
+
+    Data::SharedPtr _data;
+    Model::SharedPtr _model;
+    unsigned _ntaxa;
+    unsigned _nstates;
+    unsigned _npatterns;
+    bool _rooted;
+    bool _prefer_gpu;
+    bool _single;
+    bool _quiet;
+    bool _using_data;
+};
+
+inline Likelihood::Likelihood()
+    : _ntaxa(0), _nstates(0), _npatterns(0), _rooted(false), _prefer_gpu(true), _single(false), _quiet(false), _using_data(true) {
+    _model = Model::SharedPtr(new Model());
+    _devices.assign(1, 0);
+    // BeagleLib error codes, so that useful messages reach the user (reference src/likelihood.hpp:79-87)
+    _beagle_error[0] = "success";
+    _beagle_error[-1] = "unspecified error";
+    _beagle_error[-2] = "not enough memory could be allocated";
+    _beagle_error[-3] = "unspecified exception";
+    _beagle_error[-4] = "the instance index is out of range, or the instance has not been created";
+    _beagle_error[-5] = "one of the indices specified exceeded the range of the array";
+    _beagle_error[-6] = "no resource matches requirements";
+    _beagle_error[-7] = "no implementation matches requirements";
+    _beagle_error[-8] = "floating-point range exceeded";
+}
+
+inline std::string Likelihood::errorText(int code) const {
+    std::map<int, std::string>::const_iterator it = _beagle_error.find(code);
+    return "BeagleLib error code was " + std::to_string(code) + " (" + (it == _beagle_error.end() ? std::string("?") : it->second) + ")";
+}
+
+inline void Likelihood::finalizeInstances() {
+    for (int inst : _instances) {
+        const int code = beagleFinalizeInstance(inst);
+        if (code != 0) throw XStrom("Likelihood failed to finalize BeagleLib instance. " + errorText(code));
+    }
+    _instances.clear();
+}
+
+inline Likelihood::~Likelihood() {
+    for (int inst : _instances) {
+        const int code = beagleFinalizeInstance(inst);
+        if (code != 0) std::cerr << "Likelihood destructor failed to finalize BeagleLib instance. " << errorText(code) << std::endl;
+    }
+}
+
+inline std::string Likelihood::availableResources() {
+    BeagleResourceList* rsrcList = beagleGetResourceList();
+    std::string s;
+    for (int i = 0; i < rsrcList->length; ++i) {
+        std::string desc = rsrcList->list[i].description ? rsrcList->list[i].description : "";
+        while (!desc.empty() && desc.back() == ' ') desc.pop_back();
+        s += std::to_string(i) + ": " + rsrcList->list[i].name;
+        if (!desc.empty()) s += " (" + desc + ")";
+        s += "\n";
+    }
+    return s;
+}
+
+inline void Likelihood::setData(Data::SharedPtr data) {
+    _data = data;
+    if (!_instances.empty()) {       // instance exists: re-create it for the new data (reference :124-138)
+        finalizeInstances();
+        initBeagleLib();
+    }
+}
+
+inline void Likelihood::setModel(Model::SharedPtr model) {
+    _model = model;
+    if (!_instances.empty()) {       // category count is fixed at creation (reference :140-153, :206)
+        finalizeInstances();
+        initBeagleLib();
+    }
+}
+
+inline void Likelihood::setDevices(const std::vector<int>& devices) {
+    if (devices.empty()) throw XStrom("setDevices needs at least one device");
+    _devices = devices;
+    if (!_instances.empty()) {
+        finalizeInstances();
+        initBeagleLib();
+    }
+}
+
+inline void Likelihood::setSinglePrecision(bool on) {
+    _single = on;
+    if (!_instances.empty()) {
+        finalizeInstances();
+        initBeagleLib();
+    }
+}
+
+inline void Likelihood::initBeagleLib() {
+    if (!_instances.empty()) return;     // no-op once created
+    assert(_data);
+    _ntaxa = _data->getNumTaxa();
+    _npatterns = _data->getNumPatterns();
+    _nstates = 4;
+    _rooted = false;
+    if (!_quiet) {
+        std::cout << "Sequence length:    " << _data->getSeqLen() << std::endl;
+        std::cout << "Number of taxa:     " << _ntaxa << std::endl;
+        std::cout << "Number of patterns: " << _npatterns << std::endl;
+    }
+    const unsigned num_internals = _rooted ? (_ntaxa - 1) : (_ntaxa - 2);
+    const unsigned num_transition_probs = _rooted ? (2 * _ntaxa - 2) : (2 * _ntaxa - 3);
+
+    long requirementFlags = (_single ? BEAGLE_FLAG_PRECISION_SINGLE : BEAGLE_FLAG_PRECISION_DOUBLE) | BEAGLE_FLAG_SCALING_MANUAL;
+    long preferenceFlags = _prefer_gpu ? BEAGLE_FLAG_PROCESSOR_GPU : BEAGLE_FLAG_PROCESSOR_CPU;
+
+    const unsigned nshards = std::min<unsigned>(static_cast<unsigned>(_devices.size()), std::max(1u, _npatterns));
+    for (unsigned r = 0; r < nshards; ++r) {
+        unsigned lo, hi;
+        Data::sliceBounds(_npatterns, r, nshards, lo, hi);
+        int resource = _devices[r];
+        BeagleInstanceDetails details;
+        const int inst = beagleCreateInstance(_ntaxa,                 // tips
+                                              num_internals,          // partials
+                                              _ntaxa,                 // sequences
+                                              _nstates,               // states
+                                              hi - lo,                // patterns (this shard's slice)
+                                              1,                      // models
+                                              num_transition_probs,   // transition matrices
+                                              _model->_num_categ,     // rate categories
+                                              num_internals + 1,      // scale buffers
+                                              &resource, 1,           // device of this shard
+                                              preferenceFlags, requirementFlags, &details);
+        if (inst < 0) {
+            for (int i : _instances) beagleFinalizeInstance(i);
+            _instances.clear();
+            throw XStrom("Likelihood init function failed to create Likelihood instance (" + errorText(inst) + ")");
+        }
+        _instances.push_back(inst);
+    }
+    setTipStates();
+    setPatternWeights();
+}
+
+inline void Likelihood::setTipStates() {
+    assert(_data);
+    const unsigned nshards = numShards();
+    for (unsigned r = 0; r < nshards; ++r) {
+        unsigned lo, hi;
+        Data::sliceBounds(_npatterns, r, nshards, lo, hi);
+        for (unsigned t = 0; t < _ntaxa; ++t) {
+#ifdef STROM_B200_ENGINE
+            const std::vector<unsigned char> codes = _data->packTipCodes(t, lo, hi);
+            const int code = sb200SetTipStatesU8(_instances[r], static_cast<int>(t), codes.data());
+#else
+            const Data::pattern_t& row = _data->getDataMatrix()[t];
+            const int code = beagleSetTipStates(_instances[r], static_cast<int>(t), &row[lo]);
+#endif
+            if (code != 0)
+                throw XStrom("failed to set tip state for taxon " + std::to_string(t + 1) + " (\"" + _data->getTaxonNames()[t] + "\"; " +
+                             errorText(code) + ")");
+        }
+    }
+}
+
+inline void Likelihood::setPatternWeights() {
+    assert(_data);
+    const Data::pattern_counts_t& v = _data->getPatternCounts();
+    if (v.empty()) throw XStrom("failed to set pattern weights because data matrix has empty pattern count vector");
+    const unsigned nshards = numShards();
+    for (unsigned r = 0; r < nshards; ++r) {
+        unsigned lo, hi;
+        Data::sliceBounds(_npatterns, r, nshards, lo, hi);
+        const int code = beagleSetPatternWeights(_instances[r], &v[lo]);
+        if (code != 0) throw XStrom("failed to set pattern weights. " + errorText(code));
+    }
+}
+
+inline void Likelihood::setDiscreteGammaShape() {
+    for (int inst : _instances) {
+        int code = _model->setBeagleAmongSiteRateVariationRates(inst);
+        if (code != 0) throw XStrom("failed to set category rates. " + errorText(code));
+        code = _model->setBeagleAmongSiteRateVariationProbs(inst);
+        if (code != 0) throw XStrom("failed to set category probabilities. " + errorText(code));
+    }
+}
+
+inline void Likelihood::setModelRateMatrix() {
+    for (int inst : _instances) {
+        int code = _model->setBeagleStateFrequencies(inst);
+        if (code != 0) throw XStrom("failed to set state frequencies. " + errorText(code));
+        code = _model->setBeagleEigenDecomposition(inst);
+        if (code != 0) throw XStrom("failed to set eigen decomposition. " + errorText(code));
+        code = _model->setBeagleAmongSiteRateVariationRates(inst);
+        if (code != 0) throw XStrom("failed to set among-site rate variation rates. " + errorText(code));
+        code = _model->setBeagleAmongSiteRateVariationProbs(inst);
+        if (code != 0) throw XStrom("failed to set among-site rate variation weights. " + errorText(code));
+    }
+}
+
+// Children before parents (reverse level order), one 7-int operation per internal node; the matrix of
+// every node's edge is indexed by the node's number, except that the last entry -- preorder[0], whose
+// number 2n-3 is out of range -- uses the root tip's number (reference src/likelihood.hpp:296-355).
+inline void Likelihood::defineOperations(Tree::SharedPtr t) {
+    _operations.clear();
+    _pmatrix_index.clear();
+    _edge_lengths.clear();
+    for (size_t i = t->_levelorder.size(); i-- > 0;) {
+        Node* nd = t->_levelorder[i];
+        assert(nd->_number >= 0);
+        _pmatrix_index.push_back(nd->_number);
+        _edge_lengths.push_back(nd->_edge_length);
+        if (nd->_left_child) {
+            assert(nd->_left_child->_right_sib);
+            _operations.push_back(nd->_number);                          // destination partials
+            _operations.push_back(nd->_number - static_cast<int>(_ntaxa) + 1);   // scaling buffer to write
+            _operations.push_back(BEAGLE_OP_NONE);                       // scaling buffer to read
+            _operations.push_back(nd->_left_child->_number);             // left child partials
+            _operations.push_back(nd->_left_child->_number);             // left child transition matrix
+            _operations.push_back(nd->_left_child->_right_sib->_number); // right child partials (binary tree)
+            _operations.push_back(nd->_left_child->_right_sib->_number); // right child transition matrix
+        }
+    }
+    if (!t->_is_rooted) _pmatrix_index[_pmatrix_index.size() - 1] = t->_root->_number;
+}
+
+inline void Likelihood::updateTransitionMatrices() {
+    for (int inst : _instances) {
+        const int code = beagleUpdateTransitionMatrices(inst, 0, &_pmatrix_index[0], NULL, NULL, &_edge_lengths[0],
+                                                        static_cast<int>(_pmatrix_index.size()));
+        if (code != 0) throw XStrom("failed to update transition matrices. " + errorText(code));
+    }
+}
+
+inline void Likelihood::calculatePartials() {
+    const int totalOperations = static_cast<int>(_operations.size() / 7);
+    for (int inst : _instances) {
+        int code = beagleResetScaleFactors(inst, 0);
+        if (code != 0) throw XStrom("failed to reset scale factors in calculatePartials. " + errorText(code));
+        code = beagleUpdatePartials(inst, reinterpret_cast<BeagleOperation*>(&_operations[0]), totalOperations, 0);
+        if (code != 0) throw XStrom("failed to update partials. " + errorText(code));
+    }
+}
+
+inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
+    if (!_using_data) return 0.0;
+    if (t->_is_rooted) throw XStrom("can only compute likelihoods for unrooted trees currently");
+    if (!_data) throw XStrom("must call setData before calcLogLikelihood");
+
+    initBeagleLib();   // no-op if valid instances already exist
+
+    // "root" is leaf 0 and has exactly one child
+    assert(t->_root->_number == 0 && t->_root->_left_child == t->_preorder[0] && !t->_preorder[0]->_right_sib);
+
+    defineOperations(t);
+    assert(_pmatrix_index.size() == _edge_lengths.size());
+    int index_focal_child = t->_root->_number;           // the root tip
+    int index_focal_parent = t->_preorder[0]->_number;   // its only child
+    double log_likelihood = 0.0;
+
+#ifdef STROM_B200_ENGINE
+    // one fused call per shard (asynchronous), then the scalars are added in shard order
+    StromEvalArgs args;
+    args.stateFrequencies = &_model->_state_freqs[0];
+    args.eigenVectors = _model->_eigenvectors;
+    args.inverseEigenVectors = _model->_inverse_eigenvectors;
+    args.eigenValues = _model->_eigenvalues;
+    args.categoryRates = &_model->_relative_rates[0];
+    args.categoryWeights = &_model->_rate_probs[0];
+    args.matrixIndices = &_pmatrix_index[0];
+    args.edgeLengths = &_edge_lengths[0];
+    args.edgeCount = static_cast<int>(_pmatrix_index.size());
+    args.operations = reinterpret_cast<const BeagleOperation*>(&_operations[0]);
+    args.operationCount = static_cast<int>(_operations.size() / 7);
+    args.rootParentBuffer = index_focal_parent;
+    args.rootChildBuffer = index_focal_child;
+    args.rootMatrix = index_focal_child;
+    for (int inst : _instances) {
+        const int code = sb200EvalAsync(inst, &args, NULL);
+        if (code != 0) throw XStrom("failed to evaluate the likelihood on the engine. " + errorText(code));
+    }
+    for (int inst : _instances) {
+        double part = 0.0;
+        const int code = sb200Finish(inst, &part);
+        if (code != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(code));
+        log_likelihood += part;
+    }
+#else
+    setModelRateMatrix();
+    setDiscreteGammaShape();
+    updateTransitionMatrices();
+    calculatePartials();
+    int stateFrequencyIndex = 0, categoryWeightsIndex = 0, cumulativeScalingIndex = 0;
+    for (int inst : _instances) {
+        double part = 0.0;
+        const int code = beagleCalculateEdgeLogLikelihoods(inst, &index_focal_parent, &index_focal_child, &index_focal_child, NULL, NULL,
+                                                           &categoryWeightsIndex, &stateFrequencyIndex, &cumulativeScalingIndex, 1, &part,
+                                                           NULL, NULL);
+        if (code != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(code));
+        log_likelihood += part;
+    }
+#endif
+    return log_likelihood;
+}
+
+}  // namespace strom

@@ -57,11 +57,12 @@ def main():
     api = BeagleAPI(build_oracle())
     for key, (nex, tre) in FIXTURES.items():
         names, data, counts, nsites = H.read_nexus_data(os.path.join(REF, nex))
-        tree = H.build_tree(H.read_nexus_trees(os.path.join(REF, tre))[0])
+        newick = H.read_nexus_trees(os.path.join(REF, tre))[0]
+        tree = H.build_tree(newick)
         ops, pidx, elen = H.define_operations(tree)
         n, P = data.shape
         out = dict(data=data.astype(np.uint8), counts=counts, ops=ops, pmatrix_index=pidx, edge_lengths=elen,
-                   parent=np.int32(tree.preorder[0].number), nsites=np.int32(nsites))
+                   parent=np.int32(tree.preorder[0].number), nsites=np.int32(nsites), newick=np.array(newick))
         for mname in MODELS:
             m = model_dict(mname)
             inst = api.create(n, P, len(m["rates"]))
