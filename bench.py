@@ -149,8 +149,8 @@ def synthetic_inputs(args, rank, world, device):
     from strom_b200 import synth
     tree = synth.RandomTree(args.taxa, seed=1, mean_edge=0.05)
     model = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA, 4)
-    P = args.patterns
-    lo, hi = rank * P // world, (rank + 1) * P // world
+    from strom_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(args.patterns, rank, world)
     tips = synth.simulate_alignment(tree, model, lo, hi, seed=3, device=device)
     tips_h = tips.cpu().numpy()
     del tips

@@ -13,6 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import beagle
+from .sharding import sum_over_ranks
 
 _DP = C.POINTER(C.c_double)
 _IP = C.POINTER(C.c_int)
@@ -140,13 +141,13 @@ class ShardedLikelihood:
         self.E.check(self.E.sb200EvalAsync(self.inst, C.byref(args.c), C.c_void_p(self.out.data_ptr())), "evaluate")
         if self.distributed:
             with self.torch.cuda.stream(self.stream):
-                self.torch.distributed.all_reduce(self.out)
+                sum_over_ranks(self.out)
 
     def replay_async(self):
         self.E.check(self.E.sb200ReplayAsync(self.inst, C.c_void_p(self.out.data_ptr())), "replay")
         if self.distributed:
             with self.torch.cuda.stream(self.stream):
-                self.torch.distributed.all_reduce(self.out)
+                sum_over_ranks(self.out)
 
     def calc_log_likelihood(self, args: EvalArgs) -> float:
         self.eval_async(args)
