@@ -110,6 +110,10 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
 }
+// Asks the memory system to bring `bytes` (multiple of 16) at `gmemSrc` into L2; no destination, no wait.
+__device__ __forceinline__ void bulkPrefetchL2(const void* gmemSrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmemSrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -254,6 +258,10 @@ __device__ __forceinline__ void accumulateFactor(double& acc, double& prod, doub
 }
 
 constexpr int kOpSegment = 32;                 // operations staged in shared memory at a time (x2 buffers)
+#ifndef SB200_PREFETCH_AHEAD
+#define SB200_PREFETCH_AHEAD 3
+#endif
+constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;              // steps between an operand tile's L2 prefetch and its register load
 constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 
 #ifndef SB200_MINBLK_R1
@@ -321,21 +329,55 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
         }
     };
-    // joins the (log sum, product) scaler of a finished child chain (rare: once per joined chain)
-    auto joinSlot = [&](int slot, double (&prod)[R]) {
+    // joins the (log sum, product) scaler of a finished child chain
+    auto joinValues = [&](const double (&a)[R], const double (&pr)[R], double (&prod)[R]) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            double a = sAcc[r][tid] + accMine[static_cast<size_t>(slot) * Ppad + r * G];
-            accumulateFactor(a, prod[r], prodMine[static_cast<size_t>(slot) * Ppad + r * G]);
-            sAcc[r][tid] = a;
+            double acc = sAcc[r][tid] + a[r];
+            accumulateFactor(acc, prod[r], pr[r]);
+            sAcc[r][tid] = acc;
+        }
+    };
+    auto loadSlot = [&](int slot, double (&a)[R], double (&pr)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            a[r] = accMine[static_cast<size_t>(slot) * Ppad + r * G];
+            pr[r] = prodMine[static_cast<size_t>(slot) * Ppad + r * G];
+        }
+    };
+    auto joinSlot = [&](int slot, double (&prod)[R]) {
+        double a[R], pr[R];
+        loadSlot(slot, a, pr);
+        joinValues(a, pr, prod);
+    };
+    // L2 prefetch of the operand tiles an operation will read (one bulk request per tile, one thread):
+    // issued kPrefetchAhead steps early so the register prefetch one step ahead finds the data in L2
+    constexpr unsigned TILE_BYTES = G * R * C * 4 * sizeof(real);
+    auto prefetchOperands = [&](int j) {
+        const int4 w0 = opWord(j, 0), w1 = opWord(j, 1);
+        const size_t tile0 = static_cast<size_t>(blockIdx.x) * (G * R);          // first pattern of this block's tile
+        const real* ptile = A.partials + tile0 * C * 4;
+        auto operand = [&](int src) {
+            if (src >= nTips) bulkPrefetchL2(ptile + static_cast<size_t>(src - nTips) * bufStride, TILE_BYTES);
+            else bulkPrefetchL2(A.tips + static_cast<size_t>(src) * A.tipStride + tile0, G * R);
+        };
+        auto slot = [&](int sl) {
+            bulkPrefetchL2(A.slotAcc + static_cast<size_t>(sl) * Ppad + tile0, G * R * 8);
+            bulkPrefetchL2(A.slotProd + static_cast<size_t>(sl) * Ppad + tile0, G * R * 8);
+        };
+        operand(w0.w);
+        if (w1.z >= 0) slot(w1.z);
+        if (w1.w & OP_CHAIN_START) {
+            operand(w0.y);
+            if (w1.y >= 0) slot(w1.y);
         }
     };
 
     real X[R][4], Y[R][4];
     int sX[R], sY[R];
-    double prod[R];
+    double prod[R], pendAcc[R], pendProd[R];             // pend*: scaler of the next step's sibling chain, if any
 #pragma unroll
-    for (int r = 0; r < R; ++r) { sAcc[r][tid] = 0.0; prod[r] = 1.0; sX[r] = 0; sY[r] = 0; }
+    for (int r = 0; r < R; ++r) { sAcc[r][tid] = 0.0; prod[r] = 1.0; pendAcc[r] = 0.0; pendProd[r] = 1.0; sX[r] = 0; sY[r] = 0; }
 
     // ---- prologue: first operation's matrices and operands
     loadSegment(0);
@@ -345,7 +387,13 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         stage(0, w0.z, w1.x, (w1.w & OP_TIPTIP) ? opWord(0, 2).y : -1);
         fetch(w0.y, X, sX);
         fetch(w0.w, Y, sY);
+        if (w1.z >= 0) loadSlot(w1.z, pendAcc, pendProd);
         if (w1.y >= 0) joinSlot(w1.y, prod);
+        if (tid == 0) {
+#pragma unroll
+            for (int a = 1; a <= kPrefetchAhead; ++a)
+                if (a < nOps) prefetchOperands(a);
+        }
     }
 
     for (int j = 0; j < nOps; ++j) {
@@ -360,6 +408,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             n1 = opWord(j + 1, 1);
             stage((j + 1) & 1, n0.z, n1.x, (n1.w & OP_TIPTIP) ? opWord(j + 1, 2).y : -1);
         }
+        if (tid == 0 && j + 1 + kPrefetchAhead < nOps) prefetchOperands(j + 1 + kPrefetchAhead);
         const int flags = w1.w;
         const real* sa = sm[j & 1];
         const real* sb = sa + MSZ;
@@ -371,7 +420,10 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         double mfac[R];                                      // this step's rescaling maxima (1 when not rescaled)
         if (flags & OP_TIPTIP) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
-            if (more) fetch(n0.w, Y, sY);                    // sY was saved in sYc above
+            if (more) {                                      // sY was saved in sYc above
+                fetch(n0.w, Y, sY);
+                if (n1.z >= 0) loadSlot(n1.z, pendAcc, pendProd);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int combo = sX[r] * 5 + sYc[r];
@@ -411,9 +463,12 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
                 }
             }
-            if (w1.z >= 0) joinSlot(w1.z, prod);
-            // next step's operand B is requested now; the rescaling below hides its latency
-            if (more) fetch(n0.w, Y, sY);
+            if (w1.z >= 0) joinValues(pendAcc, pendProd, prod);
+            // next step's operand B (and its chain's scaler) is requested now; the rescaling below hides the latency
+            if (more) {
+                fetch(n0.w, Y, sY);
+                if (n1.z >= 0) loadSlot(n1.z, pendAcc, pendProd);
+            }
 
             if (flags & OP_RESCALE) {
                 // stage-major over the R patterns: R independent dependency chains, no branch in between
