@@ -13,7 +13,9 @@
 //   matrices [matrix][36*C]                   already in the shared-memory image the pruning kernel wants:
 //              16*C reals  row-major P_k[i][j], interleaved over categories as [(i*4+j)/2][k][(i*4+j)%2]
 //                          (the C category lanes of a warp read C consecutive 16-byte words: no bank conflict)
-//              20*C reals  tip table T[k][s][i] = P_k[i][s], row s=4 all ones (the missing state)
+//              20*C reals  tip table T[k][i][s] = P_k[i][s], column s=4 all ones (the missing state); state
+//                          fastest so that the 16 lanes of a shared-memory pass (4 patterns x 4 categories)
+//                          fall into distinct banks for s <= 3
 //   log-scalers [slot][Ppad] FP64 (cumulative buffers and per-chain subtree sums)
 //
 // The work is an HBM-bound 4x4 matrix-vector product (about 0.6 flop/byte): no tensor cores.
@@ -104,7 +106,7 @@ template <typename real> __device__ __forceinline__ real rmax(real a, real b) { 
 // matrix image indexing (see the layout note at the top of this file)
 // ------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ constexpr int rmIndex(int C, int k, int e) { return (((e >> 1) * C + k) << 1) + (e & 1); }
-__host__ __device__ __forceinline__ constexpr int tipIndex(int C, int k, int s, int i) { return 16 * C + (k * 5 + s) * 4 + i; }
+__host__ __device__ __forceinline__ constexpr int tipIndex(int C, int k, int s, int i) { return 16 * C + k * 20 + i * 5 + s; }
 
 __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
@@ -217,7 +219,7 @@ template <typename real, int C>
 __device__ __forceinline__ void factorTip(const real* __restrict__ sm, int k, int state, real (&F)[4]) {
     const real* T = sm + tipIndex(C, k, state, 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) F[i] = T[i];
+    for (int i = 0; i < 4; ++i) F[i] = T[i * 5];
 }
 
 // Branch-free reciprocal for the rescaling (argument is a normal number in (0, ~1]; the caller routes
@@ -257,11 +259,11 @@ __device__ __forceinline__ void accumulateFactor(double& acc, double& prod, doub
     else prod = t;
 }
 
-constexpr int kOpSegment = 32;                 // operations staged in shared memory at a time (x2 buffers)
+constexpr int kOpChunk = 256;                  // operations of a group held in shared memory at a time
 #ifndef SB200_PREFETCH_AHEAD
 #define SB200_PREFETCH_AHEAD 3
 #endif
-constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;              // steps between an operand tile's L2 prefetch and its register load
+constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // steps between an operand tile's L2 prefetch and its register load
 constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 
 #ifndef SB200_MINBLK_R1
@@ -279,64 +281,57 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
     constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
     constexpr int NCH = MSZ / CHUNK;                     // 16-byte chunks per operand image
     constexpr int TTS = ttStride(C);                     // reals per tip x tip table
+    constexpr int NTT = TTS / CHUNK;                     // 16-byte chunks per table
     constexpr int IMG = TTS > 2 * MSZ ? TTS : 2 * MSZ;   // shared image of one step: two matrices OR one table
+    constexpr int NSTG = (IMG / CHUNK + kPruneThreads - 1) / kPruneThreads;   // staging chunks per thread
+    constexpr unsigned TILE_BYTES = G * R * C * 4 * sizeof(real);
     __shared__ __align__(16) real sm[2][IMG];
-    __shared__ int4 sops[2][kOpSegment * kOpWords];
+    __shared__ int4 sops[kOpChunk * kOpWords];
     __shared__ double sAcc[R][kPruneThreads];            // log part of the running scaler (touched rarely)
 
     const int tid = threadIdx.x;
     const int k = tid % C, g = tid / C;
     const Group grp = A.groups[groupBase + blockIdx.y];
     const int nOps = grp.opEnd - grp.opStart;
-    const int4* gops = reinterpret_cast<const int4*>(A.ops + grp.opStart);
-    const int nTips = A.nTips;
     const int Ppad = A.Ppad;
-    const int p0 = blockIdx.x * (G * R) + g;             // r-th pattern of this thread: p0 + r*G (< Ppad)
+    const size_t tile0 = static_cast<size_t>(blockIdx.x) * (G * R);   // first pattern of this block's tile
     const size_t bufStride = static_cast<size_t>(Ppad) * C * 4;
-    real* const pmine = A.partials + (static_cast<size_t>(p0) * C + k) * 4;
-    const uint8_t* const tmine = A.tips + p0;
-    double* const accMine = A.slotAcc + p0;
-    double* const prodMine = A.slotProd + p0;
+    real* const pmine = A.partials + ((tile0 + g) * C + k) * 4;       // r-th pattern of this thread: + r*G*C*4
+    const uint8_t* const tmine = A.tips + tile0 + g;
+    double* const accMine = A.slotAcc + tile0 + g;
+    double* const prodMine = A.slotProd + tile0 + g;
 
-    auto loadSegment = [&](int q) {        // operations [q*SEG, (q+1)*SEG) of the group -> sops[q&1]
-        const int first = q * kOpSegment * kOpWords;
-        const int words = min(kOpSegment, nOps - q * kOpSegment) * kOpWords;
-        if (tid < words) sops[q & 1][tid] = gops[first + tid];
-    };
-    auto opWord = [&](int j, int w) -> int4 { return sops[(j / kOpSegment) & 1][(j % kOpSegment) * kOpWords + w]; };
-    auto stage = [&](int buf, int ma, int mb, int tt) {
-        if (tt >= 0) {
+    // ---- helpers ---------------------------------------------------------------------------
+    // matrix images (or the tip x tip table) of one operation -> sm[buf], 16 bytes per cp.async
+    auto stage = [&](int buf, const int4& w0, const int4& w1, int tt) {
+        if (w1.w & OP_TIPTIP) {
             const real* src = A.ttTables + static_cast<size_t>(tt) * TTS;
 #pragma unroll
-            for (int c = tid; c < TTS / CHUNK; c += kPruneThreads) cpAsync16(&sm[buf][c * CHUNK], src + c * CHUNK);
+            for (int s = 0; s < NSTG; ++s) {
+                const int c = tid + s * kPruneThreads;
+                if (c < NTT) cpAsync16(&sm[buf][c * CHUNK], src + c * CHUNK);
+            }
         } else {
 #pragma unroll
-            for (int c = tid; c < 2 * NCH; c += kPruneThreads) {
-                const int o = c >= NCH ? 1 : 0, cc = c - o * NCH;
-                cpAsync16(&sm[buf][o * MSZ + cc * CHUNK], A.mats + static_cast<size_t>(o ? mb : ma) * MSZ + cc * CHUNK);
+            for (int s = 0; s < NSTG; ++s) {
+                const int c = tid + s * kPruneThreads;
+                if (c < 2 * NCH) {
+                    const int o = c >= NCH ? 1 : 0;
+                    cpAsync16(&sm[buf][c * CHUNK], A.mats + static_cast<size_t>(o ? w1.x : w0.z) * MSZ + (c - o * NCH) * CHUNK);
+                }
             }
         }
         cpAsyncCommit();
     };
-    auto fetch = [&](int src, real (&v)[R][4], int (&state)[R]) {
-        if (src < nTips) {
-            const uint8_t* t = tmine + static_cast<size_t>(src) * A.tipStride;
+    auto fetchTip = [&](int src, int (&state)[R]) {
+        const uint8_t* t = tmine + static_cast<size_t>(src) * A.tipStride;
 #pragma unroll
-            for (int r = 0; r < R; ++r) state[r] = t[r * G];
-        } else {
-            const real* base = pmine + static_cast<size_t>(src - nTips) * bufStride;
-#pragma unroll
-            for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
-        }
+        for (int r = 0; r < R; ++r) state[r] = t[r * G];
     };
-    // joins the (log sum, product) scaler of a finished child chain
-    auto joinValues = [&](const double (&a)[R], const double (&pr)[R], double (&prod)[R]) {
+    auto fetchPartial = [&](int src, real (&v)[R][4]) {
+        const real* base = pmine + static_cast<size_t>(src - A.nTips) * bufStride;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double acc = sAcc[r][tid] + a[r];
-            accumulateFactor(acc, prod[r], pr[r]);
-            sAcc[r][tid] = acc;
-        }
+        for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
     };
     auto loadSlot = [&](int slot, double (&a)[R], double (&pr)[R]) {
 #pragma unroll
@@ -345,31 +340,23 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             pr[r] = prodMine[static_cast<size_t>(slot) * Ppad + r * G];
         }
     };
-    auto joinSlot = [&](int slot, double (&prod)[R]) {
-        double a[R], pr[R];
-        loadSlot(slot, a, pr);
-        joinValues(a, pr, prod);
-    };
-    // L2 prefetch of the operand tiles an operation will read (one bulk request per tile, one thread):
-    // issued kPrefetchAhead steps early so the register prefetch one step ahead finds the data in L2
-    constexpr unsigned TILE_BYTES = G * R * C * 4 * sizeof(real);
-    auto prefetchOperands = [&](int j) {
-        const int4 w0 = opWord(j, 0), w1 = opWord(j, 1);
-        const size_t tile0 = static_cast<size_t>(blockIdx.x) * (G * R);          // first pattern of this block's tile
+    // L2 prefetch of everything an operation will read from HBM (one bulk request per tile, issued by one
+    // thread kPrefetchAhead steps early): the register loads one step ahead then hit L2
+    auto prefetchOperands = [&](const int4& w0, const int4& w1) {
         const real* ptile = A.partials + tile0 * C * 4;
-        auto operand = [&](int src) {
-            if (src >= nTips) bulkPrefetchL2(ptile + static_cast<size_t>(src - nTips) * bufStride, TILE_BYTES);
-            else bulkPrefetchL2(A.tips + static_cast<size_t>(src) * A.tipStride + tile0, G * R);
-        };
-        auto slot = [&](int sl) {
-            bulkPrefetchL2(A.slotAcc + static_cast<size_t>(sl) * Ppad + tile0, G * R * 8);
-            bulkPrefetchL2(A.slotProd + static_cast<size_t>(sl) * Ppad + tile0, G * R * 8);
-        };
-        operand(w0.w);
-        if (w1.z >= 0) slot(w1.z);
+        if (w1.w & OP_B_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * A.tipStride + tile0, G * R);
+        else bulkPrefetchL2(ptile + static_cast<size_t>(w0.w - A.nTips) * bufStride, TILE_BYTES);
+        if (w1.z >= 0) {
+            bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
+            bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
+        }
         if (w1.w & OP_CHAIN_START) {
-            operand(w0.y);
-            if (w1.y >= 0) slot(w1.y);
+            if (w1.w & OP_A_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * A.tipStride + tile0, G * R);
+            else bulkPrefetchL2(ptile + static_cast<size_t>(w0.y - A.nTips) * bufStride, TILE_BYTES);
+            if (w1.y >= 0) {
+                bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
+                bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
+            }
         }
     };
 
@@ -379,62 +366,58 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
 #pragma unroll
     for (int r = 0; r < R; ++r) { sAcc[r][tid] = 0.0; prod[r] = 1.0; pendAcc[r] = 0.0; pendProd[r] = 1.0; sX[r] = 0; sY[r] = 0; }
 
-    // ---- prologue: first operation's matrices and operands
-    loadSegment(0);
-    __syncthreads();
-    {
-        const int4 w0 = opWord(0, 0), w1 = opWord(0, 1);     // {dest,a,ma,b} {mb,sa,sb,flags}
-        stage(0, w0.z, w1.x, (w1.w & OP_TIPTIP) ? opWord(0, 2).y : -1);
-        fetch(w0.y, X, sX);
-        fetch(w0.w, Y, sY);
-        if (w1.z >= 0) loadSlot(w1.z, pendAcc, pendProd);
-        if (w1.y >= 0) joinSlot(w1.y, prod);
-        if (tid == 0) {
-#pragma unroll
-            for (int a = 1; a <= kPrefetchAhead; ++a)
-                if (a < nOps) prefetchOperands(a);
-        }
-    }
-
-    for (int j = 0; j < nOps; ++j) {
-        cpAsyncWaitAll();
-        __syncthreads();          // matrices of step j visible; everyone is done with step j-1's image and op words
-        const bool more = j + 1 < nOps;
-        if ((j % kOpSegment) == 0 && (j / kOpSegment + 1) * kOpSegment < nOps) loadSegment(j / kOpSegment + 1);
-        const int4 w0 = opWord(j, 0), w1 = opWord(j, 1);
-        int4 n0 = w0, n1 = w1;
-        if (more) {
-            n0 = opWord(j + 1, 0);
-            n1 = opWord(j + 1, 1);
-            stage((j + 1) & 1, n0.z, n1.x, (n1.w & OP_TIPTIP) ? opWord(j + 1, 2).y : -1);
-        }
-        if (tid == 0 && j + 1 + kPrefetchAhead < nOps) prefetchOperands(j + 1 + kPrefetchAhead);
-        const int flags = w1.w;
-        const real* sa = sm[j & 1];
-        const real* sb = sa + MSZ;
-        int sYc[R];                                          // this step's B tip states (sY is re-used by the prefetch)
-#pragma unroll
-        for (int r = 0; r < R; ++r) sYc[r] = sY[r];
-
-        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
-        double mfac[R];                                      // this step's rescaling maxima (1 when not rescaled)
-        if (flags & OP_TIPTIP) {
-            // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
-            if (more) {                                      // sY was saved in sYc above
-                fetch(n0.w, Y, sY);
-                if (n1.z >= 0) loadSlot(n1.z, pendAcc, pendProd);
-            }
+    // operand A of a chain start, and the scaler of the chain that produced it
+    auto startChain = [&](const int4& w0, const int4& w1) {
+        if (w1.w & OP_A_TIP) fetchTip(w0.y, sX);
+        else fetchPartial(w0.y, X);
+        if (w1.y >= 0) {
+            double a[R], pr[R];
+            loadSlot(w1.y, a, pr);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int combo = sX[r] * 5 + sYc[r];
-                const real* T = sa + (combo * C + k) * 4;
+                double acc = sAcc[r][tid] + a[r];
+                accumulateFactor(acc, prod[r], pr[r]);
+                sAcc[r][tid] = acc;
+            }
+        }
+    };
+    // operand B (and its chain's scaler) of an operation, one step ahead of its use
+    auto fetchB = [&](const int4& w0, const int4& w1) {
+        if (w1.w & OP_B_TIP) fetchTip(w0.w, sY);
+        else fetchPartial(w0.w, Y);
+        if (w1.z >= 0) loadSlot(w1.z, pendAcc, pendProd);
+    };
+
+    // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
+    auto step = [&](const int j, const int nc, const int4& w0, const int4& w1, const int4& n0, const int4& n1) {
+        cpAsyncWaitAll();
+        __syncthreads();          // images of step j visible; everyone is done with step j-1's image
+        const bool more = j + 1 < nc;
+        const int flags = w1.w;
+        if (more) stage((j + 1) & 1, n0, n1, (n1.w & OP_TIPTIP) ? sops[(j + 1) * kOpWords + 2].y : -1);
+        if (tid == 0 && j + 1 + kPrefetchAhead < nc)
+            prefetchOperands(sops[(j + 1 + kPrefetchAhead) * kOpWords], sops[(j + 1 + kPrefetchAhead) * kOpWords + 1]);
+        const real* sa = sm[j & 1];
+        const real* sb = sa + MSZ;
+        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
+        double mfac[R];                                      // this step's rescaling maxima (1 when not rescaled)
+
+        if (flags & OP_TIPTIP) {
+            // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
+            int combo[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) combo[r] = sX[r] * 5 + sY[r];
+            if (more) fetchB(n0, n1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const real* T = sa + (combo[r] * C + k) * 4;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) X[r][i] = T[i];
-                mfac[r] = static_cast<double>(sa[100 * C + combo]);
+                mfac[r] = static_cast<double>(sa[100 * C + combo[r]]);
             }
         } else {
             // factor of operand A (from registers, or tip table at a chain start), then operand B
-            if ((flags & OP_CHAIN_START) && w0.y < nTips) {
+            if (flags & OP_A_TIP) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) factorTip<real, C>(sa, k, sX[r], X[r]);
             } else {
@@ -446,11 +429,11 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     for (int i = 0; i < 4; ++i) X[r][i] = F[i];
                 }
             }
-            if (w0.w < nTips) {
+            if (flags & OP_B_TIP) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     real F[4];
-                    factorTip<real, C>(sb, k, sYc[r], F);
+                    factorTip<real, C>(sb, k, sY[r], F);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
                 }
@@ -463,12 +446,16 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
                 }
             }
-            if (w1.z >= 0) joinValues(pendAcc, pendProd, prod);
-            // next step's operand B (and its chain's scaler) is requested now; the rescaling below hides the latency
-            if (more) {
-                fetch(n0.w, Y, sY);
-                if (n1.z >= 0) loadSlot(n1.z, pendAcc, pendProd);
+            if (w1.z >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double acc = sAcc[r][tid] + pendAcc[r];
+                    accumulateFactor(acc, prod[r], pendProd[r]);
+                    sAcc[r][tid] = acc;
+                }
             }
+            // next step's operand B is requested now; the rescaling below hides its latency
+            if (more) fetchB(n0, n1);
 
             if (flags & OP_RESCALE) {
                 // stage-major over the R patterns: R independent dependency chains, no branch in between
@@ -531,9 +518,8 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 }
             }
         }
-
         if (flags & OP_CHAIN_END) {
-            const int sOut = opWord(j, 2).x;
+            const int sOut = sops[j * kOpWords + 2].x;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 double a = sAcc[r][tid];
@@ -549,7 +535,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 }
                 if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && k == 0) {
                     const double total = scalerTotal(a, prod[r]);
-                    double* c = A.cum + p0 + r * G;
+                    double* c = A.cum + tile0 + g + r * G;
                     if (cumMode) *c = total;
                     else *c += total;
                 }
@@ -557,10 +543,39 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 prod[r] = 1.0;
             }
         }
-        if (more && (n1.w & OP_CHAIN_START)) {
-            fetch(n0.y, X, sX);
-            if (n1.y >= 0) joinSlot(n1.y, prod);
+        if (more && (n1.w & OP_CHAIN_START)) startChain(n0, n1);
+    };
+
+    // ---- the group, a chunk of operations at a time (one chunk unless the group is very long) ---------
+    for (int chunk0 = 0; chunk0 < nOps; chunk0 += kOpChunk) {
+        const int nc = min(kOpChunk, nOps - chunk0);
+        if (chunk0 > 0) __syncthreads();
+        {
+            const int4* gops = reinterpret_cast<const int4*>(A.ops + grp.opStart + chunk0);
+            for (int w = tid; w < nc * kOpWords; w += kPruneThreads) sops[w] = gops[w];
         }
+        __syncthreads();
+        int4 a0 = sops[0], a1 = sops[1];
+        stage(0, a0, a1, (a1.w & OP_TIPTIP) ? sops[2].y : -1);
+        if (a1.w & OP_CHAIN_START) startChain(a0, a1);       // (a later chunk may begin in mid-chain: A is carried)
+        fetchB(a0, a1);
+        if (tid == 0) {
+#pragma unroll
+            for (int a = 1; a <= kPrefetchAhead; ++a)
+                if (a < nc) prefetchOperands(sops[a * kOpWords], sops[a * kOpWords + 1]);
+        }
+        // two steps per iteration with the operation words ping-ponging between (a0,a1) and (b0,b1): no copies
+        int j = 0;
+        for (; j + 1 < nc; j += 2) {
+            const int4 b0 = sops[(j + 1) * kOpWords], b1 = sops[(j + 1) * kOpWords + 1];
+            step(j, nc, a0, a1, b0, b1);
+            if (j + 2 < nc) {
+                a0 = sops[(j + 2) * kOpWords];
+                a1 = sops[(j + 2) * kOpWords + 1];
+            }
+            step(j + 1, nc, b0, b1, a0, a1);
+        }
+        if (j < nc) step(j, nc, a0, a1, a0, a1);
     }
 }
 

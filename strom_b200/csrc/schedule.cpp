@@ -29,11 +29,14 @@ static DevOp makeOp(int dest, int a, int ma, int b, int mb, int sa, int sb, int 
 // (and rescaling maxima): they get a table computed once per evaluation instead of per pattern.
 static void assignTipTipTables(Schedule& out, int tipCount) {
     out.tipTipCount = 0;
-    for (DevOp& d : out.ops)
-        if ((d.flags & OP_CHAIN_START) && d.a >= 0 && d.a < tipCount && d.b < tipCount) {
+    for (DevOp& d : out.ops) {
+        if ((d.flags & OP_CHAIN_START) && d.a >= 0 && d.a < tipCount) d.flags |= OP_A_TIP;
+        if (d.b < tipCount) d.flags |= OP_B_TIP;
+        if ((d.flags & OP_A_TIP) && (d.flags & OP_B_TIP)) {
             d.flags |= OP_TIPTIP;
             d.tt = out.tipTipCount++;
         }
+    }
 }
 
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,

@@ -39,7 +39,9 @@ enum {
     OP_CHAIN_START = 2,    // operand A comes from memory (tips or a finished buffer)
     OP_CHAIN_END = 4,      // last operation of its chain: emit the subtree log-scaler, reset
     OP_ADD_TO_CUM = 8,     // with OP_CHAIN_END: the chain total goes into the cumulative buffer
-    OP_TIPTIP = 16         // both operands are tips: the result is one of 25 precomputed vectors per category
+    OP_TIPTIP = 16,        // both operands are tips: the result is one of 25 precomputed vectors per category
+    OP_A_TIP = 32,         // operand A is a tip (only with OP_CHAIN_START)
+    OP_B_TIP = 64          // operand B is a tip
 };
 
 // Host-side view of a chain (device code only sees the flags above).
