@@ -345,6 +345,8 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("prune_chains_dram_bytes_per_eval")
+                if traffic is not None:
+                    traffic = traffic * (args.patterns / 1e6) / world      # captured at 1M patterns on one rank; linear in patterns
             except Exception:
                 traffic = None
         line = {

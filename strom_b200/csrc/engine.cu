@@ -77,6 +77,7 @@ struct Engine {
     DevOp* dOps = nullptr;
     Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
+    long long* dTrace = nullptr;          // tuning builds: per-step clock samples (sb200DebugTrace)
     int* dTTOps = nullptr;                // op index of every tip x tip table
     void* dTT = nullptr;                  // tip x tip tables
     size_t ttOpsCap = 0, ttCap = 0;
@@ -403,6 +404,7 @@ struct Engine {
         a.slotProd = dSlots + static_cast<size_t>(sched.slotCount) * Ppad;
         a.cum = cum;
         a.ttTables = static_cast<const real*>(dTT);
+        a.trace = dTrace;
         a.ops = dOps;
         a.groups = dGroups;
         a.tipStride = tipStride;
@@ -958,6 +960,22 @@ extern "C" int sb200PartialsTime(int instance, double* totalMs, long* calls) {
         E.collectProfile();
         if (totalMs) *totalMs = E.partialsMsSum;
         if (calls) *calls = E.partialsCalls;
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+// Tuning aid (kernels built with -DSB200_TRACE): clock64 samples of block (0,0), 8 per step, 60 steps,
+// of the LAST pruning launch.  Allocates the buffer on first use; pass NULL to only enable.
+extern "C" __attribute__((visibility("default"))) int sb200DebugTrace(int instance, long long* out) {
+    return withEngine(instance, [&](Engine& E) {
+        if (!E.dTrace) {
+            CK(cudaMalloc(&E.dTrace, sizeof(long long) * 480));
+            CK(cudaMemset(E.dTrace, 0, sizeof(long long) * 480));
+        }
+        if (out) {
+            CK(cudaStreamSynchronize(E.stream));
+            CK(cudaMemcpy(out, E.dTrace, sizeof(long long) * 480, cudaMemcpyDeviceToHost));
+        }
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }

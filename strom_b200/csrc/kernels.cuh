@@ -51,6 +51,7 @@ struct PruneArgs {
     double* slotProd;                //                          product part [slot][Ppad] (scaler = acc + log(prod))
     double* cum;                     // cumulative scale buffer or nullptr
     const real* ttTables;            // [tipTipCount][ttStride(C)]
+    long long* trace;                // optional per-step clock samples of block (0,0) (tuning builds only)
     const DevOp* ops;
     const Group* groups;
     long long tipStride;
@@ -98,6 +99,16 @@ __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
 __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
     asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
+// Streaming variants: partials that no later operation re-reads from memory (every node inside a chain)
+// are written with an evict-first hint so that, when the working set is near the L2 size (rbcl738: 120 MB),
+// L2 keeps the chain-end buffers that WILL be re-read.
+__device__ __forceinline__ void st4Stream(double* p, const double (&v)[4]) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void st4Stream(float* p, const float (&v)[4]) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
 template <typename real> __device__ __forceinline__ real rmax(real a, real b) { return a > b ? a : b; }
@@ -389,18 +400,27 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
     };
 
     // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
+#ifdef SB200_TRACE
+#define SB200_TICK(slot) if (A.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && j < 60) A.trace[j * 8 + (slot)] = clock64();
+#else
+#define SB200_TICK(slot)
+#endif
     auto step = [&](const int j, const int nc, const int4& w0, const int4& w1, const int4& n0, const int4& n1) {
+        SB200_TICK(0)
         cpAsyncWaitAll();
+        SB200_TICK(1)
         __syncthreads();          // images of step j visible; everyone is done with step j-1's image
+        SB200_TICK(2)
         const bool more = j + 1 < nc;
         const int flags = w1.w;
         if (more) stage((j + 1) & 1, n0, n1, (n1.w & OP_TIPTIP) ? sops[(j + 1) * kOpWords + 2].y : -1);
-        if (tid == 0 && j + 1 + kPrefetchAhead < nc)
+        if (kPrefetchAhead > 0 && tid == 0 && j + 1 + kPrefetchAhead < nc)
             prefetchOperands(sops[(j + 1 + kPrefetchAhead) * kOpWords], sops[(j + 1 + kPrefetchAhead) * kOpWords + 1]);
         const real* sa = sm[j & 1];
         const real* sb = sa + MSZ;
         real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
         double mfac[R];                                      // this step's rescaling maxima (1 when not rescaled)
+        SB200_TICK(6)
 
         if (flags & OP_TIPTIP) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
@@ -429,6 +449,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     for (int i = 0; i < 4; ++i) X[r][i] = F[i];
                 }
             }
+            SB200_TICK(7)
             if (flags & OP_B_TIP) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -454,6 +475,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     sAcc[r][tid] = acc;
                 }
             }
+            SB200_TICK(3)
             // next step's operand B is requested now; the rescaling below hides its latency
             if (more) fetchB(n0, n1);
 
@@ -492,8 +514,14 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 for (int r = 0; r < R; ++r) mfac[r] = 1.0;
             }
         }
+        SB200_TICK(4)
+        if (flags & OP_CHAIN_END) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) st4(dest + r * (G * C * 4), X[r]);
+            for (int r = 0; r < R; ++r) st4(dest + r * (G * C * 4), X[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) st4Stream(dest + r * (G * C * 4), X[r]);
+        }
         {
             // deferred log: multiply the maxima, fold into the log sum only before an underflow
             double t[R];
@@ -544,6 +572,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             }
         }
         if (more && (n1.w & OP_CHAIN_START)) startChain(n0, n1);
+        SB200_TICK(5)
     };
 
     // ---- the group, a chunk of operations at a time (one chunk unless the group is very long) ---------
@@ -559,7 +588,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         stage(0, a0, a1, (a1.w & OP_TIPTIP) ? sops[2].y : -1);
         if (a1.w & OP_CHAIN_START) startChain(a0, a1);       // (a later chunk may begin in mid-chain: A is carried)
         fetchB(a0, a1);
-        if (tid == 0) {
+        if (kPrefetchAhead > 0 && tid == 0) {
 #pragma unroll
             for (int a = 1; a <= kPrefetchAhead; ++a)
                 if (a < nc) prefetchOperands(sops[a * kOpWords], sops[a * kOpWords + 1]);
