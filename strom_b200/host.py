@@ -32,6 +32,8 @@ class HostAPI:
         L.strom_model_numbers.argtypes = [_DP, _DP, C.c_double, C.c_int, C.c_double, _DP, _DP, _DP, _DP, _DP, _IP, C.c_char_p, C.c_int]
         L.strom_loglik.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, _IP, C.c_int, C.c_int,
                                    _DP, _DP, C.c_char_p, C.c_int]
+        L.strom_mcmc.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint, C.c_double,
+                                 _DP, _DP, C.c_int, _IP, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         self._err = C.create_string_buffer(1024)
 
     def _check(self, rc):
@@ -96,6 +98,23 @@ class HostAPI:
                                           int(dev.size), dev.ctypes.data_as(_IP), int(single), repeats, C.byref(out), C.byref(sec),
                                           self._err, 1024))
         return out.value, sec.value
+
+
+    # ---- MCMC (callers of the hot path) ------------------------------------------------------
+    def mcmc(self, data_handle: int, newick: str, seed: int = 13579, niter: int = 100, burnin: int = 100, samplefreq: int = 1,
+             nchains: int = 1, heatfactor: float = 0.5, ncateg: int = 4, gammashape: float = 0.5, freqs=(0.25,) * 4,
+             rmat=(1.0 / 6,) * 6, devices=(0,)):
+        """Returns (trace [rows][15] = iteration, lnL, lnPrior, TL, 6 r, 4 pi, alpha; seconds)."""
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        r = np.ascontiguousarray(rmat, dtype=np.float64)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        max_rows = niter // max(samplefreq, 1) + 2
+        rows = np.zeros((max_rows, 15))
+        sec = C.c_double()
+        n = self._check(self.lib.strom_mcmc(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor, ncateg,
+                                            gammashape, f.ctypes.data_as(_DP), r.ctypes.data_as(_DP), int(dev.size),
+                                            dev.ctypes.data_as(_IP), rows.ctypes.data_as(_DP), max_rows, C.byref(sec), self._err, 1024))
+        return rows[:n].copy(), sec.value
 
 
 _host = None

@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "likelihood.hpp"
+#include "mcmc.hpp"
 #include "tree_manip.hpp"
 
 namespace strom {
@@ -181,5 +182,30 @@ HOST_API int strom_loglik(int data_handle, const char* newick, const double* fre
         }
         *logl = v;
         return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+// Strom::run's MCMC branch on the host classes.  Fills `rows` (max_rows x 15 doubles: iteration, lnL,
+// lnPrior, TL, 6 exchangeabilities, 4 frequencies, alpha) with the cold chain's samples; returns the row count.
+HOST_API int strom_mcmc(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
+                        unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
+                        int ndevices, const int* devices, double* rows, int max_rows, double* seconds, char* err, int errlen) {
+    try {
+        McmcOptions opt;
+        opt.seed = seed; opt.niter = niter; opt.burnin = burnin; opt.samplefreq = samplefreq ? samplefreq : 1; opt.nchains = nchains;
+        opt.heatfactor = heatfactor; opt.ncateg = ncateg; opt.gammashape = gammashape;
+        opt.statefreq.assign(freqs, freqs + 4);
+        opt.rmatrix.assign(rmat, rmat + 6);
+        if (ndevices > 0) opt.devices.assign(devices, devices + ndevices);
+        const auto t0 = std::chrono::steady_clock::now();
+        const std::vector<TraceRow> tr = runMCMC(dataOf(data_handle), newick, opt);
+        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const int n = std::min<int>(static_cast<int>(tr.size()), max_rows);
+        for (int i = 0; i < n; ++i) {
+            double* r = rows + static_cast<size_t>(i) * 15;
+            r[0] = tr[i].iteration; r[1] = tr[i].lnL; r[2] = tr[i].lnPrior; r[3] = tr[i].TL;
+            for (int k = 0; k < 11; ++k) r[4 + k] = tr[i].params[k];
+        }
+        return n;
     } catch (const std::exception& e) { return fail(e, err, errlen); }
 }

@@ -1,0 +1,471 @@
+// mcmc.hpp -- the callers of the hot path: a compact Metropolis-coupled MCMC driver over the Likelihood
+// facade, used to show that the same host code produces the same trace on the CUDA engine and on the
+// reference's CPU call path (north-star: "with the same seed the MCMC trace must be identical up to
+// tolerance").  It follows the reference's control flow and acceptance rule:
+//   Updater::update  pull -> prior -> propose -> push -> calcLogLikelihood -> prior -> heated MH test
+//                    -> accept | revert+push -> tune -> reset            (reference src/updater.hpp:184-225)
+//   Updater::tune    adaptive lambda, gamma_n = 10/(100+n), cap 1000     (src/updater.hpp:136-151)
+//   Chain::nextStep  gamma shape (if C > 1), state freqs, exchangeabilities, tree, tree length
+//                                                                        (src/chain.hpp:285-294)
+//   swapChains       logR = (b_i - b_j)(k_j - k_i); heating powers, chain indices and lambdas swap
+//                                                                        (src/strom.hpp:326-402)
+//   heating powers   1 / (1 + heatfactor * i)                            (src/strom.hpp:202-215)
+// Deliberate differences (these classes are host control flow, outside the rebuilt hot path):
+//   * Lot draws from std::mt19937 / std::gamma_distribution (Boost's generators are not available), so the
+//     streams differ from a real strom build; parity is defined between the two back-ends of THIS code;
+//   * TreeUpdater is a reduced LOCAL move: one random internal edge, its three-edge focal path scaled by
+//     m = exp(lambda (u - 0.5)), and with probability 1/2 an NNI swap across that edge -- it exercises
+//     topology + edge-length changes through the engine but is not the reference's 8-case proposal.
+#pragma once
+#include <cmath>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "likelihood.hpp"
+#include "tree_manip.hpp"
+
+namespace strom {
+
+class Lot {
+  public:
+    explicit Lot(unsigned seed = 1) : _gen(seed) {}
+    void setSeed(unsigned seed) { _gen.seed(seed); }
+    double uniform() {                      // (0,1): one 32-bit draw, never exactly 0
+        return (static_cast<double>(_gen()) + 0.5) / 4294967296.0;
+    }
+    double logUniform() { return std::log(uniform()); }
+    double gamma(double shape, double scale) { return std::gamma_distribution<double>(shape, scale)(_gen); }
+    int randint(int low, int high) {        // inclusive, from one uniform like the reference (src/lot.hpp:79-106)
+        const double u = uniform();
+        const int n = high - low + 1;
+        int k = static_cast<int>(u * n);
+        if (k >= n) k = n - 1;
+        return low + k;
+    }
+    typedef std::shared_ptr<Lot> SharedPtr;
+
+  private:
+    std::mt19937 _gen;
+};
+
+class Updater {
+  public:
+    virtual ~Updater() {}
+    void setLikelihood(Likelihood::SharedPtr l) { _likelihood = l; }
+    void setTreeManip(TreeManip::SharedPtr t) { _tree_manipulator = t; }
+    void setLot(Lot::SharedPtr lot) { _lot = lot; }
+    void setLambda(double l) { _lambda = l; }
+    void setHeatingPower(double p) { _heating_power = p; }
+    void setTuning(bool on) { _tuning = on; _naccepts = 0; _nattempts = 0; }
+    void setTargetAcceptanceRate(double t) { _target_acceptance = t; }
+    void setPriorParameters(const std::vector<double>& c) { _prior_parameters = c; }
+    double getLambda() const { return _lambda; }
+    double getAcceptPct() const { return _nattempts == 0 ? 0.0 : 100.0 * _naccepts / _nattempts; }
+    const std::string& getUpdaterName() const { return _name; }
+
+    virtual double calcLogPrior() const = 0;
+    double calcLogLikelihood() const { return _likelihood->calcLogLikelihood(_tree_manipulator->getTree()); }
+
+    virtual double update(double prev_lnL) {
+        pullCurrentStateFromModel();
+        const double prev_log_prior = calcLogPrior();
+        proposeNewState();
+        pushCurrentStateToModel();
+        double log_likelihood = calcLogLikelihood();
+        const double log_prior = calcLogPrior();
+        bool accept = true;
+        if (log_prior > logMinusInfinity()) {
+            const double log_diff = _log_hastings_ratio + _heating_power * ((log_likelihood + log_prior) - (prev_lnL + prev_log_prior));
+            if (_lot->logUniform() > log_diff) accept = false;
+        } else {
+            accept = false;
+        }
+        if (accept) ++_naccepts;
+        else {
+            revert();
+            pushCurrentStateToModel();
+            log_likelihood = prev_lnL;      // the reference does not recompute after a rejection (:216-218)
+        }
+        tune(accept);
+        _log_hastings_ratio = 0.0;
+        return log_likelihood;
+    }
+
+    // Gamma(a, b) prior on tree length, symmetric Dirichlet(c) on edge proportions (src/updater.hpp:227-268)
+    double calcEdgeLengthPrior() const {
+        Tree::SharedPtr tree = _tree_manipulator->getTree();
+        const double TL = _tree_manipulator->calcTreeLength();
+        const double n = tree->numLeaves();
+        const double num_edges = 2.0 * n - (tree->isRooted() ? 2.0 : 3.0);
+        const double a = _prior_parameters[0], b = _prior_parameters[1], c = _prior_parameters[2];
+        double lp = (a - 1.0) * std::log(TL) - TL / b - a * std::log(b) - std::lgamma(a);
+        lp += std::lgamma(num_edges * c);
+        if (c != 1.0) {
+            for (double len : edgeLengths()) lp += (c - 1.0) * std::log(len / TL);
+            lp -= std::lgamma(c) * num_edges;
+        }
+        return lp;
+    }
+
+    virtual void pullCurrentStateFromModel() = 0;
+
+  protected:
+    static double logMinusInfinity() { return -1.0e300; }
+    virtual void tune(bool accepted) {
+        ++_nattempts;
+        if (!_tuning) return;
+        const double gamma_n = 10.0 / (100.0 + static_cast<double>(_nattempts));
+        if (accepted) _lambda *= 1.0 + gamma_n * (1.0 - _target_acceptance) / (2.0 * _target_acceptance);
+        else _lambda *= 1.0 - gamma_n * 0.5;
+        if (_lambda > 1000.0) _lambda = 1000.0;
+    }
+    virtual void revert() = 0;
+    virtual void proposeNewState() = 0;
+    virtual void pushCurrentStateToModel() const = 0;
+    std::vector<double> edgeLengths() const;     // defined after TreeAccess
+
+    Lot::SharedPtr _lot;
+    Likelihood::SharedPtr _likelihood;
+    TreeManip::SharedPtr _tree_manipulator;
+    std::string _name = "updater";
+    double _lambda = 0.0001;
+    double _log_hastings_ratio = 0.0;
+    double _target_acceptance = 0.3;
+    unsigned _naccepts = 0, _nattempts = 0;
+    bool _tuning = true;
+    std::vector<double> _prior_parameters;
+    double _heating_power = 1.0;
+};
+
+// Updater is a friend of Tree and Node (like in the reference); derived classes reach them through it.
+inline std::vector<double> Updater::edgeLengths() const {
+    std::vector<double> v;
+    for (Node* nd : _tree_manipulator->getTree()->_preorder) v.push_back(nd->_edge_length);
+    return v;
+}
+
+class GammaShapeUpdater : public Updater {
+  public:
+    GammaShapeUpdater() { _name = "Gamma Rate Variance"; }
+    double calcLogPrior() const override {
+        const double a = _prior_parameters[0], b = _prior_parameters[1];
+        return (a - 1.0) * std::log(_curr_point) - _curr_point / b - a * std::log(b) - std::lgamma(a);
+    }
+    void pullCurrentStateFromModel() override { _curr_point = _likelihood->getModel()->getGammaShape(); }
+
+  private:
+    void pushCurrentStateToModel() const override { _likelihood->getModel()->setGammaShape(_curr_point); }
+    void proposeNewState() override {
+        _prev_point = _curr_point;
+        const double m = std::exp(_lambda * (_lot->uniform() - 0.5));
+        _curr_point = m * _prev_point;
+        _log_hastings_ratio = std::log(m);
+    }
+    void revert() override { _curr_point = _prev_point; }
+    double _prev_point = 0.0, _curr_point = 0.0;
+};
+
+class DirichletUpdater : public Updater {
+  public:
+    double calcLogPrior() const override {
+        bool flat = true, bad = false;
+        double lp = 0.0, sum = 0.0;
+        for (size_t i = 0; i < _curr_point.size(); ++i) {
+            if (_prior_parameters[i] != 1.0) flat = false;
+            if (_curr_point[i] == 0.0) bad = true;
+            lp += (_prior_parameters[i] - 1.0) * std::log(_curr_point[i]) - std::lgamma(_prior_parameters[i]);
+            sum += _prior_parameters[i];
+        }
+        if (flat) return std::lgamma(sum);
+        if (bad) return logMinusInfinity();
+        return lp + std::lgamma(sum);
+    }
+
+  protected:
+    void proposeNewState() override {      // Dirichlet(1 + x/lambda) forward, same reverse (src/dirichlet_updater.hpp:78-142)
+        const size_t dim = _curr_point.size();
+        _prev_point = _curr_point;
+        std::vector<double> fwd(dim), rev(dim);
+        double sum_dev = 0.0;
+        for (size_t i = 0; i < dim; ++i) {
+            fwd[i] = std::max(1.0 + _prev_point[i] / _lambda, 1.e-12);
+            _curr_point[i] = _lot->gamma(fwd[i], 1.0);
+            sum_dev += _curr_point[i];
+        }
+        for (double& x : _curr_point) x /= sum_dev;
+        double lf = std::lgamma(std::accumulate(fwd.begin(), fwd.end(), 0.0)), lr = 0.0, sr = 0.0;
+        for (size_t i = 0; i < dim; ++i) {
+            lf += (fwd[i] - 1.0) * std::log(_prev_point[i]) - std::lgamma(fwd[i]);
+            rev[i] = 1.0 + _curr_point[i] / _lambda;
+            sr += rev[i];
+            lr += (rev[i] - 1.0) * std::log(_curr_point[i]) - std::lgamma(rev[i]);
+        }
+        _log_hastings_ratio = lr + std::lgamma(sr) - lf;
+    }
+    void revert() override { _curr_point = _prev_point; }
+    std::vector<double> _curr_point, _prev_point;
+};
+
+class StateFreqUpdater : public DirichletUpdater {
+  public:
+    StateFreqUpdater() { _name = "State Frequencies"; }
+    void pullCurrentStateFromModel() override { _curr_point = _likelihood->getModel()->getStateFreqs(); }
+
+  private:
+    void pushCurrentStateToModel() const override { _likelihood->getModel()->setStateFreqs(_curr_point); }
+};
+
+class ExchangeabilityUpdater : public DirichletUpdater {
+  public:
+    ExchangeabilityUpdater() { _name = "Exchangeabilities"; }
+    void pullCurrentStateFromModel() override { _curr_point = _likelihood->getModel()->getExchangeabilities(); }
+
+  private:
+    void pushCurrentStateToModel() const override { _likelihood->getModel()->setExchangeabilities(_curr_point); }
+};
+
+class TreeLengthUpdater : public Updater {
+  public:
+    TreeLengthUpdater() { _name = "Tree Length"; }
+    double calcLogPrior() const override { return calcEdgeLengthPrior(); }
+    void pullCurrentStateFromModel() override { _curr_point = _tree_manipulator->calcTreeLength(); }
+
+  private:
+    void pushCurrentStateToModel() const override { _tree_manipulator->scaleAllEdgeLengths(_curr_point / _prev_point); }
+    void proposeNewState() override {
+        _prev_point = _curr_point;
+        const double m = std::exp(_lambda * (_lot->uniform() - 0.5));
+        _curr_point = m * _prev_point;
+        _log_hastings_ratio = std::log(m);
+    }
+    void revert() override { std::swap(_curr_point, _prev_point); }     // so the push scales back (src/tree_length_updater.hpp:82-89)
+    double _prev_point = 0.0, _curr_point = 0.0;
+};
+
+// Reduced LOCAL move (see the header comment).
+class TreeUpdater : public Updater {
+  public:
+    TreeUpdater() { _name = "Tree Topol. and Edge Lengths"; }
+    double calcLogPrior() const override {
+        const double n = _tree_manipulator->getTree()->numLeaves();
+        const double log_num_topologies = std::lgamma(2.0 * n - 5.0 + 1.0) - (n - 3.0) * std::log(2.0) - std::lgamma(n - 3.0 + 1.0);
+        return -log_num_topologies + calcEdgeLengthPrior();
+    }
+    void pullCurrentStateFromModel() override {}
+
+  private:
+    void pushCurrentStateToModel() const override {}
+    void proposeNewState() override {
+        _x = _tree_manipulator->randomInternalEdge(_lot->uniform());
+        _a = _x->getLeftChild();
+        _b = _a->getRightSib();
+        Node* y = _x->getParent();
+        _d = (_x == y->getLeftChild()) ? _x->getRightSib() : y->getLeftChild();
+        _top = (_lot->uniform() < 0.5) ? _a : _b;
+        _bottom = _d;
+        _len_top = _top->getEdgeLength();
+        _len_mid = _x->getEdgeLength();
+        _len_bot = _bottom->getEdgeLength();
+        const double m = std::exp(_lambda * (_lot->uniform() - 0.5));
+        const double num_edges = static_cast<double>(_tree_manipulator->getTree()->numNodes() - 1);
+        const double TL = _tree_manipulator->calcTreeLength();
+        const double Pac = (_len_top + _len_mid + _len_bot) / TL;
+        _log_hastings_ratio = 3.0 * std::log(m) - num_edges * std::log(Pac * m + 1.0 - Pac);
+        _top->setEdgeLength(m * _len_top);
+        _x->setEdgeLength(m * _len_mid);
+        _bottom->setEdgeLength(m * _len_bot);
+        _swapped = _lot->uniform() < 0.5;
+        if (_swapped) {
+            _moved = (_top == _a) ? _b : _a;        // the child of x that is NOT on the focal path changes places with d
+            _tree_manipulator->nniNodeSwap(_moved, _d);
+        }
+    }
+    void revert() override {
+        if (_swapped) _tree_manipulator->nniNodeSwap(_d, _moved);   // d now hangs from x, moved from y: swap back
+        _top->setEdgeLength(_len_top);
+        _x->setEdgeLength(_len_mid);
+        _bottom->setEdgeLength(_len_bot);
+    }
+    Node *_x = nullptr, *_a = nullptr, *_b = nullptr, *_d = nullptr, *_top = nullptr, *_bottom = nullptr, *_moved = nullptr;
+    double _len_top = 0, _len_mid = 0, _len_bot = 0;
+    bool _swapped = false;
+};
+
+class Chain {
+  public:
+    Chain() {
+        _shape_updater.reset(new GammaShapeUpdater);
+        _shape_updater->setLambda(1.0);
+        _shape_updater->setPriorParameters({1.0, 1.0});
+        _statefreq_updater.reset(new StateFreqUpdater);
+        _statefreq_updater->setLambda(0.001);
+        _statefreq_updater->setPriorParameters({1.0, 1.0, 1.0, 1.0});
+        _exchangeability_updater.reset(new ExchangeabilityUpdater);
+        _exchangeability_updater->setLambda(0.001);
+        _exchangeability_updater->setPriorParameters({1.0, 1.0, 1.0, 1.0, 1.0, 1.0});
+        _tree_updater.reset(new TreeUpdater);
+        _tree_updater->setLambda(0.2);
+        _tree_updater->setPriorParameters({1.0, 10.0, 1.0});
+        _tree_length_updater.reset(new TreeLengthUpdater);
+        _tree_length_updater->setLambda(0.2);
+        _tree_length_updater->setPriorParameters({1.0, 10.0, 1.0});
+        for (Updater* u : all()) u->setTargetAcceptanceRate(0.3);
+    }
+    void setTreeFromNewick(const std::string& newick) {
+        _tree_manipulator.reset(new TreeManip);
+        _tree_manipulator->buildFromNewick(newick, false, false);
+        for (Updater* u : all()) u->setTreeManip(_tree_manipulator);
+    }
+    void setLikelihood(Likelihood::SharedPtr l) { _likelihood = l; for (Updater* u : all()) u->setLikelihood(l); }
+    void setLot(Lot::SharedPtr lot) { for (Updater* u : all()) u->setLot(lot); }
+    void setHeatingPower(double p) { _heating_power = p; for (Updater* u : all()) u->setHeatingPower(p); }
+    double getHeatingPower() const { return _heating_power; }
+    void setChainIndex(unsigned i) { _chain_index = i; }
+    unsigned getChainIndex() const { return _chain_index; }
+    void startTuning() { for (Updater* u : all()) u->setTuning(true); }
+    void stopTuning() { for (Updater* u : all()) u->setTuning(false); }
+    std::vector<double> getLambdas() const {
+        return {_shape_updater->getLambda(), _statefreq_updater->getLambda(), _exchangeability_updater->getLambda(),
+                _tree_updater->getLambda(), _tree_length_updater->getLambda()};
+    }
+    void setLambdas(const std::vector<double>& v) {     // tree length gets the tree updater's lambda (src/chain.hpp:163-164)
+        _shape_updater->setLambda(v[0]);
+        _statefreq_updater->setLambda(v[1]);
+        _exchangeability_updater->setLambda(v[2]);
+        _tree_updater->setLambda(v[3]);
+        _tree_length_updater->setLambda(v[3]);
+    }
+    std::vector<double> getAcceptPercentages() const {
+        std::vector<double> v;
+        for (Updater* u : all()) v.push_back(u->getAcceptPct());
+        return v;
+    }
+    Model::SharedPtr getModel() { return _likelihood->getModel(); }
+    TreeManip::SharedPtr getTreeManip() { return _tree_manipulator; }
+    double getLogLikelihood() const { return _log_likelihood; }
+    double calcLogLikelihood() const { return _shape_updater->calcLogLikelihood(); }
+    double calcLogJointPrior() const {                   // the tree-length updater's prior is left out (src/chain.hpp:274-283)
+        return _shape_updater->calcLogPrior() + _statefreq_updater->calcLogPrior() + _exchangeability_updater->calcLogPrior() +
+               _tree_updater->calcLogPrior();
+    }
+    void start() {
+        for (Updater* u : all()) u->pullCurrentStateFromModel();
+        _log_likelihood = calcLogLikelihood();
+    }
+    void nextStep(int) {
+        if (_likelihood->getModel()->getGammaNCateg() > 1) _log_likelihood = _shape_updater->update(_log_likelihood);
+        _log_likelihood = _statefreq_updater->update(_log_likelihood);
+        _log_likelihood = _exchangeability_updater->update(_log_likelihood);
+        _log_likelihood = _tree_updater->update(_log_likelihood);
+        _log_likelihood = _tree_length_updater->update(_log_likelihood);
+    }
+
+  private:
+    std::vector<Updater*> all() const {
+        return {_shape_updater.get(), _statefreq_updater.get(), _exchangeability_updater.get(), _tree_updater.get(),
+                _tree_length_updater.get()};
+    }
+    Likelihood::SharedPtr _likelihood;
+    TreeManip::SharedPtr _tree_manipulator;
+    std::shared_ptr<GammaShapeUpdater> _shape_updater;
+    std::shared_ptr<StateFreqUpdater> _statefreq_updater;
+    std::shared_ptr<ExchangeabilityUpdater> _exchangeability_updater;
+    std::shared_ptr<TreeUpdater> _tree_updater;
+    std::shared_ptr<TreeLengthUpdater> _tree_length_updater;
+    unsigned _chain_index = 0;
+    double _heating_power = 1.0;
+    double _log_likelihood = 0.0;
+};
+
+// One sampled row of the cold chain: iteration, lnL, lnPrior, TL, 6 exchangeabilities, 4 frequencies, alpha
+// (the columns of the reference's params.txt, src/output_manager.hpp:102-114, src/model.hpp:356-368).
+struct TraceRow {
+    unsigned iteration;
+    double lnL, lnPrior, TL;
+    double params[11];
+};
+
+struct McmcOptions {
+    unsigned seed = 13579, niter = 100, burnin = 100, samplefreq = 1, nchains = 1, ncateg = 4;
+    double heatfactor = 0.5, gammashape = 0.5;
+    std::vector<double> statefreq = {0.25, 0.25, 0.25, 0.25};
+    std::vector<double> rmatrix = {1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6};   // on the simplex, like strom's default
+    std::vector<int> devices = {0};          // chain c runs on devices[c % size]: one heated chain per GPU
+};
+
+// Strom::run's MCMC branch (src/strom.hpp:486-523): initChains, burn-in with tuning, sampling with swaps.
+inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& newick, const McmcOptions& opt) {
+    Lot::SharedPtr lot(new Lot(opt.seed));
+    std::vector<Chain> chains(opt.nchains);
+    for (unsigned c = 0; c < opt.nchains; ++c) {
+        Chain& ch = chains[c];
+        ch.setTreeFromNewick(newick);
+        ch.setLot(lot);
+        Model::SharedPtr model(new Model());
+        model->setExchangeabilitiesAndStateFreqs(opt.rmatrix, opt.statefreq);
+        model->setGammaShape(opt.gammashape);
+        model->setGammaNCateg(opt.ncateg);
+        Likelihood::SharedPtr lik(new Likelihood());
+        lik->setQuiet(true);
+        lik->setDevices(std::vector<int>(1, opt.devices[c % opt.devices.size()]));
+        lik->setData(data);
+        lik->setModel(model);
+        ch.setLikelihood(lik);
+        ch.startTuning();
+        ch.setChainIndex(c);
+        ch.setHeatingPower(1.0 / (1.0 + opt.heatfactor * c));
+        ch.start();
+    }
+    std::vector<TraceRow> trace;
+    auto sample = [&](unsigned iteration) {
+        for (Chain& ch : chains) {
+            if (ch.getHeatingPower() != 1.0) continue;
+            TraceRow r;
+            r.iteration = iteration;
+            r.lnL = ch.calcLogLikelihood();             // one more full evaluation per sample, as in Strom::sample (:455)
+            r.lnPrior = ch.calcLogJointPrior();
+            r.TL = ch.getTreeManip()->calcTreeLength();
+            const std::vector<double> x = ch.getModel()->getExchangeabilities(), f = ch.getModel()->getStateFreqs();
+            for (int i = 0; i < 6; ++i) r.params[i] = x[i];
+            for (int i = 0; i < 4; ++i) r.params[6 + i] = f[i];
+            r.params[10] = ch.getModel()->getGammaShape();
+            trace.push_back(r);
+        }
+    };
+    auto swapChains = [&]() {
+        if (opt.nchains == 1) return;
+        const unsigned i = static_cast<unsigned>(lot->randint(0, static_cast<int>(opt.nchains) - 1));
+        const unsigned j = (i + 1 + static_cast<unsigned>(lot->randint(0, static_cast<int>(opt.nchains) - 2))) % opt.nchains;
+        const double heat_i = chains[i].getHeatingPower(), heat_j = chains[j].getHeatingPower();
+        const double k_i = chains[i].calcLogLikelihood() + chains[i].calcLogJointPrior();
+        const double k_j = chains[j].calcLogLikelihood() + chains[j].calcLogJointPrior();
+        const double logR = (heat_i - heat_j) * (k_j - k_i);
+        if (lot->logUniform() < logR) {
+            const unsigned idx_i = chains[i].getChainIndex(), idx_j = chains[j].getChainIndex();
+            chains[j].setHeatingPower(heat_i);
+            chains[i].setHeatingPower(heat_j);
+            chains[j].setChainIndex(idx_i);
+            chains[i].setChainIndex(idx_j);
+            const std::vector<double> li = chains[i].getLambdas(), lj = chains[j].getLambdas();
+            chains[i].setLambdas(lj);
+            chains[j].setLambdas(li);
+        }
+    };
+    sample(0);
+    for (unsigned it = 1; it <= opt.burnin; ++it) {
+        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+        swapChains();
+    }
+    for (Chain& ch : chains) ch.stopTuning();
+    for (unsigned it = 1; it <= opt.niter; ++it) {
+        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+        if (it % opt.samplefreq == 0) sample(it);
+        swapChains();
+    }
+    return trace;
+}
+
+}  // namespace strom

@@ -1,0 +1,40 @@
+"""Trace parity: the same host code and seed on the CUDA engine and on the reference's CPU call path give
+the same MCMC trace up to tolerance (north-star).  A logL difference of 1e-13 can in principle flip one
+accept decision; the test reports the first divergence instead of demanding bit-equality."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(api, key, **kw):
+    fx = load_golden(key)
+    cols = np.repeat(np.arange(fx["data"].shape[1]), fx["counts"].astype(int))
+    h = api.data_from_codes(fx["data"].astype(np.int32)[:, cols], compress=True)
+    tr, sec = api.mcmc(h, str(fx["newick"]), **kw)
+    api.data_free(h)
+    return tr, sec
+
+
+@pytest.mark.parametrize("key,kw", [("rbcl10", dict(niter=300, burnin=200, nchains=4, samplefreq=10, seed=13579)),
+                                    ("rbcL", dict(niter=200, burnin=100, nchains=2, samplefreq=5, seed=7)),
+                                    ("rbcl10", dict(niter=100, burnin=50, nchains=1, ncateg=1, samplefreq=5, seed=3))])
+def test_trace_matches_cpu_call_path(key, kw):
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    gpu, _ = _run(host(), key, **kw)
+    cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), key, **kw)
+    assert gpu.shape == cpu.shape
+    rel = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-300)
+    bad = np.argwhere(rel > 1e-9)
+    assert bad.size == 0, "first divergence at sample row %d column %d: gpu %r cpu %r" % (
+        bad[0][0], bad[0][1], gpu[bad[0][0], bad[0][1]], cpu[bad[0][0], bad[0][1]])
+
+
+def test_chain_per_gpu_placement_runs():
+    # config C5 shape: one Likelihood (engine instance) per heated chain; here all pinned to device 0
+    from strom_b200.host import host
+    tr, sec = _run(host(), "rbcl738", niter=10, burnin=10, nchains=2, samplefreq=5, seed=1, devices=(0, 0))
+    assert tr.shape[0] == 3 and np.all(np.isfinite(tr)) and tr[-1, 1] > tr[0, 1]
