@@ -71,7 +71,7 @@ struct Engine {
     bool blockInFlight = false;
     // schedule
     Schedule sched;
-    uint64_t schedHash = 0;
+    bool schedAccumulate = false;
     bool schedValid = false;
     std::vector<BeagleOperation> schedOps;
     DevOp* dOps = nullptr;
@@ -91,7 +91,7 @@ struct Engine {
     double* dBlockSums = nullptr;
     unsigned int* dTicket = nullptr;
     double* dOut = nullptr;
-    double* hOut = nullptr;               // pinned
+    double* hOut = nullptr;               // pinned, written by the root kernel directly
     int rootBlocks = 0;
     // last root-edge call (for replay)
     int lastParent = -1, lastChild = -1, lastMatrix = -1, lastWIdx = 0, lastFIdx = 0, lastRootCum = BEAGLE_OP_NONE;
@@ -279,19 +279,25 @@ struct Engine {
         if (C == 1 || C == 2 || C == 4 || C == 8) return (kPruneThreads / C) * (bigTiles() ? kBigR : 1);
         return 128;
     }
-    // Enough (tile x group) blocks per launch to fill the 148 SMs several times over, as few groups as
-    // possible otherwise (a group is a serial stream; fewer groups = less per-block set-up).
+    // How many groups a launch's chains are dealt into.  Every block pays a fixed set-up (operation words,
+    // first images and operands: two dependent trips to L2/HBM), so as few groups as possible -- but:
+    //   * few pattern tiles (latency-bound sizes such as rbcl738, 20 tiles): exactly ONE wave of resident
+    //     blocks (148 SMs x 3 CTAs), each streaming through many operations;
+    //   * many tiles (streaming sizes): enough blocks for >= 8 waves, so the last partial wave costs little.
     int groupsPerLevel() const {
         const int tiles = Ppad / patternsPerBlock();
-        const int wantBlocks = 148 * 16;      // >= 8 waves of 2 resident blocks per SM: the tail wave costs little
-        return std::max(1, (wantBlocks + tiles - 1) / tiles);
+        int slots = 148 * 3;
+        if (const char* f = std::getenv("SB200_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
+        if (tiles * 2 <= slots) return std::max(1, slots / tiles);
+        return std::max(1, (8 * slots + tiles - 1) / tiles);
     }
 
     int prepareSchedule(const BeagleOperation* ops, int count, bool accumulate) {
-        const uint64_t h = hashOps(ops, count, accumulate);
-        if (schedValid && h == schedHash && static_cast<int>(schedOps.size()) == count &&
+        // same operation list as last call (the common case: 4 of strom's 5 updaters do not touch the
+        // topology): reuse the plan that is already in HBM.  One memcmp of 28 bytes per operation.
+        if (schedValid && schedAccumulate == accumulate && static_cast<int>(schedOps.size()) == count &&
             (count == 0 || std::memcmp(schedOps.data(), ops, sizeof(BeagleOperation) * count) == 0))
-            return BEAGLE_SUCCESS;                     // same topology as last call: reuse plan in HBM
+            return BEAGLE_SUCCESS;
         Schedule s;
         int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s);
         if (rc != BEAGLE_SUCCESS) return rc;
@@ -302,7 +308,7 @@ struct Engine {
         schedValid = false;
         sched = std::move(s);
         schedOps.assign(ops, ops + count);
-        schedHash = h;
+        schedAccumulate = accumulate;
         // stage + upload
         const size_t opsB = sizeof(DevOp) * sched.ops.size();
         const size_t chB = sizeof(Group) * sched.groups.size();
@@ -418,7 +424,12 @@ struct Engine {
             ++launches;
         }
         const bool big = bigTiles();
+        int traceLevel = -1, levelIndex = 0;
+        if (const char* f = std::getenv("SB200_TRACE_LEVEL")) traceLevel = std::atoi(f);   // tuning aid (needs -DSB200_TRACE)
+        long long* const traceBuf = a.trace;
         for (const Level& L : sched.levels) {
+            a.trace = (traceLevel < 0 || traceLevel == levelIndex) ? traceBuf : nullptr;
+            ++levelIndex;
             if (L.groupCount == 0) continue;
             switch (C) {
                 case 1: big ? launchLevelCG<real, 1, kBigR>(a, L, cumMode) : launchLevelCG<real, 1, 1>(a, L, cumMode); break;
@@ -523,8 +534,9 @@ struct Engine {
         return BEAGLE_SUCCESS;
     }
 
+    // The root kernel wrote the scalar straight into pinned host memory (hOut is device-accessible through
+    // UVA): the 8-byte device->host transfer is part of the kernel, only the stream wait remains.
     int readScalar(double* out) {
-        CK(cudaMemcpyAsync(hOut, dOut, sizeof(double), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         blockInFlight = false;
         schedInFlight = false;
@@ -589,15 +601,15 @@ static int evalCommon(Engine& E, const StromEvalArgs* a, double* deviceOut) {
     std::memcpy(m->evals, a->eigenValues, sizeof(double) * 4);
     std::memcpy(m->weights, a->categoryWeights, sizeof(double) * E.C);
     std::memcpy(E.hHeader()->rates, a->categoryRates, sizeof(double) * E.C);
+    if (E.nScale < 1) return BEAGLE_ERROR_OUT_OF_RANGE;
+    E.uploadBlock();
+    E.launchMatrices();          // the GPU starts on the matrices while the host checks / rebuilds the plan
     rc = E.prepareSchedule(a->operations, a->operationCount, true);
     if (rc) return rc;
-    E.uploadBlock();
-    E.launchMatrices();
-    if (E.nScale < 1) return BEAGLE_ERROR_OUT_OF_RANGE;
     E.scaleBuffer(0);
     E.scaleZeroPending[0] = 1;
     E.launchPartials(0);
-    return E.launchRoot(a->rootParentBuffer, a->rootChildBuffer, a->rootMatrix, 0, 0, 0, deviceOut ? deviceOut : E.dOut);
+    return E.launchRoot(a->rootParentBuffer, a->rootChildBuffer, a->rootMatrix, 0, 0, 0, deviceOut ? deviceOut : E.hOut);
 }
 
 }  // namespace sb200
@@ -828,7 +840,7 @@ extern "C" int beagleCalculateEdgeLogLikelihoods(int instance, const int* parent
         return BEAGLE_ERROR_OUT_OF_RANGE;
     return withEngine(instance, [&](Engine& E) {
         int rc = E.launchRoot(parentBufferIndices[0], childBufferIndices[0], probabilityIndices[0],
-                              categoryWeightsIndices[0], stateFrequenciesIndices[0], cumulativeScaleIndices[0], E.dOut);
+                              categoryWeightsIndices[0], stateFrequenciesIndices[0], cumulativeScaleIndices[0], E.hOut);
         if (rc) return rc;
         return E.readScalar(outSumLogLikelihood);
     });
@@ -883,7 +895,7 @@ extern "C" int sb200ReplayAsync(int instance, double* deviceOut) {
         if (E.lastCumIndex != BEAGLE_OP_NONE) E.scaleZeroPending[E.lastCumIndex] = 1;
         E.launchPartials(E.lastCumIndex);
         return E.launchRoot(E.lastParent, E.lastChild, E.lastMatrix, E.lastWIdx, E.lastFIdx, E.lastRootCum,
-                            deviceOut ? deviceOut : E.dOut);
+                            deviceOut ? deviceOut : E.hOut);
     });
 }
 

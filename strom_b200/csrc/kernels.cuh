@@ -401,7 +401,10 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
 
     // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
 #ifdef SB200_TRACE
-#define SB200_TICK(slot) if (A.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && j < 60) A.trace[j * 8 + (slot)] = clock64();
+#ifndef SB200_TRACE_TID
+#define SB200_TRACE_TID 0
+#endif
+#define SB200_TICK(slot) if (A.trace && tid == SB200_TRACE_TID && blockIdx.x == 0 && blockIdx.y == 0 && j < 60) A.trace[j * 8 + (slot)] = clock64();
 #else
 #define SB200_TICK(slot)
 #endif

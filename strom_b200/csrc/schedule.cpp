@@ -6,17 +6,6 @@
 
 namespace sb200 {
 
-uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate) {
-    uint64_t h = 1469598103934665603ull ^ (accumulate ? 0x9e3779b97f4a7c15ull : 0);
-    const unsigned char* p = reinterpret_cast<const unsigned char*>(ops);
-    const size_t n = sizeof(BeagleOperation) * static_cast<size_t>(count);
-    for (size_t i = 0; i < n; ++i) {
-        h ^= p[i];
-        h *= 1099511628211ull;
-    }
-    return h;
-}
-
 static DevOp makeOp(int dest, int a, int ma, int b, int mb, int sa, int sb, int flags, int sOut) {
     DevOp d;
     d.dest = dest; d.a = a; d.ma = ma; d.b = b; d.mb = mb; d.sa = sa; d.sb = sb; d.flags = flags; d.sOut = sOut;

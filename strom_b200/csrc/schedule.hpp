@@ -89,7 +89,4 @@ struct Schedule {
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
                   int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out);
 
-// FNV-1a over the raw operation list, used to reuse a schedule when the topology is unchanged.
-uint64_t hashOps(const BeagleOperation* ops, int count, bool accumulate);
-
 }  // namespace sb200

@@ -29,3 +29,23 @@ for _ in range(n_eval):
     L.calc_log_likelihood(ea)
 print("fused call us/eval", (time.perf_counter() - t0) * 1e6 / n_eval)
 L.close()
+
+# host-side split of the fused call: enqueue (sb200EvalAsync returns) vs completion (sb200Finish)
+import ctypes as C
+from strom_b200.engine import api
+E = api()
+L2 = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], 4, device=0)
+E.lib.sb200Finish.argtypes = [C.c_int, C.POINTER(C.c_double)]
+out = C.c_double()
+for _ in range(20):
+    E.sb200EvalAsync(L2.inst, C.byref(ea.c), None); E.lib.sb200Finish(L2.inst, C.byref(out))
+te = tf = 0.0
+for _ in range(n_eval):
+    t0 = time.perf_counter()
+    E.sb200EvalAsync(L2.inst, C.byref(ea.c), None)
+    t1 = time.perf_counter()
+    E.lib.sb200Finish(L2.inst, C.byref(out))
+    t2 = time.perf_counter()
+    te += t1 - t0; tf += t2 - t1
+print("enqueue us %.1f  finish-wait us %.1f  total %.1f  logL %.6f" % (te * 1e6 / n_eval, tf * 1e6 / n_eval, (te + tf) * 1e6 / n_eval, out.value))
+L2.close()
