@@ -278,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
     tree, model, tips_h, lo, hi = synthetic_inputs(args, rank, world, dev)
     torch.cuda.empty_cache()
     Pl = hi - lo
-    L = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, distributed=distributed)
+    L = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, distributed=distributed, single=(args.dtype == "f32"))
     ea = EvalArgs(model, tree.ops, tree.pmatrix_index, tree.edge_lengths, tree.parent_buffer, 0)
     n, K, W = args.taxa, args.steps, args.warmup
 
@@ -352,7 +352,7 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
             "evals_per_sec": K / (dev_ms / 1000.0), "logL": logl, "logL_e2e": logl2,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": ea.h2d_bytes, "d2h_bytes_per_step": 8,
                     "evals_per_sec": K / (max(e2e_ms, e2e_wall_ms) / 1000.0), "ms_per_step_events": e2e_ms / K,
@@ -393,6 +393,7 @@ def main():
     ap.add_argument("--taxa", type=int, default=1000)
     ap.add_argument("--patterns", type=int, default=1000000)
     ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f32 = the stated FP32 variant (partials/matrices float)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rbcl738", action="store_true")
     args = ap.parse_args()
