@@ -492,11 +492,13 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
 #pragma unroll
                     for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_xor_sync(0xffffffffu, m[r], off));
                 }
+                // below this the hardware reciprocal seed (flush-to-zero) is not usable: exact division instead
+                constexpr real kTiny = sizeof(real) == 4 ? real(1e-30) : real(1e-290);
                 bool tiny = false;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     m[r] = (m[r] == real(0)) ? real(1) : m[r];
-                    tiny |= m[r] < real(1e-290);
+                    tiny |= m[r] < kTiny;
                 }
                 real inv[R];
                 if (!tiny) {
