@@ -112,6 +112,45 @@ def test_underflow_needs_rescaling(engine, oracle):
     assert rel_err(le, lo) < LOGL_RTOL
 
 
+def _shaped_problem(newick, npat, seed):
+    from oracle import strom_host_ref as H
+    rng = np.random.default_rng(seed)
+    tree = H.build_tree(newick)
+    ops, pidx, elen = H.define_operations(tree)
+    n = tree.nleaves
+    data = rng.integers(0, 4, size=(n, npat)).astype(np.uint8)
+    data[rng.random(data.shape) < 0.02] = 4
+    return dict(data=data, counts=rng.integers(1, 4, size=npat).astype(np.float64), ops=ops, pmatrix_index=pidx,
+                edge_lengths=elen, parent=np.int32(tree.preorder[0].number))
+
+
+@pytest.mark.parametrize("model", ["gtr_g4", "jc"])
+def test_caterpillar_tree_is_one_long_chain(engine, oracle, model):
+    # 700 taxa in a ladder: ONE chain of 698 operations, longer than the 256 operations a block keeps in shared
+    # memory (chunked path), with enough rescaling for the deferred log to fold several times
+    n = 700
+    nwk = "1:0.3"
+    for t in range(2, n - 1):
+        nwk = "(%s,%d:0.4):0.2" % (nwk, t)
+    nwk = "(%s,%d:0.3,%d:0.1)" % (nwk, n - 1, n)
+    fx = _shaped_problem(nwk, 70, 5)
+    m = named_model(model)
+    lo, le = full_eval(oracle, fx, m), full_eval(engine, fx, m)
+    assert np.isfinite(lo) and rel_err(le, lo) < LOGL_RTOL
+
+
+def test_balanced_tree_has_the_most_launches(engine, oracle):
+    def sub(lo, hi):
+        if hi - lo == 1:
+            return "%d:0.07" % (lo + 1)
+        mid = (lo + hi) // 2
+        return "(%s,%s):0.05" % (sub(lo, mid), sub(mid, hi))
+    nwk = "(%s,%s,%s)" % (sub(0, 86), sub(86, 171), sub(171, 256))
+    fx = _shaped_problem(nwk, 333, 6)
+    m = named_model("gtr_g4")
+    assert rel_err(full_eval(engine, fx, m), full_eval(oracle, fx, m)) < LOGL_RTOL
+
+
 def test_repeat_calls_and_changed_parameters(engine, oracle):
     # one instance, many calls: new edge lengths, new model, new topology (schedule cache must follow)
     fx = random_problem(40, 300, 21)
