@@ -83,7 +83,7 @@ def build_host(force: bool = False) -> str:
     """C++ host mirror of the reference's Likelihood/Model/Data/Tree classes, linked to the CUDA engine."""
     build_engine()
     if force or _stale(HOST_LIB, host_sources() + [ENGINE_LIB]):
-        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-DSTROM_B200_ENGINE",
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-pthread", "-DSTROM_B200_ENGINE",
                "-o", HOST_LIB, os.path.join(HOST_DIR, "capi.cpp"), "-L" + CSRC, "-lstrom_b200", "-Wl,-rpath,$ORIGIN/../csrc"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -96,7 +96,7 @@ def build_host_oracle(force: bool = False) -> str:
     """TEST ONLY: the same host classes on the reference's 13-call path, linked to the CPU checker."""
     build_oracle()
     if force or _stale(HOST_ORACLE_LIB, host_sources() + [ORACLE_LIB]):
-        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-pthread",
                "-o", HOST_ORACLE_LIB, os.path.join(HOST_DIR, "capi.cpp"), "-L" + os.path.dirname(ORACLE_LIB),
                "-loracle_beagle", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)

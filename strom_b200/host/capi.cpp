@@ -187,9 +187,12 @@ HOST_API int strom_loglik(int data_handle, const char* newick, const double* fre
 
 // Strom::run's MCMC branch on the host classes.  Fills `rows` (max_rows x 15 doubles: iteration, lnL,
 // lnPrior, TL, 6 exchangeabilities, 4 frequencies, alpha) with the cold chain's samples; returns the row count.
-HOST_API int strom_mcmc(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
-                        unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
-                        int ndevices, const int* devices, double* rows, int max_rows, double* seconds, char* err, int errlen) {
+// `flags`: 1 = every chain draws from its own random stream, 2 = chains are stepped side by side on host threads
+// (one heated chain per GPU; implies 1).  0 = the reference's single shared stream, chains in turn.
+HOST_API int strom_mcmc_ex(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
+                           unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
+                           int ndevices, const int* devices, unsigned flags, double* rows, int max_rows, double* seconds, char* err,
+                           int errlen) {
     try {
         McmcOptions opt;
         opt.seed = seed; opt.niter = niter; opt.burnin = burnin; opt.samplefreq = samplefreq ? samplefreq : 1; opt.nchains = nchains;
@@ -197,6 +200,8 @@ HOST_API int strom_mcmc(int data_handle, const char* newick, unsigned seed, unsi
         opt.statefreq.assign(freqs, freqs + 4);
         opt.rmatrix.assign(rmat, rmat + 6);
         if (ndevices > 0) opt.devices.assign(devices, devices + ndevices);
+        opt.perChainStreams = (flags & 1u) != 0;
+        opt.parallelChains = (flags & 2u) != 0;
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<TraceRow> tr = runMCMC(dataOf(data_handle), newick, opt);
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -209,3 +214,11 @@ HOST_API int strom_mcmc(int data_handle, const char* newick, unsigned seed, unsi
         return n;
     } catch (const std::exception& e) { return fail(e, err, errlen); }
 }
+
+HOST_API int strom_mcmc(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
+                        unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
+                        int ndevices, const int* devices, double* rows, int max_rows, double* seconds, char* err, int errlen) {
+    return strom_mcmc_ex(data_handle, newick, seed, niter, burnin, samplefreq, nchains, heatfactor, ncateg, gammashape, freqs, rmat,
+                         ndevices, devices, 0u, rows, max_rows, seconds, err, errlen);
+}
+

@@ -18,10 +18,15 @@
 //     topology + edge-length changes through the engine but is not the reference's 8-case proposal.
 #pragma once
 #include <cmath>
+#include <condition_variable>
+#include <exception>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "likelihood.hpp"
@@ -394,16 +399,84 @@ struct McmcOptions {
     std::vector<double> statefreq = {0.25, 0.25, 0.25, 0.25};
     std::vector<double> rmatrix = {1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6};   // on the simplex, like strom's default
     std::vector<int> devices = {0};          // chain c runs on devices[c % size]: one heated chain per GPU
+    // Reference behaviour (both false): ONE random stream shared by all chains, chains stepped one after the other
+    // (src/strom.hpp:316-402).  That order dependence is what forbids running the chains side by side, so:
+    bool perChainStreams = false;            // chain c draws from its own stream, seeded from (seed, c); the swap
+                                             // proposals keep the master stream.  Changes the trace (documented deviation).
+    bool parallelChains = false;             // step all chains at once, one host thread per chain (implies perChainStreams);
+                                             // the result does not depend on thread timing
+};
+
+// Runs body(c) for c = 0..n-1 on n persistent host threads, once per call of run(); rethrows the first failure.
+class ChainThreads {
+  public:
+    ChainThreads(unsigned n, std::function<void(unsigned)> body) : _n(n), _body(std::move(body)), _errors(n) {
+        for (unsigned c = 0; c < n; ++c) _threads.emplace_back([this, c] { loop(c); });
+    }
+    ~ChainThreads() {
+        {
+            std::lock_guard<std::mutex> lk(_mu);
+            _stop = true;
+        }
+        _go.notify_all();
+        for (std::thread& t : _threads) t.join();
+    }
+    void run() {
+        {
+            std::lock_guard<std::mutex> lk(_mu);
+            _pending = _n;
+            ++_generation;
+        }
+        _go.notify_all();
+        std::unique_lock<std::mutex> lk(_mu);
+        _finished.wait(lk, [this] { return _pending == 0; });
+        for (std::exception_ptr& e : _errors)
+            if (e) {
+                std::exception_ptr first = e;
+                for (std::exception_ptr& x : _errors) x = nullptr;
+                std::rethrow_exception(first);
+            }
+    }
+
+  private:
+    void loop(unsigned c) {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(_mu);
+                _go.wait(lk, [&] { return _stop || _generation != seen; });
+                if (_stop) return;
+                seen = _generation;
+            }
+            try {
+                _body(c);
+            } catch (...) {
+                _errors[c] = std::current_exception();
+            }
+            std::lock_guard<std::mutex> lk(_mu);
+            if (--_pending == 0) _finished.notify_one();
+        }
+    }
+    unsigned _n;
+    std::function<void(unsigned)> _body;
+    std::vector<std::exception_ptr> _errors;
+    std::vector<std::thread> _threads;
+    std::mutex _mu;
+    std::condition_variable _go, _finished;
+    unsigned long _generation = 0;
+    unsigned _pending = 0;
+    bool _stop = false;
 };
 
 // Strom::run's MCMC branch (src/strom.hpp:486-523): initChains, burn-in with tuning, sampling with swaps.
 inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& newick, const McmcOptions& opt) {
     Lot::SharedPtr lot(new Lot(opt.seed));
+    const bool ownStreams = opt.perChainStreams || opt.parallelChains;
     std::vector<Chain> chains(opt.nchains);
     for (unsigned c = 0; c < opt.nchains; ++c) {
         Chain& ch = chains[c];
         ch.setTreeFromNewick(newick);
-        ch.setLot(lot);
+        ch.setLot(ownStreams ? Lot::SharedPtr(new Lot(opt.seed + 1000003u * (c + 1))) : lot);
         Model::SharedPtr model(new Model());
         model->setExchangeabilitiesAndStateFreqs(opt.rmatrix, opt.statefreq);
         model->setGammaShape(opt.gammashape);
@@ -454,14 +527,24 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
             chains[j].setLambdas(li);
         }
     };
+    // one iteration of every chain: in turn (reference), or side by side -- one chain per GPU keeps all GPUs busy
+    int iteration = 0;
+    std::unique_ptr<ChainThreads> pool;
+    if (opt.parallelChains && opt.nchains > 1)
+        pool.reset(new ChainThreads(opt.nchains, [&](unsigned c) { chains[c].nextStep(iteration); }));
+    auto stepAll = [&](unsigned it) {
+        iteration = static_cast<int>(it);
+        if (pool) pool->run();
+        else for (Chain& ch : chains) ch.nextStep(iteration);
+    };
     sample(0);
     for (unsigned it = 1; it <= opt.burnin; ++it) {
-        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+        stepAll(it);
         swapChains();
     }
     for (Chain& ch : chains) ch.stopTuning();
     for (unsigned it = 1; it <= opt.niter; ++it) {
-        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+        stepAll(it);
         if (it % opt.samplefreq == 0) sample(it);
         swapChains();
     }

@@ -38,3 +38,20 @@ def test_chain_per_gpu_placement_runs():
     from strom_b200.host import host
     tr, sec = _run(host(), "rbcl738", niter=10, burnin=10, nchains=2, samplefreq=5, seed=1, devices=(0, 0))
     assert tr.shape[0] == 3 and np.all(np.isfinite(tr)) and tr[-1, 1] > tr[0, 1]
+
+
+def test_parallel_chains_match_cpu_call_path_and_turn_order():
+    """Config C5's driver: heated chains stepped side by side on host threads, one engine instance per chain, spread
+    over every visible GPU (all on device 0 when there is one).  Same trace as stepping them in turn, and as the
+    CPU call path, whatever the thread timing."""
+    import torch
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    devices = tuple(range(torch.cuda.device_count()))
+    kw = dict(niter=150, burnin=100, nchains=4, samplefreq=10, seed=99)
+    side, _ = _run(host(), "rbcl10", parallel_chains=True, devices=devices, **kw)
+    turn, _ = _run(host(), "rbcl10", per_chain_streams=True, devices=devices, **kw)
+    cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), "rbcl10", parallel_chains=True, **kw)
+    assert np.array_equal(side, turn)
+    rel = np.abs(side - cpu) / np.maximum(np.abs(cpu), 1e-300)
+    assert rel.max() <= 1e-9
