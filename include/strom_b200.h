@@ -92,6 +92,16 @@ STROM_API long sb200LaunchCount(int instance);
  * (unfused per-operation traffic), and the bytes the chain-fused schedule actually moves. */
 STROM_API int sb200LastTraffic(int instance, double* algorithmicBytes, double* scheduledBytes);
 
+/* Incremental evaluation (the reference recomputes every node on every call,
+ * src/likelihood.hpp:409-413).  With enable != 0 the instance keeps, for every partials buffer, the total
+ * log-scaler of the subtree below it (16 bytes per pattern and buffer of extra HBM), and an operation list given
+ * to beagleUpdatePartials / sb200Eval may then cover only the nodes whose partials changed since the previous
+ * call -- children before parents, ending at the root's partials -- together with only the transition matrices
+ * that changed: operands that the list does not produce are taken, with their subtree scalers, as the previous
+ * calls left them, and the cumulative scale buffer still receives the whole tree's log-scaler.  The first call
+ * after enabling must list every node.  Lists must be forests (no buffer written twice or read before written). */
+STROM_API int sb200SetSubtreeScalers(int instance, int enable);
+
 /* Host-only schedule inspection (no GPU needed): builds the chain/level schedule for an
  * operation list and reports, per operation, its level and chain id.  Returns the number of
  * levels (>= 0) or a negative error code.  chainOut/levelOut may be NULL. */

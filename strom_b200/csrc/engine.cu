@@ -77,6 +77,7 @@ struct Engine {
     DevOp* dOps = nullptr;
     Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
+    bool keepSubtreeScalers = false;      // incremental evaluation: permanent per-buffer subtree scaler slots (sb200SetSubtreeScalers)
     long long* dTrace = nullptr;          // tuning builds: per-step clock samples (sb200DebugTrace)
     int* dTTOps = nullptr;                // op index of every tip x tip table
     void* dTT = nullptr;                  // tip x tip tables
@@ -299,7 +300,7 @@ struct Engine {
             (count == 0 || std::memcmp(schedOps.data(), ops, sizeof(BeagleOperation) * count) == 0))
             return BEAGLE_SUCCESS;
         Schedule s;
-        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s);
+        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s, keepSubtreeScalers);
         if (rc != BEAGLE_SUCCESS) return rc;
         for (const DevOp& d : s.ops) {
             if (d.a >= 0 && d.a < nTips && !tipSet[d.a]) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -987,6 +988,17 @@ extern "C" __attribute__((visibility("default"))) int sb200DebugTrace(int instan
         if (out) {
             CK(cudaStreamSynchronize(E.stream));
             CK(cudaMemcpy(out, E.dTrace, sizeof(long long) * 480, cudaMemcpyDeviceToHost));
+        }
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200SetSubtreeScalers(int instance, int enable) {
+    return withEngine(instance, [&](Engine& E) {
+        const bool on = enable != 0;
+        if (on != E.keepSubtreeScalers) {
+            E.keepSubtreeScalers = on;
+            E.schedValid = false;                      // the plan depends on it
         }
         return static_cast<int>(BEAGLE_SUCCESS);
     });

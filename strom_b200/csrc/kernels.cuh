@@ -551,6 +551,22 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 }
             }
         }
+        if (flags & OP_STORE_S) {
+            // incremental plans: every node keeps the log-scaler of its subtree (the chain carries on)
+            const int sKeep = sops[j * kOpWords + 2].x;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double a = sAcc[r][tid], pr = prod[r];
+                if (pr < 1e-100) {
+                    a += foldedLog(pr, 1.0);
+                    pr = 1.0;
+                }
+                if (k == 0) {
+                    accMine[static_cast<size_t>(sKeep) * Ppad + r * G] = a;
+                    prodMine[static_cast<size_t>(sKeep) * Ppad + r * G] = pr;
+                }
+            }
+        }
         if (flags & OP_CHAIN_END) {
             const int sOut = sops[j * kOpWords + 2].x;
 #pragma unroll
@@ -694,6 +710,12 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int groupBase, const 
         real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride + static_cast<size_t>(p) * C * 4;
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) st4(dest + kk * 4, X[kk]);
+        if (op.flags & OP_STORE_S) {
+            double a = acc, pr = prod;
+            if (pr < 1e-100) foldProduct(a, pr, 1.0);
+            A.slotAcc[static_cast<size_t>(op.sOut) * Ppad + p] = a;
+            A.slotProd[static_cast<size_t>(op.sOut) * Ppad + p] = pr;
+        }
         if (op.flags & OP_CHAIN_END) {
             if (op.sOut >= 0) {
                 if (prod < 1e-100) foldProduct(acc, prod, 1.0);

@@ -29,7 +29,8 @@ static void assignTipTipTables(Schedule& out, int tipCount) {
 }
 
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
-                  int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out) {
+                  int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out,
+                  bool keepSubtreeScalers) {
     out = Schedule();
     const int nbuf = tipCount + partialsBufferCount;
     if (count < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -82,6 +83,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
         else ++out.nPartialPartial;
     };
 
+    if (!forest && keepSubtreeScalers && accumulate) return BEAGLE_ERROR_NO_IMPLEMENTATION;
     if (!forest) {
         // Conservative path: the list order is the only safe order; one operation per launch.
         for (int o = 0; o < count; ++o) {
@@ -144,7 +146,14 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
     std::vector<int> slotOfChain(nChains, -1);
     std::vector<int> roots;
     for (int o = 0; o < count; ++o) if (consumers[o] == 0) roots.push_back(o);
-    if (accumulate) {
+    const bool keep = keepSubtreeScalers && accumulate;
+    if (keep) {
+        // permanent slots, one per partials buffer; every chain end (and, below, every other operation) stores
+        for (int c = 0; c < nChains; ++c) slotOfChain[c] = ops[chainOps[c].back()].destinationPartials - tipCount;
+        out.slotCount = partialsBufferCount;
+        if (roots.size() > 1)
+            for (int r : roots) out.rootSlots.push_back(slotOfChain[out.opChain[r]]);
+    } else if (accumulate) {
         for (int c = 0; c < nChains; ++c) {
             const int last = chainOps[c].back();
             const bool isRoot = consumers[last] == 0;
@@ -190,8 +199,12 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
                 for (size_t j = 0; j < chainOps[c].size(); ++j) {
                     const int o = chainOps[c][j];
                     const BeagleOperation& op = ops[o];
-                    auto slotFor = [&](int inOp) {
-                        return (accumulate && inOp >= 0) ? slotOfChain[out.opChain[inOp]] : -1;
+                    // scaler that comes with an operand read from memory: its producer's chain slot, or (incremental
+                    // plans) the permanent slot of an internal buffer that an earlier call computed
+                    auto slotFor = [&](int inOp, int buffer) {
+                        if (!accumulate) return -1;
+                        if (inOp >= 0) return slotOfChain[out.opChain[inOp]];
+                        return (keep && buffer >= tipCount) ? buffer - tipCount : -1;
                     };
                     int fl = op.destinationScaleWrite >= 0 ? OP_RESCALE : 0;
                     if (j == 0) fl |= OP_CHAIN_START;
@@ -199,18 +212,24 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
                         fl |= OP_CHAIN_END;
                         if (dc.flags & CHAIN_ADD_TO_CUM) fl |= OP_ADD_TO_CUM;
                     }
-                    const int sOut = (j + 1 == chainOps[c].size()) ? dc.sOut : -1;
+                    int sOut = (j + 1 == chainOps[c].size()) ? dc.sOut : -1;
                     const int dest = op.destinationPartials - tipCount;
+                    if (keep && j + 1 < chainOps[c].size()) {
+                        fl |= OP_STORE_S;
+                        sOut = dest;
+                        out.scalerRows += 2;
+                    }
                     DevOp d;
                     if (carriedChild[o] < 0)
                         d = makeOp(dest, op.child1Partials, op.child1TransitionMatrix, op.child2Partials,
-                                   op.child2TransitionMatrix, slotFor(in1[o]), slotFor(in2[o]), fl, sOut);
+                                   op.child2TransitionMatrix, slotFor(in1[o], op.child1Partials),
+                                   slotFor(in2[o], op.child2Partials), fl, sOut);
                     else if (carriedChild[o] == 0)
                         d = makeOp(dest, -1, op.child1TransitionMatrix, op.child2Partials, op.child2TransitionMatrix, -1,
-                                   slotFor(in2[o]), fl, sOut);
+                                   slotFor(in2[o], op.child2Partials), fl, sOut);
                     else
                         d = makeOp(dest, -1, op.child2TransitionMatrix, op.child1Partials, op.child1TransitionMatrix, -1,
-                                   slotFor(in1[o]), fl, sOut);
+                                   slotFor(in1[o], op.child1Partials), fl, sOut);
                     if (d.a >= 0) (d.a < tipCount ? out.tipReads : out.partialReads) += 1;
                     (d.b < tipCount ? out.tipReads : out.partialReads) += 1;
                     out.scalerRows += 2 * ((d.sa >= 0) + (d.sb >= 0));

@@ -30,7 +30,7 @@ struct DevOp {
     int sa;      // subtree log-scaler slot to add for A, or -1
     int sb;      // subtree log-scaler slot to add for B, or -1
     int flags;   // OP_* bits
-    int sOut;    // OP_CHAIN_END: slot receiving the chain's subtree log-scaler, or -1
+    int sOut;    // OP_CHAIN_END / OP_STORE_S: slot receiving the subtree log-scaler of dest, or -1
     int tt;      // OP_TIPTIP: index of this operation's precomputed (stateA, stateB) table
     int pad[2];
 };
@@ -41,7 +41,9 @@ enum {
     OP_ADD_TO_CUM = 8,     // with OP_CHAIN_END: the chain total goes into the cumulative buffer
     OP_TIPTIP = 16,        // both operands are tips: the result is one of 25 precomputed vectors per category
     OP_A_TIP = 32,         // operand A is a tip (only with OP_CHAIN_START)
-    OP_B_TIP = 64          // operand B is a tip
+    OP_B_TIP = 64,         // operand B is a tip
+    OP_STORE_S = 128       // plans that keep every node's subtree log-scaler: store the running scaler in slot
+                           // sOut and carry on (a chain end stores and resets, as always)
 };
 
 // Host-side view of a chain (device code only sees the flags above).
@@ -86,7 +88,13 @@ struct Schedule {
 // Returns BEAGLE_SUCCESS or an error code (index out of range, unsupported scale-read).
 // `groupsPerLevel`: how many thread-block groups a launch should be split into at most (the engine
 // derives it from the pattern-tile count so that every launch has enough blocks to fill the GPU).
+// `keepSubtreeScalers`: incremental evaluation.  Slot s = (buffer s + tipCount) permanently holds the total
+// log-scaler of the subtree below that buffer: every operation stores its own, and an operand that is an
+// internal buffer NOT produced by this list contributes the value an earlier call left in its slot.  The
+// list may then cover only the nodes whose partials changed (children before parents, up to the root) and
+// the cumulative buffer still receives the whole tree's scaler.  The list must be a forest.
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
-                  int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out);
+                  int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out,
+                  bool keepSubtreeScalers = false);
 
 }  // namespace sb200

@@ -42,6 +42,7 @@ class EngineAPI:
             "sb200ReplayAsync": (C.c_int, [C.c_int, C.c_void_p]),
             "sb200Synchronize": (C.c_int, [C.c_int]),
             "sb200SetProfiling": (C.c_int, [C.c_int, C.c_int]),
+            "sb200SetSubtreeScalers": (C.c_int, [C.c_int, C.c_int]),
             "sb200PartialsTime": (C.c_int, [C.c_int, _DP, C.POINTER(C.c_long)]),
             "sb200LaunchCount": (C.c_long, [C.c_int]),
             "sb200LastTraffic": (C.c_int, [C.c_int, _DP, _DP]),

@@ -250,3 +250,56 @@ def test_many_instances_coexist(engine):
         assert rel_err(ll, float(fx["lnL_" + name])) < LOGL_RTOL
     for inst in insts:
         engine.finalize(inst)
+
+
+@pytest.mark.parametrize("source,model,seed", [(("random", 40, 300), "gtr_g4", 1), (("random", 25, 70), "gtr_g3", 2),
+                                               (("random", 60, 2000), "jc", 3), (("golden", "rbcl738"), "gtr_g4", 4),
+                                               (("random", 120, 500), "gtr_g8", 5)])
+def test_incremental_lists_cover_only_the_changed_path(engine, oracle, source, model, seed):
+    """with sb200SetSubtreeScalers the operation list may hold only the nodes above the
+    edges that changed (and only the changed matrices); logL must equal a full evaluation of the CPU oracle."""
+    fx = random_problem(source[1], source[2], 100 + seed) if source[0] == "random" else load_golden(source[1])
+    m = named_model(model)
+    ops = np.asarray(fx["ops"], dtype=np.int32).reshape(-1, 7)
+    pidx = np.asarray(fx["pmatrix_index"], dtype=np.int32)
+    el = np.asarray(fx["edge_lengths"], dtype=np.float64).copy()
+    parent = int(fx["parent"])
+    parent_of = {}
+    for o in ops:
+        parent_of[int(o[3])] = int(o[0])
+        parent_of[int(o[5])] = int(o[0])
+    n, P = fx["data"].shape
+    ie, io = engine.create(n, P, len(m["rates"])), oracle.create(n, P, len(m["rates"]))
+    for api, inst in ((engine, ie), (oracle, io)):
+        api.set_data(inst, fx["data"].astype(np.int32), fx["counts"])
+    engine.lib.sb200SetSubtreeScalers.argtypes = [C.c_int, C.c_int]
+    assert engine.lib.sb200SetSubtreeScalers(ie, 1) == 0
+    a = engine.calc_log_likelihood(ie, m, ops, pidx, el, parent, 0)
+    b = oracle.calc_log_likelihood(io, m, ops, pidx, el, parent, 0)
+    assert rel_err(a, b) < LOGL_RTOL
+    rng = np.random.default_rng(seed)
+    sizes = []
+    for it in range(12):
+        changed = rng.choice(pidx.size, size=int(rng.integers(1, 4)), replace=False)
+        if it == 5:
+            changed = np.array([pidx.size - 1])                     # the root edge alone: no partial changes at all
+        el[changed] *= rng.uniform(0.3, 2.0, size=changed.size)
+        dirty = {parent}                                            # the root's partials are always listed
+        for e in changed:
+            v = parent_of.get(int(pidx[e])) if e != pidx.size - 1 else None
+            while v is not None:
+                dirty.add(v)
+                v = parent_of.get(v)
+        sub = np.array([o for o in ops if int(o[0]) in dirty], dtype=np.int32)
+        sizes.append(len(sub))
+        a = engine.calc_log_likelihood(ie, m, sub, pidx[changed], el[changed], parent, 0)
+        b = oracle.calc_log_likelihood(io, m, ops, pidx, el, parent, 0)
+        assert rel_err(a, b) < LOGL_RTOL, (it, len(sub))
+    assert min(sizes) == 1 and max(sizes) < len(ops)
+    # a new model invalidates everything: full list again, then incremental lists keep working
+    m2 = named_model("gtr_i_g4" if len(m["rates"]) == 4 else model)
+    a = engine.calc_log_likelihood(ie, m2, ops, pidx, el, parent, 0)
+    b = oracle.calc_log_likelihood(io, m2, ops, pidx, el, parent, 0)
+    assert rel_err(a, b) < LOGL_RTOL
+    engine.finalize(ie)
+    oracle.finalize(io)
