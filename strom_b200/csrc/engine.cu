@@ -83,6 +83,22 @@ struct Engine {
     void* dTT = nullptr;                  // tip x tip tables
     size_t ttOpsCap = 0, ttCap = 0;
     size_t opsCap = 0, groupsCap = 0, rootCap = 0;
+    // Plans that are not the active one but still sit in HBM, most recently used last.  An incremental MCMC
+    // alternates between the full list (every change of the model) and short path lists: without these the
+    // 700-operation plan would be rebuilt and uploaded again after every tree move.
+    struct ParkedPlan {
+        Schedule sched;
+        bool accumulate = false, valid = false;
+        std::vector<BeagleOperation> key;
+        DevOp* dOps = nullptr;
+        Group* dGroups = nullptr;
+        int* dRootSlots = nullptr;
+        int* dTTOps = nullptr;
+        void* dTT = nullptr;
+        size_t ttOpsCap = 0, ttCap = 0, opsCap = 0, groupsCap = 0, rootCap = 0;
+    };
+    static constexpr size_t kParkedPlans = 3;
+    std::vector<ParkedPlan> parked;
     void* hSchedStage = nullptr;          // pinned staging for schedule uploads
     size_t schedStageCap = 0;
     cudaEvent_t schedCopied = nullptr;
@@ -125,6 +141,7 @@ struct Engine {
         for (double* p : dScale) cudaFree(p);
         dScale.clear();
         cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dGroups); cudaFree(dRootSlots); cudaFree(dTTOps); cudaFree(dTT);
+        freeParkedPlans();
         cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut);
         if (hBlock) cudaFreeHost(hBlock);
         if (hSchedStage) cudaFreeHost(hSchedStage);
@@ -293,12 +310,54 @@ struct Engine {
         return std::max(1, (8 * slots + tiles - 1) / tiles);
     }
 
+    // active plan <-> parked plan (pointer and vector swaps only)
+    void swapPlan(ParkedPlan& p) {
+        std::swap(sched, p.sched);
+        std::swap(schedAccumulate, p.accumulate);
+        std::swap(schedValid, p.valid);
+        std::swap(schedOps, p.key);
+        std::swap(dOps, p.dOps);
+        std::swap(dGroups, p.dGroups);
+        std::swap(dRootSlots, p.dRootSlots);
+        std::swap(dTTOps, p.dTTOps);
+        std::swap(dTT, p.dTT);
+        std::swap(ttOpsCap, p.ttOpsCap);
+        std::swap(ttCap, p.ttCap);
+        std::swap(opsCap, p.opsCap);
+        std::swap(groupsCap, p.groupsCap);
+        std::swap(rootCap, p.rootCap);
+    }
+    void forgetPlans() {
+        schedValid = false;
+        for (ParkedPlan& p : parked) p.valid = false;
+    }
+    void freeParkedPlans() {
+        for (ParkedPlan& p : parked) {
+            cudaFree(p.dOps); cudaFree(p.dGroups); cudaFree(p.dRootSlots); cudaFree(p.dTTOps); cudaFree(p.dTT);
+        }
+        parked.clear();
+    }
+
     int prepareSchedule(const BeagleOperation* ops, int count, bool accumulate) {
         // same operation list as last call (the common case: 4 of strom's 5 updaters do not touch the
         // topology): reuse the plan that is already in HBM.  One memcmp of 28 bytes per operation.
-        if (schedValid && schedAccumulate == accumulate && static_cast<int>(schedOps.size()) == count &&
-            (count == 0 || std::memcmp(schedOps.data(), ops, sizeof(BeagleOperation) * count) == 0))
-            return BEAGLE_SUCCESS;
+        auto same = [&](bool valid, bool acc, const std::vector<BeagleOperation>& key) {
+            return valid && acc == accumulate && static_cast<int>(key.size()) == count &&
+                   (count == 0 || std::memcmp(key.data(), ops, sizeof(BeagleOperation) * count) == 0);
+        };
+        if (same(schedValid, schedAccumulate, schedOps)) return BEAGLE_SUCCESS;
+        for (size_t i = parked.size(); i-- > 0;)
+            if (same(parked[i].valid, parked[i].accumulate, parked[i].key)) {
+                swapPlan(parked[i]);                                   // the plan that was active takes its place ...
+                std::rotate(parked.begin() + i, parked.begin() + i + 1, parked.end());   // ... as the most recently used
+                return BEAGLE_SUCCESS;
+            }
+        // miss: park the active plan; the new one is built over the least recently used set of device arrays
+        if (schedValid) {
+            if (parked.size() < kParkedPlans) parked.insert(parked.begin(), ParkedPlan());
+            swapPlan(parked.front());
+            std::rotate(parked.begin(), parked.begin() + 1, parked.end());
+        }
         Schedule s;
         int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s, keepSubtreeScalers);
         if (rc != BEAGLE_SUCCESS) return rc;
@@ -729,7 +788,7 @@ static int setTipsCommon(Engine& E, int tipIndex, const int* s32, const unsigned
                        cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));   // pageable source: make the copy's completion explicit
     E.tipSet[tipIndex] = 1;
-    E.schedValid = false;
+    E.forgetPlans();
     return BEAGLE_SUCCESS;
 }
 
@@ -998,7 +1057,7 @@ extern "C" int sb200SetSubtreeScalers(int instance, int enable) {
         const bool on = enable != 0;
         if (on != E.keepSubtreeScalers) {
             E.keepSubtreeScalers = on;
-            E.schedValid = false;                      // the plan depends on it
+            E.forgetPlans();                           // every plan depends on it
         }
         return static_cast<int>(BEAGLE_SUCCESS);
     });

@@ -36,6 +36,8 @@ class HostAPI:
                                  _DP, _DP, C.c_int, _IP, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         L.strom_mcmc_ex.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint,
                                     C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
+        L.strom_incremental_walk.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, C.c_uint, C.c_int,
+                                             _DP, _DP, _IP, _DP, _DP, C.c_char_p, C.c_int]
         self._err = C.create_string_buffer(1024)
 
     def _check(self, rc):
@@ -105,7 +107,8 @@ class HostAPI:
     # ---- MCMC (callers of the hot path) ------------------------------------------------------
     def mcmc(self, data_handle: int, newick: str, seed: int = 13579, niter: int = 100, burnin: int = 100, samplefreq: int = 1,
              nchains: int = 1, heatfactor: float = 0.5, ncateg: int = 4, gammashape: float = 0.5, freqs=(0.25,) * 4,
-             rmat=(1.0 / 6,) * 6, devices=(0,), per_chain_streams: bool = False, parallel_chains: bool = False):
+             rmat=(1.0 / 6,) * 6, devices=(0,), per_chain_streams: bool = False, parallel_chains: bool = False,
+             incremental: bool = False):
         """Returns (trace [rows][15] = iteration, lnL, lnPrior, TL, 6 r, 4 pi, alpha; seconds).
 
         ``parallel_chains``: the heated chains are stepped side by side on host threads (one chain per GPU of
@@ -116,12 +119,28 @@ class HostAPI:
         max_rows = niter // max(samplefreq, 1) + 2
         rows = np.zeros((max_rows, 15))
         sec = C.c_double()
-        flags = (1 if per_chain_streams else 0) | (2 if parallel_chains else 0)
+        flags = (1 if per_chain_streams else 0) | (2 if parallel_chains else 0) | (4 if incremental else 0)
         n = self._check(self.lib.strom_mcmc_ex(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor,
                                                ncateg, gammashape, f.ctypes.data_as(_DP), r.ctypes.data_as(_DP), int(dev.size),
                                                dev.ctypes.data_as(_IP), flags, rows.ctypes.data_as(_DP), max_rows, C.byref(sec),
                                                self._err, 1024))
         return rows[:n].copy(), sec.value
+
+
+    def incremental_walk(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0,
+                         device: int = 0, seed: int = 1, nsteps: int = 100):
+        """Random tree moves evaluated incrementally and in full: (incremental logL[], full logL[], ops listed[],
+        seconds per incremental evaluation, seconds per full evaluation)."""
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        r = np.ascontiguousarray(rmat, dtype=np.float64)
+        a, b = np.zeros(nsteps), np.zeros(nsteps)
+        k = np.zeros(nsteps, dtype=np.int32)
+        si, sf = C.c_double(), C.c_double()
+        n = self._check(self.lib.strom_incremental_walk(data_handle, newick.encode(), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
+                                                        shape, ncat, pinvar, device, seed, nsteps, a.ctypes.data_as(_DP),
+                                                        b.ctypes.data_as(_DP), k.ctypes.data_as(_IP), C.byref(si), C.byref(sf),
+                                                        self._err, 1024))
+        return a[:n], b[:n], k[:n], si.value, sf.value
 
 
 _host = None

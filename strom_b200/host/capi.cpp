@@ -185,10 +185,83 @@ HOST_API int strom_loglik(int data_handle, const char* newick, const double* fre
     } catch (const std::exception& e) { return fail(e, err, errlen); }
 }
 
+// A random walk of LOCAL-style tree moves (three edges rescaled, half of them with an NNI swap; half of the moves
+// taken back afterwards, as a rejected proposal would be; every 16th step a new gamma shape) evaluated twice per
+// step: by a Likelihood with incremental evaluation and by one that recomputes everything.  Fills, per step, both
+// log-likelihoods and the number of operations the incremental one listed; returns the number of steps.
+HOST_API int strom_incremental_walk(int data_handle, const char* newick, const double* freqs, const double* rmat, double shape, int ncat,
+                                    double pinvar, int device, unsigned seed, int nsteps, double* incremental_logl, double* full_logl,
+                                    int* incremental_ops, double* seconds_incremental, double* seconds_full, char* err, int errlen) {
+    try {
+        Data::SharedPtr d = dataOf(data_handle);
+        TreeManip tm;
+        tm.buildFromNewick(newick, false, false);
+        Likelihood::SharedPtr inc(new Likelihood()), full(new Likelihood());
+        Model::SharedPtr model = makeModel(freqs, rmat, shape, ncat, pinvar);
+        for (Likelihood::SharedPtr L : {inc, full}) {
+            L->setQuiet(true);
+            L->setDevices(std::vector<int>(1, device));
+            L->setData(d);
+            L->setModel(model);
+        }
+        inc->setIncremental(true);
+        Lot lot(seed);
+        double ti = 0.0, tf = 0.0;
+        int step = 0;
+        auto evaluate = [&]() {
+            auto t0 = std::chrono::steady_clock::now();
+            incremental_logl[step] = inc->calcLogLikelihood(tm.getTree());
+            auto t1 = std::chrono::steady_clock::now();
+            full_logl[step] = full->calcLogLikelihood(tm.getTree());
+            auto t2 = std::chrono::steady_clock::now();
+            if (step > 0) {
+                ti += std::chrono::duration<double>(t1 - t0).count();
+                tf += std::chrono::duration<double>(t2 - t1).count();
+            }
+            incremental_ops[step] = static_cast<int>(inc->lastOperationCount());
+            ++step;
+        };
+        evaluate();
+        while (step < nsteps) {
+            if (step % 16 == 15) {
+                model->setGammaShape(shape * std::exp(lot.uniform() - 0.5));
+                evaluate();
+                continue;
+            }
+            Node* x = tm.randomInternalEdge(lot.uniform());
+            Node* a = x->getLeftChild();
+            Node* b = a->getRightSib();
+            Node* y = x->getParent();
+            Node* dsib = (x == y->getLeftChild()) ? x->getRightSib() : y->getLeftChild();
+            Node* top = lot.uniform() < 0.5 ? a : b;
+            const double lt = top->getEdgeLength(), lm = x->getEdgeLength(), lb = dsib->getEdgeLength();
+            const double m = std::exp(0.4 * (lot.uniform() - 0.5));
+            top->setEdgeLength(m * lt);
+            x->setEdgeLength(m * lm);
+            dsib->setEdgeLength(m * lb);
+            const bool swapped = lot.uniform() < 0.5;
+            Node* moved = (top == a) ? b : a;
+            if (swapped) tm.nniNodeSwap(moved, dsib);
+            evaluate();
+            if (step < nsteps && lot.uniform() < 0.5) {           // take the move back, as a rejection does
+                if (swapped) tm.nniNodeSwap(dsib, moved);
+                top->setEdgeLength(lt);
+                x->setEdgeLength(lm);
+                dsib->setEdgeLength(lb);
+                evaluate();
+            }
+        }
+        if (seconds_incremental) *seconds_incremental = ti / std::max(1, step - 1);
+        if (seconds_full) *seconds_full = tf / std::max(1, step - 1);
+        return step;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
 // Strom::run's MCMC branch on the host classes.  Fills `rows` (max_rows x 15 doubles: iteration, lnL,
 // lnPrior, TL, 6 exchangeabilities, 4 frequencies, alpha) with the cold chain's samples; returns the row count.
 // `flags`: 1 = every chain draws from its own random stream, 2 = chains are stepped side by side on host threads
-// (one heated chain per GPU; implies 1).  0 = the reference's single shared stream, chains in turn.
+// (one heated chain per GPU; implies 1), 4 = incremental likelihood (only the changed path is re-evaluated).
+// 0 = the reference's single shared stream, chains in turn, every node recomputed on every call.
 HOST_API int strom_mcmc_ex(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
                            unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
                            int ndevices, const int* devices, unsigned flags, double* rows, int max_rows, double* seconds, char* err,
@@ -202,6 +275,7 @@ HOST_API int strom_mcmc_ex(int data_handle, const char* newick, unsigned seed, u
         if (ndevices > 0) opt.devices.assign(devices, devices + ndevices);
         opt.perChainStreams = (flags & 1u) != 0;
         opt.parallelChains = (flags & 2u) != 0;
+        opt.incremental = (flags & 4u) != 0;
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<TraceRow> tr = runMCMC(dataOf(data_handle), newick, opt);
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -53,6 +53,13 @@ class Likelihood {
     void setSinglePrecision(bool on);         // FP32 partials / matrices variant (scalers stay FP64)
     void setQuiet(bool quiet) { _quiet = quiet; }
     unsigned numShards() const { return static_cast<unsigned>(_instances.size()); }
+    // Incremental evaluation (the reference recomputes everything, src/likelihood.hpp:409-413):
+    // calcLogLikelihood compares the tree and model with what the engine holds from the previous call and lists only
+    // the nodes whose partials changed (the path from every touched edge to the root) and only the transition
+    // matrices that changed.  A new model or a different Tree object falls back to the full list.  No updater has to
+    // cooperate: a rejected move is simply the next difference.  Has no effect on the CPU call path.
+    void setIncremental(bool on);
+    unsigned lastOperationCount() const { return static_cast<unsigned>(_operations.size() / 7); }
 
     typedef std::shared_ptr<Likelihood> SharedPtr;
 
@@ -64,6 +71,9 @@ class Likelihood {
     void setDiscreteGammaShape();
     void setModelRateMatrix();
     void defineOperations(Tree::SharedPtr t);
+    bool defineChangedOperations(Tree::SharedPtr t);
+    void rememberState(Tree::SharedPtr t, double log_likelihood);
+    void modelNumbers(std::vector<double>& v) const;
     void updateTransitionMatrices();
     void calculatePartials();
     std::string errorText(int code) const;
@@ -85,10 +95,22 @@ class Likelihood {
     bool _single;
     bool _quiet;
     bool _using_data;
+
+    // what the engine holds from the previous call (incremental evaluation)
+    bool _incremental;
+    bool _remembered;
+    const Tree* _held_tree;
+    std::vector<int> _buffer_of;         // by node slot (index in Tree::_nodes): buffer = matrix index, frozen at the first call
+    std::vector<int> _held_left, _held_right;   // by buffer: buffers of the two children the partials were computed from
+    std::vector<double> _held_length;    // by matrix index: edge length its transition matrices were computed from
+    std::vector<double> _held_model;
+    double _held_log_likelihood;
+    std::vector<char> _changed;          // scratch, by buffer
 };
 
 inline Likelihood::Likelihood()
-    : _ntaxa(0), _nstates(0), _npatterns(0), _rooted(false), _prefer_gpu(true), _single(false), _quiet(false), _using_data(true) {
+    : _ntaxa(0), _nstates(0), _npatterns(0), _rooted(false), _prefer_gpu(true), _single(false), _quiet(false), _using_data(true),
+      _incremental(false), _remembered(false), _held_tree(nullptr), _held_log_likelihood(0.0) {
     _model = Model::SharedPtr(new Model());
     _devices.assign(1, 0);
     // BeagleLib error codes, so that useful messages reach the user (reference src/likelihood.hpp:79-87)
@@ -109,6 +131,7 @@ inline std::string Likelihood::errorText(int code) const {
 }
 
 inline void Likelihood::finalizeInstances() {
+    _remembered = false;
     for (int inst : _instances) {
         const int code = beagleFinalizeInstance(inst);
         if (code != 0) throw XStrom("Likelihood failed to finalize BeagleLib instance. " + errorText(code));
@@ -210,6 +233,12 @@ inline void Likelihood::initBeagleLib() {
             throw XStrom("Likelihood init function failed to create Likelihood instance (" + errorText(inst) + ")");
         }
         _instances.push_back(inst);
+#ifdef STROM_B200_ENGINE
+        if (_incremental) {
+            const int code = sb200SetSubtreeScalers(inst, 1);
+            if (code != 0) throw XStrom("failed to switch incremental evaluation. " + errorText(code));
+        }
+#endif
     }
     setTipStates();
     setPatternWeights();
@@ -297,6 +326,106 @@ inline void Likelihood::defineOperations(Tree::SharedPtr t) {
     if (!t->_is_rooted) _pmatrix_index[_pmatrix_index.size() - 1] = t->_root->_number;
 }
 
+inline void Likelihood::setIncremental(bool on) {
+#ifdef STROM_B200_ENGINE
+    if (on == _incremental) return;
+    _incremental = on;
+    _remembered = false;
+    for (int inst : _instances) {
+        const int code = sb200SetSubtreeScalers(inst, on ? 1 : 0);
+        if (code != 0) throw XStrom("failed to switch incremental evaluation. " + errorText(code));
+    }
+#else
+    (void)on;
+#endif
+}
+
+// the numbers the engine turns into transition matrices and root frequencies
+inline void Likelihood::modelNumbers(std::vector<double>& v) const {
+    v.clear();
+    v.insert(v.end(), _model->_eigenvectors, _model->_eigenvectors + 16);
+    v.insert(v.end(), _model->_inverse_eigenvectors, _model->_inverse_eigenvectors + 16);
+    v.insert(v.end(), _model->_eigenvalues, _model->_eigenvalues + 4);
+    v.insert(v.end(), _model->_state_freqs.begin(), _model->_state_freqs.end());
+    v.insert(v.end(), _model->_relative_rates.begin(), _model->_relative_rates.end());
+    v.insert(v.end(), _model->_rate_probs.begin(), _model->_rate_probs.end());
+}
+
+// Like defineOperations, but lists only what differs from the remembered state.  Buffers are tied to node OBJECTS
+// (refreshPreorder renumbers the internal nodes after every topology change, src/tree_manip.hpp, which would make
+// every number-keyed buffer look stale).  Returns false if nothing at all changed.
+inline bool Likelihood::defineChangedOperations(Tree::SharedPtr t) {
+    _operations.clear();
+    _pmatrix_index.clear();
+    _edge_lengths.clear();
+    const Node* base = &t->_nodes[0];
+    std::vector<double> model;
+    modelNumbers(model);
+    const bool fresh = !_remembered || _held_tree != t.get() || model != _held_model || _buffer_of.size() != t->_nodes.size();
+    if (fresh) {
+        _buffer_of.assign(t->_nodes.size(), -1);
+        for (Node* nd : t->_levelorder) _buffer_of[nd - base] = nd->_number;
+        const size_t nbuf = 2 * static_cast<size_t>(_ntaxa);
+        _held_left.assign(nbuf, -1);
+        _held_right.assign(nbuf, -1);
+        _held_length.assign(nbuf, -1.0);
+    }
+    _changed.assign(2 * static_cast<size_t>(_ntaxa), 0);      // 1: edge above changed, 2: partials must be recomputed
+    Node* top = t->_preorder[0];
+    const int root_matrix = t->_root->_number;
+    for (size_t i = t->_levelorder.size(); i-- > 0;) {
+        Node* nd = t->_levelorder[i];
+        const int buf = _buffer_of[nd - base];
+        const int mat = (nd == top) ? root_matrix : buf;
+        if (fresh || nd->_edge_length != _held_length[mat]) {
+            _pmatrix_index.push_back(mat);
+            _edge_lengths.push_back(nd->_edge_length);
+            _changed[buf] |= 1;
+        }
+        if (nd->_left_child) {
+            const int l = _buffer_of[nd->_left_child - base], r = _buffer_of[nd->_left_child->_right_sib - base];
+            if (fresh || l != _held_left[buf] || r != _held_right[buf] || _changed[l] || _changed[r]) _changed[buf] |= 2;
+        }
+    }
+    if (_pmatrix_index.empty()) {
+        bool any = false;
+        for (char c : _changed) any = any || (c & 2);
+        if (!any) return false;
+    }
+    _changed[_buffer_of[top - base]] |= 2;                       // the root's partials are always listed (they carry the scaler)
+    for (size_t i = t->_levelorder.size(); i-- > 0;) {
+        Node* nd = t->_levelorder[i];
+        const int buf = _buffer_of[nd - base];
+        if (!nd->_left_child || !(_changed[buf] & 2)) continue;
+        const int l = _buffer_of[nd->_left_child - base], r = _buffer_of[nd->_left_child->_right_sib - base];
+        _operations.push_back(buf);
+        _operations.push_back(buf - static_cast<int>(_ntaxa) + 1);
+        _operations.push_back(BEAGLE_OP_NONE);
+        _operations.push_back(l);
+        _operations.push_back(l);
+        _operations.push_back(r);
+        _operations.push_back(r);
+    }
+    return true;
+}
+
+inline void Likelihood::rememberState(Tree::SharedPtr t, double log_likelihood) {
+    const Node* base = &t->_nodes[0];
+    Node* top = t->_preorder[0];
+    for (Node* nd : t->_levelorder) {
+        const int buf = _buffer_of[nd - base];
+        _held_length[(nd == top) ? t->_root->_number : buf] = nd->_edge_length;
+        if (nd->_left_child) {
+            _held_left[buf] = _buffer_of[nd->_left_child - base];
+            _held_right[buf] = _buffer_of[nd->_left_child->_right_sib - base];
+        }
+    }
+    modelNumbers(_held_model);
+    _held_tree = t.get();
+    _held_log_likelihood = log_likelihood;
+    _remembered = true;
+}
+
 inline void Likelihood::updateTransitionMatrices() {
     for (int inst : _instances) {
         const int code = beagleUpdateTransitionMatrices(inst, 0, &_pmatrix_index[0], NULL, NULL, &_edge_lengths[0],
@@ -325,10 +454,15 @@ inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
     // "root" is leaf 0 and has exactly one child
     assert(t->_root->_number == 0 && t->_root->_left_child == t->_preorder[0] && !t->_preorder[0]->_right_sib);
 
-    defineOperations(t);
+    if (_incremental) {
+        if (!defineChangedOperations(t)) return _held_log_likelihood;
+        _remembered = false;                             // until this call has succeeded
+    } else {
+        defineOperations(t);
+    }
     assert(_pmatrix_index.size() == _edge_lengths.size());
     int index_focal_child = t->_root->_number;           // the root tip
-    int index_focal_parent = t->_preorder[0]->_number;   // its only child
+    int index_focal_parent = _incremental ? _buffer_of[t->_preorder[0] - &t->_nodes[0]] : t->_preorder[0]->_number;   // its only child
     double log_likelihood = 0.0;
 
 #ifdef STROM_B200_ENGINE
@@ -358,6 +492,7 @@ inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
         if (code != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(code));
         log_likelihood += part;
     }
+    if (_incremental) rememberState(t, log_likelihood);
 #else
     setModelRateMatrix();
     setDiscreteGammaShape();

@@ -403,6 +403,7 @@ struct McmcOptions {
     // (src/strom.hpp:316-402).  That order dependence is what forbids running the chains side by side, so:
     bool perChainStreams = false;            // chain c draws from its own stream, seeded from (seed, c); the swap
                                              // proposals keep the master stream.  Changes the trace (documented deviation).
+    bool incremental = false;                // Likelihood::setIncremental: tree moves re-evaluate only the changed path (engine builds)
     bool parallelChains = false;             // step all chains at once, one host thread per chain (implies perChainStreams);
                                              // the result does not depend on thread timing
 };
@@ -483,6 +484,7 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         model->setGammaNCateg(opt.ncateg);
         Likelihood::SharedPtr lik(new Likelihood());
         lik->setQuiet(true);
+        lik->setIncremental(opt.incremental);
         lik->setDevices(std::vector<int>(1, opt.devices[c % opt.devices.size()]));
         lik->setData(data);
         lik->setModel(model);

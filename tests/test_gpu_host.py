@@ -58,3 +58,28 @@ def test_fp32_facade(hostlib):
     ll, _ = hostlib.loglik(h, str(fx["newick"]), *MODEL_ARGS["gtr_g4"], single=True)
     assert rel_err(ll, float(fx["lnL_gtr_g4"])) < 2e-5
     hostlib.data_free(h)
+
+
+@pytest.mark.parametrize("key,ncat,pinvar,nsteps", [("rbcl10", 4, 0.0, 200), ("rbcL", 1, 0.0, 120), ("rbcl738", 4, 0.2, 150)])
+def test_incremental_likelihood_follows_tree_moves(key, ncat, pinvar, nsteps):
+    """Likelihood::setIncremental: after LOCAL-style moves (with and without NNI), take-backs and model changes the
+    incremental facade lists a handful of operations and returns the log-likelihood of a full evaluation."""
+    from helpers import PAUP_ALPHA, PAUP_PI, PAUP_R
+    from strom_b200.host import host
+    api = host()
+    fx = load_golden(key)
+    cols = np.repeat(np.arange(fx["data"].shape[1]), fx["counts"].astype(int))
+    h = api.data_from_codes(fx["data"].astype(np.int32)[:, cols], compress=True)
+    inc, full, nops, _, _ = api.incremental_walk(h, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, ncat, pinvar, nsteps=nsteps, seed=11)
+    api.data_free(h)
+    ntaxa = fx["data"].shape[0]
+    assert len(inc) == nsteps and np.all(np.isfinite(inc))
+    assert np.max(np.abs(inc - full) / np.abs(full)) < 1e-12
+    assert nops[0] == ntaxa - 2                                         # first call: everything
+    if ncat > 1:
+        assert (nops[1:] == ntaxa - 2).sum() >= 2                       # and again after every change of the model
+    moves = nops[nops < ntaxa - 2]
+    assert len(moves) > nsteps // 2
+    if ntaxa > 100:
+        assert np.median(moves) < (ntaxa - 2) / 10
+    assert len(set(np.round(full, 6))) > nsteps // 3                    # the walk really moves

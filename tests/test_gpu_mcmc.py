@@ -55,3 +55,16 @@ def test_parallel_chains_match_cpu_call_path_and_turn_order():
     assert np.array_equal(side, turn)
     rel = np.abs(side - cpu) / np.maximum(np.abs(cpu), 1e-300)
     assert rel.max() <= 1e-9
+
+
+@pytest.mark.parametrize("key,kw", [("rbcl10", dict(niter=300, burnin=200, nchains=2, samplefreq=10, seed=13579)),
+                                    ("rbcL", dict(niter=150, burnin=100, nchains=1, samplefreq=5, seed=7))])
+def test_incremental_trace_matches_cpu_call_path(key, kw):
+    """The whole MCMC with incremental likelihoods on the engine against the CPU call path that recomputes
+    everything: same trace to the north-star tolerance."""
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    gpu, _ = _run(host(), key, incremental=True, **kw)
+    cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), key, **kw)
+    rel = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-300)
+    assert gpu.shape == cpu.shape and rel.max() <= 1e-9

@@ -58,3 +58,13 @@ def test_parallel_chains_do_not_depend_on_thread_timing(hostlib):
     assert shared.shape == turn.shape and not np.array_equal(shared, turn)
     assert np.all(np.isfinite(side)) and side[-1, 1] > side[0, 1] + 20
     hostlib.data_free(h)
+
+
+def test_incremental_walk_driver_on_cpu_call_path(hostlib):
+    # on the CPU call path setIncremental has no effect: both evaluations list every node and agree exactly
+    from helpers import PAUP_ALPHA, PAUP_PI, PAUP_R
+    fx, h = _data(hostlib, "rbcl10")
+    inc, full, nops, _, _ = hostlib.incremental_walk(h, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, nsteps=40, seed=3)
+    assert len(inc) == 40 and np.array_equal(inc, full) and np.all(nops == 8)
+    assert len(set(np.round(full, 6))) > 12
+    hostlib.data_free(h)
