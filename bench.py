@@ -236,6 +236,33 @@ def rbcl738_block(E, device, steps=300, warmup=30):
     alg, sch = C.c_double(), C.c_double()
     E.sb200LastTraffic(L.inst, C.byref(alg), C.byref(sch))
     L.close()
+    # several independent evaluations at once on ONE GPU (each its own engine instance and stream), as the heated
+    # chains of an MC3 run are: one rbcl738 evaluation leaves most SMs idle, so they overlap
+    K = 4
+    Ls = [ShardedLikelihood(data, fx["counts"], 4, device=device) for _ in range(K)]
+    for Lk in Ls:
+        Lk.calc_log_likelihood(ea)
+    done = [torch.cuda.Event() for _ in range(K)]
+    def rounds(count):
+        for _ in range(count):
+            for Lk in Ls:
+                Lk.replay_async()
+    rounds(warmup)
+    torch.cuda.synchronize(device)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream(device)
+    c0.record(main)
+    for Lk in Ls:
+        Lk.stream.wait_event(c0)
+    rounds(steps)
+    for Lk, ev in zip(Ls, done):
+        ev.record(Lk.stream)
+        main.wait_event(ev)
+    c1.record(main)
+    torch.cuda.synchronize(device)
+    conc_ms = c0.elapsed_time(c1) / (steps * K)
+    for Lk in Ls:
+        Lk.close()
     # the C++ Likelihood facade (strom_b200/host/likelihood.hpp): what strom's Chain / Updaters call
     from strom_b200.host import host
     H = host()
@@ -257,6 +284,7 @@ def rbcl738_block(E, device, steps=300, warmup=30):
         "evals_per_sec_device": 1000.0 / dev_ms, "evals_per_sec_e2e_13call": 1000.0 / e2e_ms,
         "evals_per_sec_e2e_fused_call": 1000.0 / fused_ms,
         "evals_per_sec_e2e_cpp_facade": 1.0 / sec, "logL_cpp_facade": llf,
+        "evals_per_sec_device_4_concurrent_chains": 1000.0 / conc_ms,
         "partial_updates_per_sec_device": upd * 1000.0 / dev_ms,
         "cpu_evals_per_sec_1thread": one, "cpu_evals_per_sec_all_threads": allc, "cpu_threads": thr,
         "speedup_e2e_vs_cpu_1thread": (1.0 / sec) / one, "speedup_e2e_vs_cpu_all_threads": (1.0 / sec) / allc,
