@@ -102,6 +102,15 @@ STROM_API int sb200LastTraffic(int instance, double* algorithmicBytes, double* s
  * after enabling must list every node.  Lists must be forests (no buffer written twice or read before written). */
 STROM_API int sb200SetSubtreeScalers(int instance, int enable);
 
+/* Site-pattern compression on the device: what Data::compressPatterns does with a
+ * std::map over all site columns (reference src/data.hpp:102-161).  codes[taxon * nsites + site] are state codes
+ * < 32; on return patternsOut[taxon * (*patternCountOut) + pattern] holds the distinct site columns in
+ * lexicographic order (taxon 0 most significant, codes compared as integers) and countsOut[pattern] how many sites
+ * show each.  patternsOut needs room for ntaxa * nsites bytes, countsOut for nsites doubles.  Runs on CUDA device
+ * `device`; returns BEAGLE_ERROR_OUT_OF_RANGE (and writes nothing) if a code is >= 32. */
+STROM_API int sb200CompressPatterns(int device, int ntaxa, int nsites, const unsigned char* codes, unsigned char* patternsOut,
+                                    double* countsOut, int* patternCountOut);
+
 /* Host-only schedule inspection (no GPU needed): builds the chain/level schedule for an
  * operation list and reports, per operation, its level and chain id.  Returns the number of
  * levels (>= 0) or a negative error code.  chainOut/levelOut may be NULL. */

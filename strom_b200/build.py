@@ -37,7 +37,7 @@ def _stale(target: str, sources) -> bool:
 
 def engine_sources():
     inc = os.path.join(ROOT, "include")
-    return [os.path.join(CSRC, f) for f in ("engine.cu", "schedule.cpp", "kernels.cuh", "schedule.hpp")] + \
+    return [os.path.join(CSRC, f) for f in ("engine.cu", "patterns.cu", "schedule.cpp", "kernels.cuh", "schedule.hpp")] + \
            [os.path.join(inc, f) for f in ("strom_beagle.h", "strom_b200.h")]
 
 
@@ -45,7 +45,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     srcs = engine_sources()
     if force or _stale(ENGINE_LIB, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", ENGINE_LIB, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "schedule.cpp")]
+              ["-o", ENGINE_LIB, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "patterns.cu"), os.path.join(CSRC, "schedule.cpp")]
         env = dict(os.environ)
         env.pop("CC", None)
         env.pop("CXX", None)

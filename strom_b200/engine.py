@@ -43,6 +43,7 @@ class EngineAPI:
             "sb200Synchronize": (C.c_int, [C.c_int]),
             "sb200SetProfiling": (C.c_int, [C.c_int, C.c_int]),
             "sb200SetSubtreeScalers": (C.c_int, [C.c_int, C.c_int]),
+            "sb200CompressPatterns": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _DP, _IP]),
             "sb200PartialsTime": (C.c_int, [C.c_int, _DP, C.POINTER(C.c_long)]),
             "sb200LaunchCount": (C.c_long, [C.c_int]),
             "sb200LastTraffic": (C.c_int, [C.c_int, _DP, _DP]),
@@ -56,6 +57,18 @@ class EngineAPI:
     def check(self, code: int, what: str):
         if code != 0:
             raise beagle.BeagleError(what, code)
+
+    def compress_patterns(self, codes: np.ndarray, device: int = 0):
+        """Distinct site columns of codes[taxon][site] (uint8 < 32) in lexicographic order, and their counts -- on the GPU."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        ntaxa, nsites = codes.shape
+        out = np.empty(codes.size, dtype=np.uint8)
+        counts = np.empty(nsites, dtype=np.float64)
+        npat = C.c_int()
+        self.check(self.sb200CompressPatterns(device, ntaxa, nsites, codes.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                              counts.ctypes.data_as(_DP), C.byref(npat)), "compress patterns")
+        P = npat.value
+        return out[:ntaxa * P].reshape(ntaxa, P).copy(), counts[:P].copy()
 
     def schedule(self, ops: np.ndarray, ntaxa: int):
         """(levels, chains, level of each op, chain of each op) -- host-only, needs no GPU."""

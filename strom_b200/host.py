@@ -49,7 +49,9 @@ class HostAPI:
     def data_from_file(self, path: str) -> int:
         return self._check(self.lib.strom_data_from_file(path.encode(), self._err, 1024))
 
-    def data_from_codes(self, codes: np.ndarray, compress: bool = True) -> int:
+    def data_from_codes(self, codes: np.ndarray, compress=True) -> int:
+        """``compress``: False = every site its own pattern; True = Data::compressPatterns (on the GPU from 32768 sites
+        up in engine builds); 2 = always on the GPU; 3 = always on the host."""
         codes = np.ascontiguousarray(codes, dtype=np.int32)
         return self._check(self.lib.strom_data_from_codes(codes.shape[0], codes.shape[1], codes.ctypes.data_as(_IP), int(compress),
                                                           self._err, 1024))

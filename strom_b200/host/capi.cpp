@@ -82,6 +82,8 @@ HOST_API int strom_data_from_codes(int ntaxa, int nsites, const int* codes, int 
             m[t].assign(codes + static_cast<size_t>(t) * nsites, codes + static_cast<size_t>(t + 1) * nsites);
         }
         Data::SharedPtr d(new Data());
+        if (compress == 2) d->setDeviceCompression(0);        // always on the GPU (engine builds)
+        else if (compress == 3) d->setDeviceCompression(~0u);  // never
         d->setDataMatrix(names, m, compress != 0);
         return keep(d);
     } catch (const std::exception& e) { return fail(e, err, errlen); }

@@ -18,6 +18,9 @@
 #include <vector>
 
 #include "xstrom.hpp"
+#ifdef STROM_B200_ENGINE
+#include "../../include/strom_b200.h"
+#endif
 
 namespace strom {
 
@@ -62,8 +65,22 @@ class Data {
         return out;
     }
 
+    // ---- pattern compression on the GPU (engine builds) ------------------
+    // Alignments of at least `min_sites` sites are compressed by sb200CompressPatterns on CUDA device `device`
+    // (same patterns, same order, same counts); shorter ones, and any alignment with a state code >= 32, take
+    // the host path.  Default: 32768 sites, device 0.
+    void setDeviceCompression(unsigned min_sites, int device = 0) {
+        _device_min_sites = min_sites;
+        _device = device;
+    }
+    bool compressedOnDevice() const { return _compressed_on_device; }
+
   private:
     void compressPatterns();
+    bool compressPatternsOnDevice();
+    unsigned _device_min_sites = 32768;
+    int _device = 0;
+    bool _compressed_on_device = false;
     static std::string stripComments(const std::string& s);
     static std::string lower(std::string s) {
         for (char& c : s) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
@@ -92,6 +109,8 @@ inline void Data::compressPatterns() {
     const unsigned seqlen = static_cast<unsigned>(_data_matrix[0].size());
     for (const pattern_t& row : _data_matrix)
         if (row.size() != seqlen) throw XStrom("data matrix rows differ in length");
+    _compressed_on_device = compressPatternsOnDevice();
+    if (_compressed_on_device) return;
     // sort site indices by their column, lexicographically over taxa: the order std::map<pattern_t,...> yields
     std::vector<unsigned> order(seqlen);
     std::iota(order.begin(), order.end(), 0u);
@@ -119,6 +138,35 @@ inline void Data::compressPatterns() {
     if (total != seqlen)
         throw XStrom("Total number of sites before compaction (" + std::to_string(seqlen) + ") not equal to total number of sites after (" +
                      std::to_string(total) + ")");
+}
+
+// The engine's radix sort over site columns; false = not applicable here (host path takes over).
+inline bool Data::compressPatternsOnDevice() {
+#ifdef STROM_B200_ENGINE
+    const unsigned ntaxa = static_cast<unsigned>(_data_matrix.size());
+    const unsigned seqlen = static_cast<unsigned>(_data_matrix[0].size());
+    if (seqlen < _device_min_sites) return false;
+    std::vector<unsigned char> codes(static_cast<size_t>(ntaxa) * seqlen);
+    for (unsigned t = 0; t < ntaxa; ++t)
+        for (unsigned i = 0; i < seqlen; ++i) {
+            const int c = _data_matrix[t][i];
+            if (c < 0 || c >= 32) return false;
+            codes[static_cast<size_t>(t) * seqlen + i] = static_cast<unsigned char>(c);
+        }
+    std::vector<unsigned char> packed(codes.size());
+    pattern_counts_t counts(seqlen);
+    int npatterns = 0;
+    const int code = sb200CompressPatterns(_device, static_cast<int>(ntaxa), static_cast<int>(seqlen), codes.data(), packed.data(),
+                                           counts.data(), &npatterns);
+    if (code != 0) throw XStrom("pattern compression on the GPU failed (engine code " + std::to_string(code) + ")");
+    counts.resize(static_cast<size_t>(npatterns));
+    for (unsigned t = 0; t < ntaxa; ++t)
+        _data_matrix[t].assign(packed.begin() + static_cast<size_t>(t) * npatterns, packed.begin() + static_cast<size_t>(t + 1) * npatterns);
+    _pattern_counts.swap(counts);
+    return true;
+#else
+    return false;
+#endif
 }
 
 inline void Data::setDataMatrix(const taxon_names_t& names, const data_matrix_t& matrix, bool compress) {

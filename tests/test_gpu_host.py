@@ -83,3 +83,35 @@ def test_incremental_likelihood_follows_tree_moves(key, ncat, pinvar, nsteps):
     if ntaxa > 100:
         assert np.median(moves) < (ntaxa - 2) / 10
     assert len(set(np.round(full, 6))) > nsteps // 3                    # the walk really moves
+
+
+@pytest.mark.parametrize("ntaxa,nsites,alphabet,seed", [(5, 1, 4, 1), (3, 7, 2, 2), (12, 5000, 2, 3), (40, 70000, 5, 4),
+                                                        (738, 1314, 6, 5), (7, 300000, 3, 6), (2, 2049, 20, 7)])
+def test_device_pattern_compression_matches_host(ntaxa, nsites, alphabet, seed):
+    """sb200CompressPatterns against Data::compressPatterns (reference src/data.hpp:102-161): the same distinct site
+    columns, in the same (lexicographic) order, with the same counts -- engine ABI and C++ facade."""
+    from strom_b200.engine import api
+    from strom_b200.host import host
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, alphabet, size=(ntaxa, max(1, nsites // 3))).astype(np.uint8)
+    codes = base[:, rng.integers(0, base.shape[1], size=nsites)]          # plenty of repeated columns
+    H = host()
+    hh = H.data_from_codes(codes.astype(np.int32), compress=3)
+    want, wcounts, _ = H.data_arrays(hh)
+    H.data_free(hh)
+    got, counts = api().compress_patterns(codes)
+    assert got.shape == want.shape and np.array_equal(got, want) and np.array_equal(counts, wcounts)
+    assert counts.sum() == nsites
+    hd = H.data_from_codes(codes.astype(np.int32), compress=2)
+    m, w, ns = H.data_arrays(hd)
+    H.data_free(hd)
+    assert ns == nsites and np.array_equal(m, want) and np.array_equal(w, wcounts)
+
+
+def test_device_pattern_compression_rejects_wide_codes():
+    from strom_b200.beagle import BeagleError
+    from strom_b200.engine import api
+    codes = np.zeros((3, 10), dtype=np.uint8)
+    codes[1, 4] = 32
+    with pytest.raises(BeagleError):
+        api().compress_patterns(codes)
