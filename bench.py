@@ -161,7 +161,7 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (restated in oracle/; BeagleLib itself is not buildable
     here) on the host cores, bounded sample of the same workload."""
     if rank != 0:
-        return
+        return None
     threads = host_threads()
     from strom_b200 import synth
     tree = synth.RandomTree(args.taxa, seed=1, mean_edge=0.05)
@@ -182,7 +182,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": upd, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "evals_per_sec_on_sample": evals_s, "logL_sample": ll,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(args, sample=None):
@@ -406,10 +406,10 @@ def run_ours(args, rank, world, local_rank):
                                     "single_thread_value": (n - 2) * Ps * 4 * ev1}
             if not args.no_rbcl738:
                 line["rbcl738"] = rbcl738_block(E, local_rank)
-        print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def main():
@@ -430,10 +430,19 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         args.gpus = world
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    run_ours(args, rank, world, local_rank)
+    # stdout carries exactly ONE line (the JSON, from rank 0): anything a library prints meanwhile (NCCL's version
+    # banner, for one) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args, rank, world) if args.impl == "reference" else run_ours(args, rank, world, local_rank)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -208,6 +208,7 @@ struct Engine {
         CK(cudaMemsetAsync(dTicket, 0, sizeof(unsigned int), stream));
         CK(cudaMalloc(&dOut, sizeof(double)));
         CK(cudaMallocHost(&hOut, sizeof(double)));
+        if (const char* f = std::getenv("SB200_PDL")) usePdl = std::atoi(f) != 0;   // tuning aid: plain stream order
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -434,16 +435,34 @@ struct Engine {
         return BEAGLE_SUCCESS;
     }
 
+    // Launch on the engine's stream; `dependent`: the kernel follows another kernel of the same evaluation and may
+    // be scheduled while that one drains (programmatic dependent launch, see pdlWait in kernels.cuh).
+    bool usePdl = true;
+    template <typename... KArgs, typename... Args>
+    void launchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, bool dependent, Args&&... args) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (dependent && usePdl) ? 1 : 0;
+        CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    }
+
     template <typename real, int CC, int R>
     void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
         constexpr int perBlock = (kPruneThreads / CC) * R;
         dim3 grid(Ppad / perBlock, L.groupCount);
-        prune_chains_kernel<real, CC, R><<<grid, kPruneThreads, 0, stream>>>(a, L.groupStart, cumMode);
+        launchK(prune_chains_kernel<real, CC, R>, grid, dim3(kPruneThreads), true, a, L.groupStart, cumMode);
     }
     template <typename real, int CC>
     void launchLevelGeneric(const PruneArgs<real>& a, const Level& L, int cumMode) {
         dim3 grid(Ppad / 128, L.groupCount);
-        prune_chains_generic_kernel<real, CC><<<grid, 128, 0, stream>>>(a, L.groupStart, cumMode);
+        launchK(prune_chains_generic_kernel<real, CC>, grid, dim3(128), true, a, L.groupStart, cumMode);
     }
 
     template <typename real>
@@ -478,8 +497,8 @@ struct Engine {
         a.Ppad = Ppad;
         a.nTips = nTips;
         if (sched.tipTipCount > 0) {
-            tiptip_tables_kernel<real><<<sched.tipTipCount, 128, 0, stream>>>(dOps, dTTOps, static_cast<const real*>(dMats), C,
-                                                                              static_cast<real*>(dTT));
+            launchK(tiptip_tables_kernel<real>, dim3(sched.tipTipCount), dim3(128), true, static_cast<const DevOp*>(dOps),
+                    static_cast<const int*>(dTTOps), static_cast<const real*>(dMats), C, static_cast<real*>(dTT));
             CK(cudaGetLastError());
             ++launches;
         }
@@ -508,7 +527,8 @@ struct Engine {
             const int nr = static_cast<int>(sched.rootSlots.size());
             int mode = 0;
             if (scaleZeroPending[cumIdx]) { mode = 1; scaleZeroPending[cumIdx] = 0; }
-            fold_roots_kernel<<<(Ppad + 255) / 256, 256, 0, stream>>>(a.slotAcc, a.slotProd, dRootSlots, nr, cum, Ppad, mode);
+            launchK(fold_roots_kernel, dim3((Ppad + 255) / 256), dim3(256), true, static_cast<const double*>(a.slotAcc),
+                    static_cast<const double*>(a.slotProd), static_cast<const int*>(dRootSlots), nr, cum, Ppad, mode);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -568,14 +588,14 @@ struct Engine {
         a.child = child;
         a.matrix = matrix;
         switch (C) {
-            case 1: root_loglik_kernel<real, 1><<<rootBlocks, 256, 0, stream>>>(a); break;
-            case 2: root_loglik_kernel<real, 2><<<rootBlocks, 256, 0, stream>>>(a); break;
-            case 4: root_loglik_kernel<real, 4><<<rootBlocks, 256, 0, stream>>>(a); break;
-            case 8: root_loglik_kernel<real, 8><<<rootBlocks, 256, 0, stream>>>(a); break;
-            case 3: root_loglik_generic_kernel<real, 3><<<rootBlocks, 128, 0, stream>>>(a); break;
-            case 5: root_loglik_generic_kernel<real, 5><<<rootBlocks, 128, 0, stream>>>(a); break;
-            case 6: root_loglik_generic_kernel<real, 6><<<rootBlocks, 128, 0, stream>>>(a); break;
-            case 7: root_loglik_generic_kernel<real, 7><<<rootBlocks, 128, 0, stream>>>(a); break;
+            case 1: launchK(root_loglik_kernel<real, 1>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 2: launchK(root_loglik_kernel<real, 2>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 4: launchK(root_loglik_kernel<real, 4>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 8: launchK(root_loglik_kernel<real, 8>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 3: launchK(root_loglik_generic_kernel<real, 3>, dim3(rootBlocks), dim3(128), true, a); break;
+            case 5: launchK(root_loglik_generic_kernel<real, 5>, dim3(rootBlocks), dim3(128), true, a); break;
+            case 6: launchK(root_loglik_generic_kernel<real, 6>, dim3(rootBlocks), dim3(128), true, a); break;
+            case 7: launchK(root_loglik_generic_kernel<real, 7>, dim3(rootBlocks), dim3(128), true, a); break;
         }
         CK(cudaGetLastError());
         ++launches;

@@ -127,6 +127,12 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
 __device__ __forceinline__ void bulkPrefetchL2(const void* gmemSrc, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmemSrc), "r"(bytes) : "memory");
 }
+// Programmatic dependent launch: a kernel lets its successor in the stream start (blocks scheduled, prologue
+// running) as soon as all of its own blocks are under way; the successor must not touch anything an earlier
+// kernel of the evaluation produces before pdlWait(), which returns once the predecessor has completed and its
+// writes are visible.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(256)
 transition_matrices_kernel(const DevModel* __restrict__ model, const double* __restrict__ rates,
                            const int* __restrict__ matrixIndex, const double* __restrict__ edgeLength,
                            int count, int C, real* __restrict__ mats) {
+    pdlLaunchDependents();
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = flat & 15, uk = flat >> 4;
     if (uk >= count * C) return;
@@ -167,7 +174,9 @@ tiptip_tables_kernel(const DevOp* __restrict__ ops, const int* __restrict__ ttOp
                      real* __restrict__ tables) {
     __shared__ real tab[100 * kMaxCategories];
     __shared__ real mx[32];
-    const DevOp op = ops[ttOps[blockIdx.x]];
+    pdlLaunchDependents();
+    const DevOp op = ops[ttOps[blockIdx.x]];      // (plan data: uploaded by a copy, not produced by a kernel)
+    pdlWait();                                    // the matrices are
     const real* ma = mats + static_cast<size_t>(op.ma) * C * kMatStride;
     const real* mb = mats + static_cast<size_t>(op.mb) * C * kMatStride;
     const int n = 100 * C;
@@ -302,6 +311,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
 
     const int tid = threadIdx.x;
     const int k = tid % C, g = tid / C;
+    pdlLaunchDependents();
     const Group grp = A.groups[groupBase + blockIdx.y];
     const int nOps = grp.opEnd - grp.opStart;
     const int Ppad = A.Ppad;
@@ -605,6 +615,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             for (int w = tid; w < nc * kOpWords; w += kPruneThreads) sops[w] = gops[w];
         }
         __syncthreads();
+        if (chunk0 == 0) pdlWait();   // the plan is in shared memory; everything below reads what earlier kernels wrote
         int4 a0 = sops[0], a1 = sops[1];
         stage(0, a0, a1, (a1.w & OP_TIPTIP) ? sops[2].y : -1);
         if (a1.w & OP_CHAIN_START) startChain(a0, a1);       // (a later chunk may begin in mid-chain: A is carried)
@@ -636,7 +647,9 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int groupBase, const 
     constexpr int MSZ = kMatStride * C;
     __shared__ __align__(16) real sm[2 * MSZ];
     const int tid = threadIdx.x;
+    pdlLaunchDependents();
     const Group grp = A.groups[groupBase + blockIdx.y];
+    pdlWait();
     const int p = blockIdx.x * 128 + tid;                 // < Ppad
     const int Ppad = A.Ppad;
     const size_t bufStride = static_cast<size_t>(Ppad) * C * 4;
@@ -737,6 +750,8 @@ prune_chains_generic_kernel(const PruneArgs<real> A, const int groupBase, const 
 __global__ void fold_roots_kernel(const double* __restrict__ slotAcc, const double* __restrict__ slotProd,
                                   const int* __restrict__ rootSlots, int nRoots, double* __restrict__ cum, int Ppad,
                                   int cumMode) {
+    pdlLaunchDependents();
+    pdlWait();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= Ppad) return;
     double s = cumMode ? 0.0 : cum[p];
@@ -812,6 +827,8 @@ root_loglik_kernel(const RootArgs<real> A) {
     __shared__ double fw[C * 4];
     const int tid = threadIdx.x, k = tid % C, g = tid / C;
     const bool childTip = A.child < A.nTips;
+    pdlLaunchDependents();
+    pdlWait();
     loadRootTables<real, C, 256>(A, W, M, fw);
 
     const int p = blockIdx.x * G + g;                     // < Ppad
@@ -854,6 +871,8 @@ root_loglik_generic_kernel(const RootArgs<real> A) {
     __shared__ double fw[C * 4];
     const int tid = threadIdx.x;
     const bool childTip = A.child < A.nTips;
+    pdlLaunchDependents();
+    pdlWait();
     loadRootTables<real, C, 128>(A, W, M, fw);
     const int p = blockIdx.x * 128 + tid;                 // < Ppad
     const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
