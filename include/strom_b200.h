@@ -117,6 +117,15 @@ STROM_API int sb200CompressPatterns(int device, int ntaxa, int nsites, const uns
 STROM_API int sb200DebugSchedule(const BeagleOperation* operations, int operationCount, int tipCount,
                                  int partialsBufferCount, int* levelOut, int* chainOut, int* chainCountOut);
 
+/* Host-only inspection of the plan built for an operation list (with or without the permanent subtree scalers
+ * of sb200SetSubtreeScalers): per planned operation o, in launch and group order, planOut[8o..8o+7] = {destination
+ * buffer, operand A buffer or -1 (carried in registers), operand B buffer, scaler slot read with A or -1, scaler
+ * slot read with B or -1, scaler slot written or -1, flag bits (1 rescale, 2 chain start, 4 chain end, 8 adds to the
+ * cumulative buffer, 16 tip x tip, 32 A is a tip, 64 B is a tip, 128 stores its subtree scaler and carries on),
+ * launch index}.  Returns the number of planned operations (>= 0) or a negative error code. */
+STROM_API int sb200DebugPlan(const BeagleOperation* operations, int operationCount, int tipCount, int partialsBufferCount,
+                             int keepSubtreeScalers, int* planOut);
+
 #ifdef __cplusplus
 }
 #endif

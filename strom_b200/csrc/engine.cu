@@ -1112,3 +1112,27 @@ extern "C" int sb200DebugSchedule(const BeagleOperation* operations, int operati
         return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
     }
 }
+
+// Host-only inspection of a plan (see include/strom_b200.h).
+extern "C" int sb200DebugPlan(const BeagleOperation* operations, int operationCount, int tipCount, int partialsBufferCount,
+                              int keepSubtreeScalers, int* planOut) {
+    try {
+        Schedule s;
+        int rc = buildSchedule(operations, operationCount, tipCount, partialsBufferCount, 1 << 30, 1 << 30, true, 4, s,
+                               keepSubtreeScalers != 0);
+        if (rc) return rc;
+        if (planOut) {
+            for (size_t l = 0; l < s.levels.size(); ++l)
+                for (int g = s.levels[l].groupStart; g < s.levels[l].groupStart + s.levels[l].groupCount; ++g)
+                    for (int o = s.groups[g].opStart; o < s.groups[g].opEnd; ++o) {
+                        const DevOp& d = s.ops[o];
+                        int* r = planOut + 8 * static_cast<size_t>(o);
+                        r[0] = d.dest + tipCount; r[1] = d.a; r[2] = d.b; r[3] = d.sa; r[4] = d.sb; r[5] = d.sOut; r[6] = d.flags;
+                        r[7] = static_cast<int>(l);
+                    }
+        }
+        return static_cast<int>(s.ops.size());
+    } catch (...) {
+        return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
+    }
+}

@@ -48,6 +48,7 @@ class EngineAPI:
             "sb200LaunchCount": (C.c_long, [C.c_int]),
             "sb200LastTraffic": (C.c_int, [C.c_int, _DP, _DP]),
             "sb200DebugSchedule": (C.c_int, [_IP, C.c_int, C.c_int, C.c_int, _IP, _IP, _IP]),
+            "sb200DebugPlan": (C.c_int, [_IP, C.c_int, C.c_int, C.c_int, C.c_int, _IP]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -69,6 +70,16 @@ class EngineAPI:
                                               counts.ctypes.data_as(_DP), C.byref(npat)), "compress patterns")
         P = npat.value
         return out[:ntaxa * P].reshape(ntaxa, P).copy(), counts[:P].copy()
+
+    def plan(self, ops: np.ndarray, ntaxa: int, keep_subtree_scalers: bool = False) -> np.ndarray:
+        """Planned operations [n][8] = dest, a, b, sa, sb, sOut, flags, launch -- host-only, needs no GPU."""
+        ops = np.ascontiguousarray(ops, dtype=np.int32)
+        n = ops.size // 7
+        out = np.zeros((max(n, 1), 8), dtype=np.int32)
+        r = self.sb200DebugPlan(ops.ctypes.data_as(_IP), n, ntaxa, ntaxa - 2, int(keep_subtree_scalers), out.ctypes.data_as(_IP))
+        if r < 0:
+            raise beagle.BeagleError("plan", r)
+        return out[:r]
 
     def schedule(self, ops: np.ndarray, ntaxa: int):
         """(levels, chains, level of each op, chain of each op) -- host-only, needs no GPU."""

@@ -93,3 +93,71 @@ def test_out_of_range_indices_are_rejected(E):
     bad[0, 2] = 1                                                      # scale-read is not supported
     with pytest.raises(BeagleError):
         E.schedule(bad, 8)
+
+
+def _walk_plan(plan, ntaxa, in_list):
+    """Replays a plan symbolically: every operand read from memory must be there (a tip, a buffer of an earlier
+    launch, or -- incremental plans -- a buffer no operation of the list produces), chains must be contiguous."""
+    done_before_launch = {}
+    carried = None
+    written = set()
+    for dest, a, b, sa, sb, s_out, flags, launch in plan.tolist():
+        start, end = bool(flags & 2), bool(flags & 4)
+        assert (a >= 0) == start                                       # only a chain start reads operand A from memory
+        if not start:
+            assert carried is not None                                 # ... otherwise A is what the previous step produced
+        for operand in ([a] if start else []) + [b]:
+            if operand >= ntaxa and operand in in_list:
+                assert operand in written and done_before_launch[operand] < launch
+        written.add(dest)
+        done_before_launch[dest] = launch
+        carried = None if end else dest
+    return written
+
+
+@pytest.mark.parametrize("key", ["rbcl10", "rbcL", "rbcl738"])
+def test_incremental_plans_keep_every_subtree_scaler(E, key):
+    """Planner side of sb200SetSubtreeScalers: slot = buffer for every operation, chain-internal operations store and
+    carry on (flag 128), and an internal operand the list does not produce brings its own slot."""
+    fx = load_golden(key)
+    ops = np.asarray(fx["ops"], dtype=np.int32).reshape(-1, 7)
+    ntaxa = fx["data"].shape[0]
+    parent_of = {}
+    for o in ops:
+        parent_of[int(o[3])] = int(o[0])
+        parent_of[int(o[5])] = int(o[0])
+    # full list
+    plan = E.plan(ops, ntaxa, keep_subtree_scalers=True)
+    assert len(plan) == len(ops) and _walk_plan(plan, ntaxa, set(ops[:, 0].tolist())) == set(ops[:, 0].tolist())
+    for dest, a, b, sa, sb, s_out, flags, launch in plan.tolist():
+        assert s_out == dest - ntaxa
+        assert bool(flags & 128) != bool(flags & 4)                    # stores-and-continues XOR ends its chain
+        if flags & 2 and a >= ntaxa:
+            assert sa == a - ntaxa
+        if b >= ntaxa:
+            assert sb == b - ntaxa
+        if b < ntaxa:
+            assert sb == -1
+    assert sum(1 for r in plan.tolist() if r[6] & 8) == 1              # exactly one chain feeds the cumulative buffer
+    # the same list without the switch: only chain ends that are re-read own a slot
+    plain = E.plan(ops, ntaxa)
+    assert not any(r[6] & 128 for r in plain.tolist())
+    assert sum(1 for r in plain.tolist() if r[5] >= 0) < len(ops)
+    # a path list: the operations above one tip
+    tip = 1 if ntaxa > 3 else 0
+    dirty, v = set(), parent_of.get(tip)
+    while v is not None:
+        dirty.add(v)
+        v = parent_of.get(v)
+    sub = np.array([o for o in ops if int(o[0]) in dirty], dtype=np.int32)
+    path = E.plan(sub, ntaxa, keep_subtree_scalers=True)
+    assert len(path) == len(sub) and _walk_plan(path, ntaxa, dirty) == dirty
+    outside = 0
+    for dest, a, b, sa, sb, s_out, flags, launch in path.tolist():
+        assert s_out == dest - ntaxa
+        for operand, slot in ((a, sa), (b, sb)):
+            if operand >= ntaxa:
+                assert slot == operand - ntaxa
+                outside += operand not in dirty
+    assert outside >= 1 or len(sub) == 1                               # siblings along the path come with their old scalers
+    assert len({r[7] for r in path.tolist()}) == 1                     # one path = one chain = one launch
