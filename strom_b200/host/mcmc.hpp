@@ -17,6 +17,8 @@
 //     m = exp(lambda (u - 0.5)), and with probability 1/2 an NNI swap across that edge -- it exercises
 //     topology + edge-length changes through the engine but is not the reference's 8-case proposal.
 #pragma once
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <exception>
@@ -404,69 +406,23 @@ struct McmcOptions {
     bool perChainStreams = false;            // chain c draws from its own stream, seeded from (seed, c); the swap
                                              // proposals keep the master stream.  Changes the trace (documented deviation).
     bool incremental = false;                // Likelihood::setIncremental: tree moves re-evaluate only the changed path (engine builds)
-    bool parallelChains = false;             // step all chains at once, one host thread per chain (implies perChainStreams);
-                                             // the result does not depend on thread timing
+    bool parallelChains = false;             // every chain runs on its own host thread (implies perChainStreams); only the two
+                                             // chains of a swap proposal wait for each other.  Same trace as perChainStreams
+                                             // alone, whatever the thread timing
 };
 
-// Runs body(c) for c = 0..n-1 on n persistent host threads, once per call of run(); rethrows the first failure.
-class ChainThreads {
-  public:
-    ChainThreads(unsigned n, std::function<void(unsigned)> body) : _n(n), _body(std::move(body)), _errors(n) {
-        for (unsigned c = 0; c < n; ++c) _threads.emplace_back([this, c] { loop(c); });
-    }
-    ~ChainThreads() {
-        {
-            std::lock_guard<std::mutex> lk(_mu);
-            _stop = true;
-        }
-        _go.notify_all();
-        for (std::thread& t : _threads) t.join();
-    }
-    void run() {
-        {
-            std::lock_guard<std::mutex> lk(_mu);
-            _pending = _n;
-            ++_generation;
-        }
-        _go.notify_all();
-        std::unique_lock<std::mutex> lk(_mu);
-        _finished.wait(lk, [this] { return _pending == 0; });
-        for (std::exception_ptr& e : _errors)
-            if (e) {
-                std::exception_ptr first = e;
-                for (std::exception_ptr& x : _errors) x = nullptr;
-                std::rethrow_exception(first);
-            }
-    }
-
-  private:
-    void loop(unsigned c) {
-        unsigned long seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(_mu);
-                _go.wait(lk, [&] { return _stop || _generation != seen; });
-                if (_stop) return;
-                seen = _generation;
-            }
-            try {
-                _body(c);
-            } catch (...) {
-                _errors[c] = std::current_exception();
-            }
-            std::lock_guard<std::mutex> lk(_mu);
-            if (--_pending == 0) _finished.notify_one();
-        }
-    }
-    unsigned _n;
-    std::function<void(unsigned)> _body;
-    std::vector<std::exception_ptr> _errors;
-    std::vector<std::thread> _threads;
-    std::mutex _mu;
-    std::condition_variable _go, _finished;
-    unsigned long _generation = 0;
-    unsigned _pending = 0;
-    bool _stop = false;
+// A swap proposal between two chains that run on their own host threads: both post what the other needs and
+// wait for each other; nobody else waits.
+struct SwapMeeting {
+    struct Offer {
+        double k = 0.0, heat = 1.0;       // log kernel (lnL + lnPrior) and heating power of the chain
+        unsigned index = 0;
+        std::vector<double> lambdas;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    int posted = 0, left = 0;
+    Offer offer[2];                        // [0] = chain i of the pair, [1] = chain j
 };
 
 // Strom::run's MCMC branch (src/strom.hpp:486-523): initChains, burn-in with tuning, sampling with swaps.
@@ -495,20 +451,21 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         ch.start();
     }
     std::vector<TraceRow> trace;
+    auto rowOf = [](Chain& ch, unsigned iteration) {
+        TraceRow r;
+        r.iteration = iteration;
+        r.lnL = ch.calcLogLikelihood();                 // one more full evaluation per sample, as in Strom::sample (:455)
+        r.lnPrior = ch.calcLogJointPrior();
+        r.TL = ch.getTreeManip()->calcTreeLength();
+        const std::vector<double> x = ch.getModel()->getExchangeabilities(), f = ch.getModel()->getStateFreqs();
+        for (int i = 0; i < 6; ++i) r.params[i] = x[i];
+        for (int i = 0; i < 4; ++i) r.params[6 + i] = f[i];
+        r.params[10] = ch.getModel()->getGammaShape();
+        return r;
+    };
     auto sample = [&](unsigned iteration) {
-        for (Chain& ch : chains) {
-            if (ch.getHeatingPower() != 1.0) continue;
-            TraceRow r;
-            r.iteration = iteration;
-            r.lnL = ch.calcLogLikelihood();             // one more full evaluation per sample, as in Strom::sample (:455)
-            r.lnPrior = ch.calcLogJointPrior();
-            r.TL = ch.getTreeManip()->calcTreeLength();
-            const std::vector<double> x = ch.getModel()->getExchangeabilities(), f = ch.getModel()->getStateFreqs();
-            for (int i = 0; i < 6; ++i) r.params[i] = x[i];
-            for (int i = 0; i < 4; ++i) r.params[6 + i] = f[i];
-            r.params[10] = ch.getModel()->getGammaShape();
-            trace.push_back(r);
-        }
+        for (Chain& ch : chains)
+            if (ch.getHeatingPower() == 1.0) trace.push_back(rowOf(ch, iteration));
     };
     auto swapChains = [&]() {
         if (opt.nchains == 1) return;
@@ -529,24 +486,101 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
             chains[j].setLambdas(li);
         }
     };
-    // one iteration of every chain: in turn (reference), or side by side -- one chain per GPU keeps all GPUs busy
-    int iteration = 0;
-    std::unique_ptr<ChainThreads> pool;
-    if (opt.parallelChains && opt.nchains > 1)
-        pool.reset(new ChainThreads(opt.nchains, [&](unsigned c) { chains[c].nextStep(iteration); }));
-    auto stepAll = [&](unsigned it) {
-        iteration = static_cast<int>(it);
-        if (pool) pool->run();
-        else for (Chain& ch : chains) ch.nextStep(iteration);
-    };
     sample(0);
+    if (opt.parallelChains && opt.nchains > 1) {
+        // Side by side.  The swap schedule (which two chains, and the uniform deviate of the acceptance test) only
+        // consumes the master stream, never a chain's state, so it is drawn up front in the order the in-turn loop
+        // would draw it; a chain then only ever waits for the partner of its own swap proposals.
+        struct Proposal {
+            unsigned i, j;
+            double logu;
+        };
+        const unsigned total = opt.burnin + opt.niter;
+        std::vector<Proposal> proposals(total);
+        for (Proposal& p : proposals) {
+            p.i = static_cast<unsigned>(lot->randint(0, static_cast<int>(opt.nchains) - 1));
+            p.j = (p.i + 1 + static_cast<unsigned>(lot->randint(0, static_cast<int>(opt.nchains) - 2))) % opt.nchains;
+            p.logu = lot->logUniform();
+        }
+        std::mutex tableMutex;                                    // meetings exist from the first arrival to the second departure
+        std::map<unsigned, std::shared_ptr<SwapMeeting>> meetings;
+        std::atomic<bool> failed(false);
+        std::vector<std::exception_ptr> errors(opt.nchains);
+        std::vector<std::vector<TraceRow>> rows(opt.nchains);
+        auto propose = [&](unsigned c, unsigned t) {
+            const Proposal& p = proposals[t];
+            if (c != p.i && c != p.j) return;
+            Chain& ch = chains[c];
+            const int me = c == p.i ? 0 : 1;
+            std::shared_ptr<SwapMeeting> meeting;
+            {
+                std::lock_guard<std::mutex> lk(tableMutex);
+                std::shared_ptr<SwapMeeting>& slot = meetings[t];
+                if (!slot) slot.reset(new SwapMeeting());
+                meeting = slot;
+            }
+            SwapMeeting& m = *meeting;
+            SwapMeeting::Offer mine;
+            mine.k = ch.calcLogLikelihood() + ch.calcLogJointPrior();
+            mine.heat = ch.getHeatingPower();
+            mine.index = ch.getChainIndex();
+            mine.lambdas = ch.getLambdas();
+            std::unique_lock<std::mutex> lk(m.mu);
+            m.offer[me] = mine;
+            ++m.posted;
+            m.cv.notify_all();
+            while (m.posted < 2 && !failed.load()) m.cv.wait_for(lk, std::chrono::milliseconds(50));
+            if (m.posted < 2) throw XStrom("a chain failed while its swap partner was waiting");
+            const SwapMeeting::Offer& i = m.offer[0];
+            const SwapMeeting::Offer& j = m.offer[1];
+            const double logR = (i.heat - j.heat) * (j.k - i.k);
+            if (p.logu < logR) {
+                const SwapMeeting::Offer& other = m.offer[1 - me];
+                ch.setHeatingPower(other.heat);
+                ch.setChainIndex(other.index);
+                ch.setLambdas(other.lambdas);
+            }
+            const bool last = ++m.left == 2;
+            lk.unlock();
+            if (last) {
+                std::lock_guard<std::mutex> tl(tableMutex);
+                meetings.erase(t);
+            }
+        };
+        auto life = [&](unsigned c) {
+            try {
+                Chain& ch = chains[c];
+                for (unsigned it = 1; it <= opt.burnin; ++it) {
+                    ch.nextStep(static_cast<int>(it));
+                    propose(c, it - 1);
+                }
+                ch.stopTuning();
+                for (unsigned it = 1; it <= opt.niter; ++it) {
+                    ch.nextStep(static_cast<int>(it));
+                    if (it % opt.samplefreq == 0 && ch.getHeatingPower() == 1.0) rows[c].push_back(rowOf(ch, it));
+                    propose(c, opt.burnin + it - 1);
+                }
+            } catch (...) {
+                errors[c] = std::current_exception();
+                failed.store(true);                              // (waiting partners poll this flag)
+            }
+        };
+        std::vector<std::thread> threads;
+        for (unsigned c = 0; c < opt.nchains; ++c) threads.emplace_back(life, c);
+        for (std::thread& t : threads) t.join();
+        for (std::exception_ptr& e : errors)
+            if (e) std::rethrow_exception(e);
+        for (const std::vector<TraceRow>& r : rows) trace.insert(trace.end(), r.begin(), r.end());
+        std::stable_sort(trace.begin() + 1, trace.end(), [](const TraceRow& x, const TraceRow& y) { return x.iteration < y.iteration; });
+        return trace;
+    }
     for (unsigned it = 1; it <= opt.burnin; ++it) {
-        stepAll(it);
+        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
         swapChains();
     }
     for (Chain& ch : chains) ch.stopTuning();
     for (unsigned it = 1; it <= opt.niter; ++it) {
-        stepAll(it);
+        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
         if (it % opt.samplefreq == 0) sample(it);
         swapChains();
     }

@@ -56,6 +56,12 @@ def test_parallel_chains_do_not_depend_on_thread_timing(hostlib):
         assert np.array_equal(turn, side)
     shared, _ = hostlib.mcmc(h, str(fx["newick"]), **kw)
     assert shared.shape == turn.shape and not np.array_equal(shared, turn)
+    # many chains, a sample (and a swap proposal) every iteration: the cold chain moves between threads
+    kw8 = dict(seed=31, niter=80, burnin=40, nchains=8, samplefreq=1, heatfactor=0.1)
+    turn8, _ = hostlib.mcmc(h, str(fx["newick"]), per_chain_streams=True, **kw8)
+    side8, _ = hostlib.mcmc(h, str(fx["newick"]), parallel_chains=True, **kw8)
+    assert turn8.shape == (81, 15) and np.array_equal(turn8, side8)
+    assert np.array_equal(side8[:, 0], np.arange(81))
     assert np.all(np.isfinite(side)) and side[-1, 1] > side[0, 1] + 20
     hostlib.data_free(h)
 
