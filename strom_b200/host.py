@@ -36,8 +36,8 @@ class HostAPI:
                                  _DP, _DP, C.c_int, _IP, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         L.strom_mcmc_ex.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint,
                                     C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
-        L.strom_incremental_walk.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, C.c_uint, C.c_int,
-                                             _DP, _DP, _IP, _DP, _DP, C.c_char_p, C.c_int]
+        L.strom_incremental_walk.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, _IP, C.c_uint,
+                                             C.c_int, _DP, _DP, _IP, _DP, _DP, C.c_char_p, C.c_int]
         self._err = C.create_string_buffer(1024)
 
     def _check(self, rc):
@@ -130,7 +130,7 @@ class HostAPI:
 
 
     def incremental_walk(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0,
-                         device: int = 0, seed: int = 1, nsteps: int = 100):
+                         devices=(0,), seed: int = 1, nsteps: int = 100):
         """Random tree moves evaluated incrementally and in full: (incremental logL[], full logL[], ops listed[],
         seconds per incremental evaluation, seconds per full evaluation)."""
         f = np.ascontiguousarray(freqs, dtype=np.float64)
@@ -138,8 +138,10 @@ class HostAPI:
         a, b = np.zeros(nsteps), np.zeros(nsteps)
         k = np.zeros(nsteps, dtype=np.int32)
         si, sf = C.c_double(), C.c_double()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
         n = self._check(self.lib.strom_incremental_walk(data_handle, newick.encode(), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
-                                                        shape, ncat, pinvar, device, seed, nsteps, a.ctypes.data_as(_DP),
+                                                        shape, ncat, pinvar, int(dev.size), dev.ctypes.data_as(_IP), seed, nsteps,
+                                                        a.ctypes.data_as(_DP),
                                                         b.ctypes.data_as(_DP), k.ctypes.data_as(_IP), C.byref(si), C.byref(sf),
                                                         self._err, 1024))
         return a[:n], b[:n], k[:n], si.value, sf.value

@@ -192,7 +192,8 @@ HOST_API int strom_loglik(int data_handle, const char* newick, const double* fre
 // step: by a Likelihood with incremental evaluation and by one that recomputes everything.  Fills, per step, both
 // log-likelihoods and the number of operations the incremental one listed; returns the number of steps.
 HOST_API int strom_incremental_walk(int data_handle, const char* newick, const double* freqs, const double* rmat, double shape, int ncat,
-                                    double pinvar, int device, unsigned seed, int nsteps, double* incremental_logl, double* full_logl,
+                                    double pinvar, int ndevices, const int* devices, unsigned seed, int nsteps, double* incremental_logl,
+                                    double* full_logl,
                                     int* incremental_ops, double* seconds_incremental, double* seconds_full, char* err, int errlen) {
     try {
         Data::SharedPtr d = dataOf(data_handle);
@@ -202,7 +203,7 @@ HOST_API int strom_incremental_walk(int data_handle, const char* newick, const d
         Model::SharedPtr model = makeModel(freqs, rmat, shape, ncat, pinvar);
         for (Likelihood::SharedPtr L : {inc, full}) {
             L->setQuiet(true);
-            L->setDevices(std::vector<int>(1, device));
+            if (ndevices > 0) L->setDevices(std::vector<int>(devices, devices + ndevices));   // pattern shards
             L->setData(d);
             L->setModel(model);
         }

@@ -85,6 +85,24 @@ def test_incremental_likelihood_follows_tree_moves(key, ncat, pinvar, nsteps):
     assert len(set(np.round(full, 6))) > nsteps // 3                    # the walk really moves
 
 
+def test_incremental_likelihood_on_pattern_shards():
+    """The same walk with the patterns sharded over three engine instances (over the visible GPUs, round robin)."""
+    import torch
+    from helpers import PAUP_ALPHA, PAUP_PI, PAUP_R
+    from strom_b200.host import host
+    api = host()
+    fx = load_golden("rbcl738")
+    cols = np.repeat(np.arange(fx["data"].shape[1]), fx["counts"].astype(int))
+    h = api.data_from_codes(fx["data"].astype(np.int32)[:, cols], compress=True)
+    ng = torch.cuda.device_count()
+    inc, full, nops, _, _ = api.incremental_walk(h, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, 0.0, nsteps=60, seed=5,
+                                                 devices=tuple(i % ng for i in range(3)))
+    one, _, _, _, _ = api.incremental_walk(h, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, 0.0, nsteps=60, seed=5)
+    api.data_free(h)
+    assert np.max(np.abs(inc - full) / np.abs(full)) < 1e-12 and np.max(np.abs(inc - one) / np.abs(one)) < 1e-12
+    assert np.median(nops[nops < 736]) < 60
+
+
 @pytest.mark.parametrize("ntaxa,nsites,alphabet,seed", [(5, 1, 4, 1), (3, 7, 2, 2), (12, 5000, 2, 3), (40, 70000, 5, 4),
                                                         (738, 1314, 6, 5), (7, 300000, 3, 6), (2, 2049, 20, 7)])
 def test_device_pattern_compression_matches_host(ntaxa, nsites, alphabet, seed):
