@@ -177,7 +177,8 @@ struct Engine {
         // pattern axis padded to a whole number of thread-block tiles of every kernel that walks it
         // (pruning tile = patternsPerBlock(); generic / root kernels use 128- or 256/C-pattern tiles)
         {
-            const int unit = std::max(patternsPerBlock(), 128);
+            const int rootTile = (C <= 2 || C == 4 || C == 8) ? 256 / C : 128;
+            const int unit = std::max(std::max(patternsPerBlock(), 128), rootTile);     // (all powers of two)
             Ppad = ((P + unit - 1) / unit) * unit;
         }
         tipStride = Ppad;
@@ -295,17 +296,18 @@ struct Engine {
         return big;
     }
     int patternsPerBlock() const {
-        if (C == 1 || C == 2 || C == 4 || C == 8) return (kPruneThreads / C) * (bigTiles() ? kBigR : 1);
+        if (C == 1 || C == 2 || C == 4 || C == 8) return bigTiles() ? (pruneThreads(kBigR) / C) * kBigR : pruneThreads(1) / C;
         return 128;
     }
     // How many groups a launch's chains are dealt into.  Every block pays a fixed set-up (operation words,
     // first images and operands: two dependent trips to L2/HBM), so as few groups as possible -- but:
-    //   * few pattern tiles (latency-bound sizes such as rbcl738, 20 tiles): exactly ONE wave of resident
-    //     blocks (148 SMs x 3 CTAs), each streaming through many operations;
+    //   * few pattern tiles (latency-bound sizes such as rbcl738, 40 tiles of 32 patterns): TWO waves of resident
+    //     blocks (148 SMs x 6 blocks of 128 threads), measured best between 1 and 4 waves: more groups shorten
+    //     the longest sequential run of a launch, fewer groups amortise the set-up;
     //   * many tiles (streaming sizes): enough blocks for >= 8 waves, so the last partial wave costs little.
     int groupsPerLevel() const {
         const int tiles = Ppad / patternsPerBlock();
-        int slots = 148 * 3;
+        int slots = bigTiles() ? 148 * pruneBlocksPerSm(kBigR) : 148 * pruneBlocksPerSm(1) * 2;
         if (const char* f = std::getenv("SB200_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
         if (tiles * 2 <= slots) return std::max(1, slots / tiles);
         return std::max(1, (8 * slots + tiles - 1) / tiles);
@@ -455,9 +457,9 @@ struct Engine {
 
     template <typename real, int CC, int R>
     void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        constexpr int perBlock = (kPruneThreads / CC) * R;
+        constexpr int perBlock = (pruneThreads(R) / CC) * R;
         dim3 grid(Ppad / perBlock, L.groupCount);
-        launchK(prune_chains_kernel<real, CC, R>, grid, dim3(kPruneThreads), true, a, L.groupStart, cumMode);
+        launchK(prune_chains_kernel<real, CC, R>, grid, dim3(pruneThreads(R)), true, a, L.groupStart, cumMode);
     }
     template <typename real, int CC>
     void launchLevelGeneric(const PruneArgs<real>& a, const Level& L, int cumMode) {

@@ -32,7 +32,12 @@ constexpr int kMatStride = 36;      // reals per (matrix, category)
 // tip x tip table of one operation: 25 (stateA, stateB) combinations x C categories x 4 states of
 // rescaled partials, followed by the 25 rescaling maxima (padded to 32)
 __host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
-constexpr int kPruneThreads = 256;
+// Threads per block of the (pattern, category) pruning kernel.  Streaming sizes (R = 2 patterns per thread): 256
+// threads, 3 blocks per SM.  Small pattern counts (R = 1): 128 threads, 6 blocks per SM -- a step is bound by the
+// latency of one warp's instruction stream and by the block barrier, so smaller blocks and twice as many groups
+// per launch shorten the sequential part (rbcl738: 108.6 -> 100.9 us per evaluation).
+__host__ __device__ constexpr int pruneThreads(int R) { return R == 1 ? 128 : 256; }
+__host__ __device__ constexpr int pruneBlocksPerSm(int R) { return R == 1 ? 6 : 3; }
 
 // Per-eigen-index model block, resident in HBM and refreshed once per evaluation.
 struct DevModel {
@@ -286,16 +291,10 @@ constexpr int kOpChunk = 256;                  // operations of a group held in 
 constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // steps between an operand tile's L2 prefetch and its register load
 constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 
-#ifndef SB200_MINBLK_R1
-#define SB200_MINBLK_R1 3
-#endif
-#ifndef SB200_MINBLK_R2
-#define SB200_MINBLK_R2 3
-#endif
-
 template <typename real, int C, int R>
-__global__ void __launch_bounds__(kPruneThreads, R == 1 ? SB200_MINBLK_R1 : SB200_MINBLK_R2)
+__global__ void __launch_bounds__(pruneThreads(R), pruneBlocksPerSm(R))
 prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
+    constexpr int kPruneThreads = pruneThreads(R);
     constexpr int G = kPruneThreads / C;                 // patterns per pass
     constexpr int MSZ = kMatStride * C;                  // reals per operand image
     constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
