@@ -195,16 +195,22 @@ def workload_config(args, sample=None):
     return cfg
 
 
-def rbcl738_block(E, device, steps=300, warmup=30):
-    """The real-data, latency-bound case of the north star: rbcl738 (738 taxa, 1235 patterns, GTR+G4).
-    Reads the committed fixture (derived from the reference's rbcl738.nex / rbcl738nj.tre)."""
+def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
+    """The real-data, latency-bound case of the north star: rbcl738 (738 taxa, 1235 patterns), GTR+G4 with the
+    reference's paup.nex parameters (golden-checked) or, with pinvar > 0, GTR+I+G4 (BASELINE.json configs[2]: the
+    invariable-sites class is a fifth category of rate 0).  Reads the committed fixture (derived from the
+    reference's rbcl738.nex / rbcl738nj.tre)."""
     import torch
+    from strom_b200 import hostmodel
     from strom_b200.engine import EvalArgs, ShardedLikelihood
     fx = np.load(os.path.join(ROOT, "tests", "golden", "rbcl738.npz"))
     model = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA, 4)
+    if pinvar > 0.0:
+        model["rates"], model["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA, 4, pinvar)
+    NC = len(model["rates"])
     data = np.minimum(fx["data"], 4).astype(np.uint8)
     n, P = data.shape
-    L = ShardedLikelihood(data, fx["counts"], 4, device=device)
+    L = ShardedLikelihood(data, fx["counts"], NC, device=device)
     ea = EvalArgs(model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
     ll = L.calc_log_likelihood(ea)
     for _ in range(warmup):
@@ -239,7 +245,7 @@ def rbcl738_block(E, device, steps=300, warmup=30):
     # several independent evaluations at once on ONE GPU (each its own engine instance and stream), as the heated
     # chains of an MC3 run are: one rbcl738 evaluation leaves most SMs idle, so they overlap
     K = 4
-    Ls = [ShardedLikelihood(data, fx["counts"], 4, device=device) for _ in range(K)]
+    Ls = [ShardedLikelihood(data, fx["counts"], NC, device=device) for _ in range(K)]
     for Lk in Ls:
         Lk.calc_log_likelihood(ea)
     done = [torch.cuda.Event() for _ in range(K)]
@@ -268,7 +274,7 @@ def rbcl738_block(E, device, steps=300, warmup=30):
     H = host()
     cols = np.repeat(np.arange(P), fx["counts"].astype(int))
     hd = H.data_from_codes(data.astype(np.int32)[:, cols], compress=True)
-    llf, sec = H.loglik(hd, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, repeats=steps + 1)
+    llf, sec = H.loglik(hd, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
     H.data_free(hd)
     # CPU oracle on the same problem
     tips = data
@@ -277,10 +283,12 @@ def rbcl738_block(E, device, steps=300, warmup=30):
     thr = host_threads()
     allc, _, _ = time_oracle(tips, fx["counts"], model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]),
                              thr, 200, 5, budget_s=8.0)
-    upd = (n - 2) * P * 4
+    upd = (n - 2) * P * NC
     return {
-        "workload": "rbcl738: 738 taxa, 1235 patterns, GTR+G4, rbcl738nj.tre (fixture tests/golden/rbcl738.npz)",
-        "logL": ll, "logL_13call": ll2, "logL_fused": ll3, "logL_cpu": llc, "golden": -144730.8,
+        "workload": "rbcl738: 738 taxa, 1235 patterns, %s, rbcl738nj.tre (fixture tests/golden/rbcl738.npz)" %
+                    ("GTR+I+G4 (pinvar %.2f, %d categories)" % (pinvar, NC) if pinvar > 0 else "GTR+G4"),
+        "categories": NC,
+        "logL": ll, "logL_13call": ll2, "logL_fused": ll3, "logL_cpu": llc, "golden": None if pinvar > 0 else -144730.8,
         "evals_per_sec_device": 1000.0 / dev_ms, "evals_per_sec_e2e_13call": 1000.0 / e2e_ms,
         "evals_per_sec_e2e_fused_call": 1000.0 / fused_ms,
         "evals_per_sec_e2e_cpp_facade": 1.0 / sec, "logL_cpp_facade": llf,
@@ -406,6 +414,7 @@ def run_ours(args, rank, world, local_rank):
                                     "single_thread_value": (n - 2) * Ps * 4 * ev1}
             if not args.no_rbcl738:
                 line["rbcl738"] = rbcl738_block(E, local_rank)
+                line["rbcl738_i_g4"] = rbcl738_block(E, local_rank, pinvar=0.2)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()

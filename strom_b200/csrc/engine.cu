@@ -175,10 +175,12 @@ struct Engine {
         CK(cudaEventCreateWithFlags(&blockCopied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
         // pattern axis padded to a whole number of thread-block tiles of every kernel that walks it
-        // (pruning tile = patternsPerBlock(); generic / root kernels use 128- or 256/C-pattern tiles)
+        // (pruning tile = patternsPerBlock(), root kernel = rootPatternsPerBlock(C)) and of 16, the granularity of
+        // the bulk L2 prefetches of 1-byte tip rows
         {
-            const int rootTile = (C <= 2 || C == 4 || C == 8) ? 256 / C : 128;
-            const int unit = std::max(std::max(patternsPerBlock(), 128), rootTile);     // (all powers of two)
+            auto lcm = [](int a, int b) { int x = a, y = b; while (y) { const int t = x % y; x = y; y = t; } return a / x * b; };
+            int unit = lcm(lcm(patternsPerBlock(), rootPatternsPerBlock(C)), 16);
+            if ((C & (C - 1)) == 0) unit = std::max(unit, 128);
             Ppad = ((P + unit - 1) / unit) * unit;
         }
         tipStride = Ppad;
@@ -202,8 +204,7 @@ struct Engine {
         std::memset(hBlock, 0, blockBytes);
         CK(cudaMalloc(&dBlock, blockBytes));
         for (int k = 0; k < kMaxCategories; ++k) hHeader()->rates[k] = 1.0;
-        const int perBlock = C <= 2 || C == 4 || C == 8 ? 256 / C : 128;
-        rootBlocks = Ppad / perBlock;
+        rootBlocks = Ppad / rootPatternsPerBlock(C);
         CK(cudaMalloc(&dBlockSums, sizeof(double) * rootBlocks));
         CK(cudaMalloc(&dTicket, sizeof(unsigned int)));
         CK(cudaMemsetAsync(dTicket, 0, sizeof(unsigned int), stream));
@@ -296,8 +297,7 @@ struct Engine {
         return big;
     }
     int patternsPerBlock() const {
-        if (C == 1 || C == 2 || C == 4 || C == 8) return bigTiles() ? (pruneThreads(kBigR) / C) * kBigR : pruneThreads(1) / C;
-        return 128;
+        return bigTiles() ? prunePatternsPerBlock(C, kBigR) : prunePatternsPerBlock(C, 1);
     }
     // How many groups a launch's chains are dealt into.  Every block pays a fixed set-up (operation words,
     // first images and operands: two dependent trips to L2/HBM), so as few groups as possible -- but:
@@ -457,14 +457,8 @@ struct Engine {
 
     template <typename real, int CC, int R>
     void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        constexpr int perBlock = (pruneThreads(R) / CC) * R;
-        dim3 grid(Ppad / perBlock, L.groupCount);
+        dim3 grid(Ppad / prunePatternsPerBlock(CC, R), L.groupCount);
         launchK(prune_chains_kernel<real, CC, R>, grid, dim3(pruneThreads(R)), true, a, L.groupStart, cumMode);
-    }
-    template <typename real, int CC>
-    void launchLevelGeneric(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        dim3 grid(Ppad / 128, L.groupCount);
-        launchK(prune_chains_generic_kernel<real, CC>, grid, dim3(128), true, a, L.groupStart, cumMode);
     }
 
     template <typename real>
@@ -517,10 +511,10 @@ struct Engine {
                 case 2: big ? launchLevelCG<real, 2, kBigR>(a, L, cumMode) : launchLevelCG<real, 2, 1>(a, L, cumMode); break;
                 case 4: big ? launchLevelCG<real, 4, kBigR>(a, L, cumMode) : launchLevelCG<real, 4, 1>(a, L, cumMode); break;
                 case 8: big ? launchLevelCG<real, 8, kBigR>(a, L, cumMode) : launchLevelCG<real, 8, 1>(a, L, cumMode); break;
-                case 3: launchLevelGeneric<real, 3>(a, L, cumMode); break;
-                case 5: launchLevelGeneric<real, 5>(a, L, cumMode); break;
-                case 6: launchLevelGeneric<real, 6>(a, L, cumMode); break;
-                case 7: launchLevelGeneric<real, 7>(a, L, cumMode); break;
+                case 3: big ? launchLevelCG<real, 3, kBigR>(a, L, cumMode) : launchLevelCG<real, 3, 1>(a, L, cumMode); break;
+                case 5: big ? launchLevelCG<real, 5, kBigR>(a, L, cumMode) : launchLevelCG<real, 5, 1>(a, L, cumMode); break;
+                case 6: big ? launchLevelCG<real, 6, kBigR>(a, L, cumMode) : launchLevelCG<real, 6, 1>(a, L, cumMode); break;
+                case 7: big ? launchLevelCG<real, 7, kBigR>(a, L, cumMode) : launchLevelCG<real, 7, 1>(a, L, cumMode); break;
             }
             CK(cudaGetLastError());
             ++launches;
@@ -594,10 +588,10 @@ struct Engine {
             case 2: launchK(root_loglik_kernel<real, 2>, dim3(rootBlocks), dim3(256), true, a); break;
             case 4: launchK(root_loglik_kernel<real, 4>, dim3(rootBlocks), dim3(256), true, a); break;
             case 8: launchK(root_loglik_kernel<real, 8>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 3: launchK(root_loglik_generic_kernel<real, 3>, dim3(rootBlocks), dim3(128), true, a); break;
-            case 5: launchK(root_loglik_generic_kernel<real, 5>, dim3(rootBlocks), dim3(128), true, a); break;
-            case 6: launchK(root_loglik_generic_kernel<real, 6>, dim3(rootBlocks), dim3(128), true, a); break;
-            case 7: launchK(root_loglik_generic_kernel<real, 7>, dim3(rootBlocks), dim3(128), true, a); break;
+            case 3: launchK(root_loglik_kernel<real, 3>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 5: launchK(root_loglik_kernel<real, 5>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 6: launchK(root_loglik_kernel<real, 6>, dim3(rootBlocks), dim3(256), true, a); break;
+            case 7: launchK(root_loglik_kernel<real, 7>, dim3(rootBlocks), dim3(256), true, a); break;
         }
         CK(cudaGetLastError());
         ++launches;

@@ -38,6 +38,20 @@ __host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
 // per launch shorten the sequential part (rbcl738: 108.6 -> 100.9 us per evaluation).
 __host__ __device__ constexpr int pruneThreads(int R) { return R == 1 ? 128 : 256; }
 __host__ __device__ constexpr int pruneBlocksPerSm(int R) { return R == 1 ? 6 : 3; }
+// Lane layout of the (pattern, category) kernels: a warp holds 32/C whole patterns, category fastest.  For
+// C = 1, 2, 4, 8 that is all 32 lanes; for 3, 5 (+I+G4), 6, 7 the last 32 - (32/C)*C lanes (2, 2, 2, 4) idle: they
+// shadow lane 0's pattern so that every address they form is valid, and never store.
+__host__ __device__ constexpr int patternsPerWarp(int C) { return 32 / C; }
+__host__ __device__ constexpr int prunePatternsPerBlock(int C, int R) { return (pruneThreads(R) / 32) * patternsPerWarp(C) * R; }
+__host__ __device__ constexpr int rootPatternsPerBlock(int C) { return (256 / 32) * patternsPerWarp(C); }
+// Maximum over the C category lanes of a pattern when C is not a power of two: lane k first holds the maximum
+// of `cover` lanes k, k+1, ... (cyclically); taking lane k+step's value, step = min(cover, C-cover), extends
+// that to cover+step lanes.  catSteps(C) rounds; catStep(C, s) is the step of round s.
+__host__ __device__ constexpr int catSteps(int C) { return C <= 1 ? 0 : C <= 2 ? 1 : C <= 4 ? 2 : 3; }
+__host__ __device__ constexpr int catStep(int C, int s) {
+    const int cover = (1 << s) < C ? (1 << s) : C;
+    return cover < C - cover ? cover : C - cover;
+}
 
 // Per-eigen-index model block, resident in HBM and refreshed once per evaluation.
 struct DevModel {
@@ -295,7 +309,10 @@ template <typename real, int C, int R>
 __global__ void __launch_bounds__(pruneThreads(R), pruneBlocksPerSm(R))
 prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
     constexpr int kPruneThreads = pruneThreads(R);
-    constexpr int G = kPruneThreads / C;                 // patterns per pass
+    constexpr int LPW = patternsPerWarp(C);              // patterns per warp
+    constexpr bool kAllLanes = LPW * C == 32;
+    constexpr bool kPow2 = (C & (C - 1)) == 0;
+    constexpr int G = (kPruneThreads / 32) * LPW;        // patterns per pass
     constexpr int MSZ = kMatStride * C;                  // reals per operand image
     constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
     constexpr int NCH = MSZ / CHUNK;                     // 16-byte chunks per operand image
@@ -309,7 +326,13 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
     __shared__ double sAcc[R][kPruneThreads];            // log part of the running scaler (touched rarely)
 
     const int tid = threadIdx.x;
-    const int k = tid % C, g = tid / C;
+    const int lane = tid & 31;
+    const bool active = kAllLanes || lane < LPW * C;     // (idle lanes shadow the warp's first pattern, category 0)
+    const int k = active ? lane % C : 0;
+    const int g = (tid >> 5) * LPW + (active ? lane / C : 0);
+    int catSrc[3];                                       // source lanes of the category maximum (C not a power of two)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) catSrc[s] = lane - k + (k + catStep(C, s)) % C;
     pdlLaunchDependents();
     const Group grp = A.groups[groupBase + blockIdx.y];
     const int nOps = grp.opEnd - grp.opStart;
@@ -361,17 +384,23 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         }
     };
     // L2 prefetch of everything an operation will read from HBM (one bulk request per tile, issued by one
-    // thread kPrefetchAhead steps early): the register loads one step ahead then hit L2
+    // thread kPrefetchAhead steps early): the register loads one step ahead then hit L2.  (Dealing the requests
+    // to lane 0 of different warps was measured and is slower: 104.9 vs 101.3 us on rbcl738.)
+    // Bulk requests are 16-byte granular: the 1-byte tip codes of a tile that does not start / end on such a
+    // boundary are asked for with the neighbouring bytes; rows are padded to a multiple of 16.
+    constexpr bool kTipAligned = (G * R) % 16 == 0;
+    const size_t tipLo = kTipAligned ? tile0 : (tile0 & ~static_cast<size_t>(15));
+    const unsigned tipBytes = kTipAligned ? G * R : static_cast<unsigned>(((tile0 + G * R + 15) & ~static_cast<size_t>(15)) - tipLo);
     auto prefetchOperands = [&](const int4& w0, const int4& w1) {
         const real* ptile = A.partials + tile0 * C * 4;
-        if (w1.w & OP_B_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * A.tipStride + tile0, G * R);
+        if (w1.w & OP_B_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * A.tipStride + tipLo, tipBytes);
         else bulkPrefetchL2(ptile + static_cast<size_t>(w0.w - A.nTips) * bufStride, TILE_BYTES);
         if (w1.z >= 0) {
             bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
             bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
         }
         if (w1.w & OP_CHAIN_START) {
-            if (w1.w & OP_A_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * A.tipStride + tile0, G * R);
+            if (w1.w & OP_A_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * A.tipStride + tipLo, tipBytes);
             else bulkPrefetchL2(ptile + static_cast<size_t>(w0.y - A.nTips) * bufStride, TILE_BYTES);
             if (w1.y >= 0) {
                 bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
@@ -380,6 +409,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
         }
     };
 
+    const bool writer = active && k == 0;               // the lane that stores a pattern's scalers
     real X[R][4], Y[R][4];
     int sX[R], sY[R];
     double prod[R], pendAcc[R], pendProd[R];             // pend*: scaler of the next step's sibling chain, if any
@@ -496,10 +526,18 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 real m[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) m[r] = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
+                if (kPow2) {
 #pragma unroll
-                for (int off = 1; off < C; off <<= 1) {
+                    for (int off = 1; off < C; off <<= 1) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_xor_sync(0xffffffffu, m[r], off));
+                        for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_xor_sync(0xffffffffu, m[r], off));
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < catSteps(C); ++s) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_sync(0xffffffffu, m[r], catSrc[s]));
+                    }
                 }
                 // below this the hardware reciprocal seed (flush-to-zero) is not usable: exact division instead
                 constexpr real kTiny = sizeof(real) == 4 ? real(1e-30) : real(1e-290);
@@ -529,12 +567,14 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             }
         }
         SB200_TICK(4)
-        if (flags & OP_CHAIN_END) {
+        if (active) {
+            if (flags & OP_CHAIN_END) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) st4(dest + r * (G * C * 4), X[r]);
-        } else {
+                for (int r = 0; r < R; ++r) st4(dest + r * (G * C * 4), X[r]);
+            } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) st4Stream(dest + r * (G * C * 4), X[r]);
+                for (int r = 0; r < R; ++r) st4Stream(dest + r * (G * C * 4), X[r]);
+            }
         }
         {
             // deferred log: multiply the maxima, fold into the log sum only before an underflow
@@ -570,7 +610,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     a += foldedLog(pr, 1.0);
                     pr = 1.0;
                 }
-                if (k == 0) {
+                if (writer) {
                     accMine[static_cast<size_t>(sKeep) * Ppad + r * G] = a;
                     prodMine[static_cast<size_t>(sKeep) * Ppad + r * G] = pr;
                 }
@@ -586,12 +626,12 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                         a += foldedLog(prod[r], 1.0);
                         prod[r] = 1.0;
                     }
-                    if (k == 0) {
+                    if (writer) {
                         accMine[static_cast<size_t>(sOut) * Ppad + r * G] = a;
                         prodMine[static_cast<size_t>(sOut) * Ppad + r * G] = prod[r];
                     }
                 }
-                if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && k == 0) {
+                if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && writer) {
                     const double total = scalerTotal(a, prod[r]);
                     double* c = A.cum + tile0 + g + r * G;
                     if (cumMode) *c = total;
@@ -636,112 +676,6 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             step(j + 1, nc, b0, b1, a0, a1);
         }
         if (j < nc) step(j, nc, a0, a1, a0, a1);
-    }
-}
-
-// Any other category count (3,5,6,7): one thread per pattern, categories looped in registers.
-template <typename real, int C>
-__global__ void __launch_bounds__(128)
-prune_chains_generic_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
-    constexpr int MSZ = kMatStride * C;
-    __shared__ __align__(16) real sm[2 * MSZ];
-    const int tid = threadIdx.x;
-    pdlLaunchDependents();
-    const Group grp = A.groups[groupBase + blockIdx.y];
-    pdlWait();
-    const int p = blockIdx.x * 128 + tid;                 // < Ppad
-    const int Ppad = A.Ppad;
-    const size_t bufStride = static_cast<size_t>(Ppad) * C * 4;
-    real X[C][4];
-    double acc = 0.0, prod = 1.0;
-
-    for (int j = grp.opStart; j < grp.opEnd; ++j) {
-        const DevOp op = A.ops[j];
-        __syncthreads();
-        for (int q = tid; q < 2 * MSZ; q += 128) {
-            const int o = q / MSZ, w = q - o * MSZ;
-            sm[q] = A.mats[static_cast<size_t>(o ? op.mb : op.ma) * MSZ + w];
-        }
-        __syncthreads();
-        if (op.sa >= 0) {
-            acc += A.slotAcc[static_cast<size_t>(op.sa) * Ppad + p];
-            accumulateFactor(acc, prod, A.slotProd[static_cast<size_t>(op.sa) * Ppad + p]);
-        }
-        if (op.sb >= 0) {
-            acc += A.slotAcc[static_cast<size_t>(op.sb) * Ppad + p];
-            accumulateFactor(acc, prod, A.slotProd[static_cast<size_t>(op.sb) * Ppad + p]);
-        }
-        const bool aMem = (op.flags & OP_CHAIN_START) != 0;
-        const bool aTip = aMem && op.a < A.nTips;
-        const bool bTip = op.b < A.nTips;
-        const int sA = aTip ? A.tips[static_cast<size_t>(op.a) * A.tipStride + p] : 0;
-        const int sB = bTip ? A.tips[static_cast<size_t>(op.b) * A.tipStride + p] : 0;
-        const real* pa = (aMem && !aTip) ? A.partials + static_cast<size_t>(op.a - A.nTips) * bufStride : nullptr;
-        const real* pb = bTip ? nullptr : A.partials + static_cast<size_t>(op.b - A.nTips) * bufStride;
-        real m = real(0);
-#pragma unroll
-        for (int kk = 0; kk < C; ++kk) {
-            const real* ma = sm;
-            const real* mb = sm + MSZ;
-            real FA[4], FB[4], Yv[4];
-            if (aTip) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) FA[i] = ma[tipIndex(C, kk, sA, i)];
-            } else {
-                if (pa) ld4(pa + (static_cast<size_t>(p) * C + kk) * 4, X[kk]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    FA[i] = ma[rmIndex(C, kk, i * 4)] * X[kk][0] + ma[rmIndex(C, kk, i * 4 + 1)] * X[kk][1] +
-                            ma[rmIndex(C, kk, i * 4 + 2)] * X[kk][2] + ma[rmIndex(C, kk, i * 4 + 3)] * X[kk][3];
-            }
-            if (bTip) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) FB[i] = mb[tipIndex(C, kk, sB, i)];
-            } else {
-                ld4(pb + (static_cast<size_t>(p) * C + kk) * 4, Yv);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    FB[i] = mb[rmIndex(C, kk, i * 4)] * Yv[0] + mb[rmIndex(C, kk, i * 4 + 1)] * Yv[1] +
-                            mb[rmIndex(C, kk, i * 4 + 2)] * Yv[2] + mb[rmIndex(C, kk, i * 4 + 3)] * Yv[3];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                X[kk][i] = FA[i] * FB[i];
-                m = rmax(m, X[kk][i]);
-            }
-        }
-        if (op.flags & OP_RESCALE) {
-            if (m == real(0)) m = real(1);
-            const real inv = real(1) / m;
-#pragma unroll
-            for (int kk = 0; kk < C; ++kk)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) X[kk][i] *= inv;
-            accumulateFactor(acc, prod, static_cast<double>(m));
-        }
-        real* dest = A.partials + static_cast<size_t>(op.dest) * bufStride + static_cast<size_t>(p) * C * 4;
-#pragma unroll
-        for (int kk = 0; kk < C; ++kk) st4(dest + kk * 4, X[kk]);
-        if (op.flags & OP_STORE_S) {
-            double a = acc, pr = prod;
-            if (pr < 1e-100) foldProduct(a, pr, 1.0);
-            A.slotAcc[static_cast<size_t>(op.sOut) * Ppad + p] = a;
-            A.slotProd[static_cast<size_t>(op.sOut) * Ppad + p] = pr;
-        }
-        if (op.flags & OP_CHAIN_END) {
-            if (op.sOut >= 0) {
-                if (prod < 1e-100) foldProduct(acc, prod, 1.0);
-                A.slotAcc[static_cast<size_t>(op.sOut) * Ppad + p] = acc;
-                A.slotProd[static_cast<size_t>(op.sOut) * Ppad + p] = prod;
-            }
-            if ((op.flags & OP_ADD_TO_CUM) && A.cum != nullptr) {
-                const double total = scalerTotal(acc, prod);
-                if (cumMode) A.cum[p] = total;
-                else A.cum[p] += total;
-            }
-            acc = 0.0;
-            prod = 1.0;
-        }
     }
 }
 
@@ -820,11 +754,15 @@ __device__ __forceinline__ void loadRootTables(const RootArgs<real>& A, double* 
 template <typename real, int C>
 __global__ void __launch_bounds__(256)
 root_loglik_kernel(const RootArgs<real> A) {
-    constexpr int G = 256 / C;
+    constexpr int LPW = patternsPerWarp(C);
+    constexpr int G = rootPatternsPerBlock(C);
+    constexpr bool kPow2 = (C & (C - 1)) == 0;
     __shared__ double W[C * 20];
     __shared__ double M[C * 16];
     __shared__ double fw[C * 4];
-    const int tid = threadIdx.x, k = tid % C, g = tid / C;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool active = LPW * C == 32 || lane < LPW * C;  // (idle lanes shadow the warp's first pattern)
+    const int k = active ? lane % C : 0, g = (tid >> 5) * LPW + (active ? lane / C : 0);
     const bool childTip = A.child < A.nTips;
     pdlLaunchDependents();
     pdlWait();
@@ -851,62 +789,22 @@ root_loglik_kernel(const RootArgs<real> A) {
             term += sj * static_cast<double>(par[i]) * fw[k * 4 + i];
         }
     }
+    if (kPow2) {
 #pragma unroll
-    for (int off = 1; off < C; off <<= 1) term += __shfl_xor_sync(0xffffffffu, term, off);
+        for (int off = 1; off < C; off <<= 1) term += __shfl_xor_sync(0xffffffffu, term, off);
+    } else {                                              // category 0's lane adds the C terms in category order
+        const double mine = term;
+        term = 0.0;
+#pragma unroll
+        for (int j = 0; j < C; ++j) term += __shfl_sync(0xffffffffu, mine, lane - k + j);
+    }
     double v = 0.0;
-    if (k == 0 && p < A.P) {
+    if (active && k == 0 && p < A.P) {
         double ll = log(term);
         if (A.cum) ll += A.cum[p];
         v = ll * A.patWeights[p];
     }
     blockReduceAndFinish<256>(v, A.blockSums, A.ticket, A.out);
-}
-
-template <typename real, int C>
-__global__ void __launch_bounds__(128)
-root_loglik_generic_kernel(const RootArgs<real> A) {
-    __shared__ double W[C * 20];
-    __shared__ double M[C * 16];
-    __shared__ double fw[C * 4];
-    const int tid = threadIdx.x;
-    const bool childTip = A.child < A.nTips;
-    pdlLaunchDependents();
-    pdlWait();
-    loadRootTables<real, C, 128>(A, W, M, fw);
-    const int p = blockIdx.x * 128 + tid;                 // < Ppad
-    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
-    const real* pp = A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + static_cast<size_t>(p) * C * 4;
-    const int s = childTip ? A.tips[static_cast<size_t>(A.child) * A.tipStride + p] : 0;
-    const real* cp = childTip ? nullptr
-                              : A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + static_cast<size_t>(p) * C * 4;
-    double site = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < C; ++kk) {
-        real par[4];
-        ld4(pp + kk * 4, par);
-        if (childTip) {
-            const double* w = W + (kk * 5 + s) * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) site += static_cast<double>(par[i]) * w[i];
-        } else {
-            real chv[4];
-            ld4(cp + kk * 4, chv);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                double sj = 0.0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sj += M[kk * 16 + i * 4 + j] * static_cast<double>(chv[j]);
-                site += sj * static_cast<double>(par[i]) * fw[kk * 4 + i];
-            }
-        }
-    }
-    double v = 0.0;
-    if (p < A.P) {
-        double ll = log(site);
-        if (A.cum) ll += A.cum[p];
-        v = ll * A.patWeights[p];
-    }
-    blockReduceAndFinish<128>(v, A.blockSums, A.ticket, A.out);
 }
 
 }  // namespace sb200

@@ -88,6 +88,27 @@ def test_random_trees_and_ragged_sizes(engine, oracle, ntaxa, npat, model, seed)
     assert rel_err(full_eval(engine, fx, m), full_eval(oracle, fx, m)) < LOGL_RTOL
 
 
+# Every category count the engine takes, at sizes on both sides of the tile switch (P*C >= 2^18 runs the streaming
+# variant: 2 patterns per thread, 256-thread blocks); 3, 5 (+I+G4), 6 and 7 leave 2-4 lanes of each warp idle.
+@pytest.mark.parametrize("ntaxa,npat,model,seed", [(14, 70001, "gtr_g4", 21), (14, 60013, "gtr_i_g4", 22), (9, 100003, "gtr_g3", 23),
+                                                   (9, 50021, "gtr_g6", 24), (9, 40009, "gtr_g7", 25), (40, 40001, "gtr_g8", 26),
+                                                   (30, 1235, "gtr_g6", 27), (30, 97, "gtr_g7", 28), (50, 2000, "gtr_g5", 29),
+                                                   (12, 300007, "jc", 30)])
+def test_every_category_count_both_tile_sizes(engine, oracle, ntaxa, npat, model, seed):
+    fx = random_problem(ntaxa, npat, seed, missing_frac=0.05)
+    m = named_model(model)
+    ex, ox = Extra(engine), Extra(oracle)
+    Cc = len(m["rates"])
+    le, ie = full_eval(engine, fx, m, keep=True)
+    lo, io = full_eval(oracle, fx, m, keep=True)
+    assert rel_err(le, lo) < LOGL_RTOL
+    root = int(fx["parent"])
+    np.testing.assert_allclose(ex.partials(ie, root, npat, Cc), ox.partials(io, root, npat, Cc), rtol=1e-7, atol=1e-13)
+    np.testing.assert_allclose(ex.scale(ie, 0, npat), ox.scale(io, 0, npat), rtol=1e-12, atol=1e-12)
+    oracle.finalize(io)
+    engine.finalize(ie)
+
+
 def test_all_missing_column_and_zero_length_edges(engine, oracle):
     fx = random_problem(12, 40, 11, missing_frac=0.0)
     fx["data"][:, 3] = 4                      # a pattern with no information: site likelihood 1

@@ -10,7 +10,12 @@ from strom_b200.engine import EvalArgs, ShardedLikelihood
 n_eval = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 fx = np.load(os.path.join(ROOT, "tests", "golden", "rbcl738.npz"))
 model = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA, 4)
-L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], 4, device=0)
+PINV = float(os.environ.get("PINVAR", "0"))          # > 0: GTR+I+G4 (a fifth category of rate 0)
+if PINV > 0:
+    from strom_b200 import hostmodel
+    model["rates"], model["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA, 4, PINV)
+NC = len(model["rates"])
+L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0)
 ea = EvalArgs(model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
 print("logL", L.calc_log_likelihood(ea))
 for _ in range(10):
@@ -34,7 +39,7 @@ L.close()
 import ctypes as C
 from strom_b200.engine import api
 E = api()
-L2 = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], 4, device=0)
+L2 = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0)
 E.lib.sb200Finish.argtypes = [C.c_int, C.POINTER(C.c_double)]
 out = C.c_double()
 for _ in range(20):

@@ -5,7 +5,12 @@ from bench import gtr_gamma_model, PAUP_PI, PAUP_R, PAUP_ALPHA
 from strom_b200.engine import EvalArgs, ShardedLikelihood
 fx = np.load(os.path.join(ROOT, "tests", "golden", "rbcl738.npz"))
 model = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA, 4)
-L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], 4, device=0)
+PINV = float(os.environ.get("PINVAR", "0"))          # > 0: GTR+I+G4 (a fifth category of rate 0)
+if PINV > 0:
+    from strom_b200 import hostmodel
+    model["rates"], model["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA, 4, PINV)
+NC = len(model["rates"])
+L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0)
 ea = EvalArgs(model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
 L.E.lib.sb200DebugTrace.argtypes = [C.c_int, C.c_void_p]
 L.E.lib.sb200DebugTrace(L.inst, None)
