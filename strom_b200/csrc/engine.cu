@@ -35,10 +35,6 @@ struct CudaFail {
 
 static int g_device = 0;
 
-#ifndef SB200_BIG_R
-#define SB200_BIG_R 2
-#endif
-constexpr int kBigR = SB200_BIG_R;   // patterns per thread of the streaming (large-P) pruning kernel
 
 // Host image of the per-call parameter block; mirrored 1:1 in HBM and refreshed by ONE copy.
 struct ParamBlockHeader {
@@ -211,6 +207,7 @@ struct Engine {
         CK(cudaMalloc(&dOut, sizeof(double)));
         CK(cudaMallocHost(&hOut, sizeof(double)));
         if (const char* f = std::getenv("SB200_PDL")) usePdl = std::atoi(f) != 0;   // tuning aid: plain stream order
+        if (const char* f = std::getenv("SB200_TIPS_KERNEL")) useTipsKernel = std::atoi(f) != 0;
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -296,8 +293,10 @@ struct Engine {
         if (const char* f = std::getenv("SB200_FORCE_R")) big = (f[0] == '2');   // tuning aid
         return big;
     }
+    // which prune_chains_kernel variant this instance runs (fixed at creation: it sets the pattern padding)
+    int variant() const { return bigTiles() ? kVariantStream : kVariantSmall; }
     int patternsPerBlock() const {
-        return bigTiles() ? prunePatternsPerBlock(C, kBigR) : prunePatternsPerBlock(C, 1);
+        return prunePatternsPerBlock(C, variant());
     }
     // How many groups a launch's chains are dealt into.  Every block pays a fixed set-up (operation words,
     // first images and operands: two dependent trips to L2/HBM), so as few groups as possible -- but:
@@ -307,7 +306,7 @@ struct Engine {
     //   * many tiles (streaming sizes): enough blocks for >= 8 waves, so the last partial wave costs little.
     int groupsPerLevel() const {
         const int tiles = Ppad / patternsPerBlock();
-        int slots = bigTiles() ? 148 * pruneBlocksPerSm(kBigR) : 148 * pruneBlocksPerSm(1) * 2;
+        int slots = bigTiles() ? 148 * pruneBlocksPerSm(kVariantStream) : 148 * pruneBlocksPerSm(variant()) * 2;
         if (const char* f = std::getenv("SB200_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
         if (tiles * 2 <= slots) return std::max(1, slots / tiles);
         return std::max(1, (8 * slots + tiles - 1) / tiles);
@@ -440,6 +439,7 @@ struct Engine {
     // Launch on the engine's stream; `dependent`: the kernel follows another kernel of the same evaluation and may
     // be scheduled while that one drains (programmatic dependent launch, see pdlWait in kernels.cuh).
     bool usePdl = true;
+    bool useTipsKernel = true;            // SB200_TIPS_KERNEL=0 (tuning aid): tips-only launches run the general kernel
     template <typename... KArgs, typename... Args>
     void launchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, bool dependent, Args&&... args) {
         cudaLaunchConfig_t cfg{};
@@ -455,10 +455,16 @@ struct Engine {
         CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
     }
 
-    template <typename real, int CC, int R>
-    void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        dim3 grid(Ppad / prunePatternsPerBlock(CC, R), L.groupCount);
-        launchK(prune_chains_kernel<real, CC, R>, grid, dim3(pruneThreads(R)), true, a, L.groupStart, cumMode);
+    template <typename real, int CC, int V, bool TIPS>
+    void launchLevelV(const PruneArgs<real>& a, const Level& L, int cumMode) {
+        dim3 grid(Ppad / prunePatternsPerBlock(CC, V), L.groupCount);
+        launchK(prune_chains_kernel<real, CC, V, TIPS>, grid, dim3(pruneThreads(V)), true, a, L.groupStart, cumMode);
+    }
+    template <typename real, int CC>
+    void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode, int v) {
+        const bool tips = L.tipsOnly != 0 && useTipsKernel;
+        if (v == kVariantStream) tips ? launchLevelV<real, CC, kVariantStream, true>(a, L, cumMode) : launchLevelV<real, CC, kVariantStream, false>(a, L, cumMode);
+        else tips ? launchLevelV<real, CC, kVariantSmall, true>(a, L, cumMode) : launchLevelV<real, CC, kVariantSmall, false>(a, L, cumMode);
     }
 
     template <typename real>
@@ -498,7 +504,7 @@ struct Engine {
             CK(cudaGetLastError());
             ++launches;
         }
-        const bool big = bigTiles();
+        const int v = variant();
         int traceLevel = -1, levelIndex = 0;
         if (const char* f = std::getenv("SB200_TRACE_LEVEL")) traceLevel = std::atoi(f);   // tuning aid (needs -DSB200_TRACE)
         long long* const traceBuf = a.trace;
@@ -507,14 +513,14 @@ struct Engine {
             ++levelIndex;
             if (L.groupCount == 0) continue;
             switch (C) {
-                case 1: big ? launchLevelCG<real, 1, kBigR>(a, L, cumMode) : launchLevelCG<real, 1, 1>(a, L, cumMode); break;
-                case 2: big ? launchLevelCG<real, 2, kBigR>(a, L, cumMode) : launchLevelCG<real, 2, 1>(a, L, cumMode); break;
-                case 4: big ? launchLevelCG<real, 4, kBigR>(a, L, cumMode) : launchLevelCG<real, 4, 1>(a, L, cumMode); break;
-                case 8: big ? launchLevelCG<real, 8, kBigR>(a, L, cumMode) : launchLevelCG<real, 8, 1>(a, L, cumMode); break;
-                case 3: big ? launchLevelCG<real, 3, kBigR>(a, L, cumMode) : launchLevelCG<real, 3, 1>(a, L, cumMode); break;
-                case 5: big ? launchLevelCG<real, 5, kBigR>(a, L, cumMode) : launchLevelCG<real, 5, 1>(a, L, cumMode); break;
-                case 6: big ? launchLevelCG<real, 6, kBigR>(a, L, cumMode) : launchLevelCG<real, 6, 1>(a, L, cumMode); break;
-                case 7: big ? launchLevelCG<real, 7, kBigR>(a, L, cumMode) : launchLevelCG<real, 7, 1>(a, L, cumMode); break;
+                case 1: launchLevelCG<real, 1>(a, L, cumMode, v); break;
+                case 2: launchLevelCG<real, 2>(a, L, cumMode, v); break;
+                case 4: launchLevelCG<real, 4>(a, L, cumMode, v); break;
+                case 8: launchLevelCG<real, 8>(a, L, cumMode, v); break;
+                case 3: launchLevelCG<real, 3>(a, L, cumMode, v); break;
+                case 5: launchLevelCG<real, 5>(a, L, cumMode, v); break;
+                case 6: launchLevelCG<real, 6>(a, L, cumMode, v); break;
+                case 7: launchLevelCG<real, 7>(a, L, cumMode, v); break;
             }
             CK(cudaGetLastError());
             ++launches;

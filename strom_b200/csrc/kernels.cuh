@@ -36,13 +36,22 @@ __host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
 // threads, 3 blocks per SM.  Small pattern counts (R = 1): 128 threads, 6 blocks per SM -- a step is bound by the
 // latency of one warp's instruction stream and by the block barrier, so smaller blocks and twice as many groups
 // per launch shorten the sequential part (rbcl738: 108.6 -> 100.9 us per evaluation).
-__host__ __device__ constexpr int pruneThreads(int R) { return R == 1 ? 128 : 256; }
-__host__ __device__ constexpr int pruneBlocksPerSm(int R) { return R == 1 ? 6 : 3; }
+// Variants (template parameter V of prune_chains_kernel): patterns per thread R, threads per block, blocks per SM.
+// (A third variant, 64 threads x 2 patterns for small pattern counts, was measured and dropped: rbcl738 104.4 vs
+// 100.6 us.)  TIPS = the launch holds only operations whose operands from memory are tips and that read no subtree
+// scalers (level 0 of every full evaluation: 37 % of the bytes of a 1000-taxon evaluation): the partials-operand
+// and scaler-operand code is compiled out, which frees registers for one more resident block per SM.
+enum { kVariantSmall = 0, kVariantStream = 1 };
+__host__ __device__ constexpr int pruneR(int V) { return V == kVariantSmall ? 1 : 2; }
+__host__ __device__ constexpr int pruneThreads(int V) { return V == kVariantSmall ? 128 : 256; }
+__host__ __device__ constexpr int pruneBlocksPerSm(int V, bool tips = false) {
+    return V == kVariantSmall ? (tips ? 8 : 6) : (tips ? 4 : 3);
+}
 // Lane layout of the (pattern, category) kernels: a warp holds 32/C whole patterns, category fastest.  For
 // C = 1, 2, 4, 8 that is all 32 lanes; for 3, 5 (+I+G4), 6, 7 the last 32 - (32/C)*C lanes (2, 2, 2, 4) idle: they
 // shadow lane 0's pattern so that every address they form is valid, and never store.
 __host__ __device__ constexpr int patternsPerWarp(int C) { return 32 / C; }
-__host__ __device__ constexpr int prunePatternsPerBlock(int C, int R) { return (pruneThreads(R) / 32) * patternsPerWarp(C) * R; }
+__host__ __device__ constexpr int prunePatternsPerBlock(int C, int V) { return (pruneThreads(V) / 32) * patternsPerWarp(C) * pruneR(V); }
 __host__ __device__ constexpr int rootPatternsPerBlock(int C) { return (256 / 32) * patternsPerWarp(C); }
 // Maximum over the C category lanes of a pattern when C is not a power of two: lane k first holds the maximum
 // of `cover` lanes k, k+1, ... (cyclically); taking lane k+step's value, step = min(cover, C-cover), extends
@@ -305,10 +314,11 @@ constexpr int kOpChunk = 256;                  // operations of a group held in 
 constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // steps between an operand tile's L2 prefetch and its register load
 constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 
-template <typename real, int C, int R>
-__global__ void __launch_bounds__(pruneThreads(R), pruneBlocksPerSm(R))
+template <typename real, int C, int V, bool TIPS>
+__global__ void __launch_bounds__(pruneThreads(V), pruneBlocksPerSm(V, TIPS))
 prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
-    constexpr int kPruneThreads = pruneThreads(R);
+    constexpr int R = pruneR(V);
+    constexpr int kPruneThreads = pruneThreads(V);
     constexpr int LPW = patternsPerWarp(C);              // patterns per warp
     constexpr bool kAllLanes = LPW * C == 32;
     constexpr bool kPow2 = (C & (C - 1)) == 0;
@@ -393,16 +403,16 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
     const unsigned tipBytes = kTipAligned ? G * R : static_cast<unsigned>(((tile0 + G * R + 15) & ~static_cast<size_t>(15)) - tipLo);
     auto prefetchOperands = [&](const int4& w0, const int4& w1) {
         const real* ptile = A.partials + tile0 * C * 4;
-        if (w1.w & OP_B_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * A.tipStride + tipLo, tipBytes);
+        if (TIPS || (w1.w & OP_B_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * A.tipStride + tipLo, tipBytes);
         else bulkPrefetchL2(ptile + static_cast<size_t>(w0.w - A.nTips) * bufStride, TILE_BYTES);
-        if (w1.z >= 0) {
+        if (!TIPS && w1.z >= 0) {
             bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
             bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
         }
         if (w1.w & OP_CHAIN_START) {
-            if (w1.w & OP_A_TIP) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * A.tipStride + tipLo, tipBytes);
+            if (TIPS || (w1.w & OP_A_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * A.tipStride + tipLo, tipBytes);
             else bulkPrefetchL2(ptile + static_cast<size_t>(w0.y - A.nTips) * bufStride, TILE_BYTES);
-            if (w1.y >= 0) {
+            if (!TIPS && w1.y >= 0) {
                 bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
                 bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
             }
@@ -418,9 +428,9 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
 
     // operand A of a chain start, and the scaler of the chain that produced it
     auto startChain = [&](const int4& w0, const int4& w1) {
-        if (w1.w & OP_A_TIP) fetchTip(w0.y, sX);
+        if (TIPS || (w1.w & OP_A_TIP)) fetchTip(w0.y, sX);
         else fetchPartial(w0.y, X);
-        if (w1.y >= 0) {
+        if (!TIPS && w1.y >= 0) {
             double a[R], pr[R];
             loadSlot(w1.y, a, pr);
 #pragma unroll
@@ -433,9 +443,9 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
     };
     // operand B (and its chain's scaler) of an operation, one step ahead of its use
     auto fetchB = [&](const int4& w0, const int4& w1) {
-        if (w1.w & OP_B_TIP) fetchTip(w0.w, sY);
+        if (TIPS || (w1.w & OP_B_TIP)) fetchTip(w0.w, sY);
         else fetchPartial(w0.w, Y);
-        if (w1.z >= 0) loadSlot(w1.z, pendAcc, pendProd);
+        if (!TIPS && w1.z >= 0) loadSlot(w1.z, pendAcc, pendProd);
     };
 
     // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
@@ -479,7 +489,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             }
         } else {
             // factor of operand A (from registers, or tip table at a chain start), then operand B
-            if (flags & OP_A_TIP) {
+            if (!TIPS && (flags & OP_A_TIP)) {       // (TIPS: a chain start with a tip for A is a tip x tip operation)
 #pragma unroll
                 for (int r = 0; r < R; ++r) factorTip<real, C>(sa, k, sX[r], X[r]);
             } else {
@@ -492,7 +502,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                 }
             }
             SB200_TICK(7)
-            if (flags & OP_B_TIP) {
+            if (TIPS || (flags & OP_B_TIP)) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     real F[4];
@@ -509,7 +519,7 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
                     for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
                 }
             }
-            if (w1.z >= 0) {
+            if (!TIPS && w1.z >= 0) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     double acc = sAcc[r][tid] + pendAcc[r];

@@ -95,7 +95,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             out.ops.push_back(makeOp(op.destinationPartials - tipCount, op.child1Partials, op.child1TransitionMatrix,
                                      op.child2Partials, op.child2TransitionMatrix, -1, -1, fl, -1));
             out.chains.push_back(DevChain{o, 1, -1, (accumulate && rescale) ? CHAIN_ADD_TO_CUM : 0});
-            out.levels.push_back(Level{o, 1, o, 1});
+            out.levels.push_back(Level{o, 1, o, 1, 0});
             out.groups.push_back(Group{o, o + 1});
             out.opLevel[o] = o;
             out.opChain[o] = o;
@@ -184,7 +184,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             bins[best].push_back(c);
             load[best] += chainOps[c].size() + 1;     // +1: a chain start costs about one extra step
         }
-        Level L{static_cast<int>(out.chains.size()), static_cast<int>(ids.size()), static_cast<int>(out.groups.size()), nGroups};
+        Level L{static_cast<int>(out.chains.size()), static_cast<int>(ids.size()), static_cast<int>(out.groups.size()), nGroups, 0};
         for (int g = 0; g < nGroups; ++g) {
             Group G{static_cast<int>(out.ops.size()), 0};
             for (int c : bins[g]) {
@@ -245,6 +245,15 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
     }
     for (int o = 0; o < count; ++o) out.opChain[o] = chainNewId[out.opChain[o]];
     assignTipTipTables(out, tipCount);
+    for (Level& L : out.levels) {
+        bool tips = L.groupCount > 0;
+        for (int g = L.groupStart; g < L.groupStart + L.groupCount && tips; ++g)
+            for (int j = out.groups[g].opStart; j < out.groups[g].opEnd && tips; ++j) {
+                const DevOp& d = out.ops[j];
+                tips = (d.flags & OP_B_TIP) && (!(d.flags & OP_CHAIN_START) || (d.flags & OP_A_TIP)) && d.sa < 0 && d.sb < 0;
+            }
+        L.tipsOnly = tips ? 1 : 0;
+    }
     return BEAGLE_SUCCESS;
 }
 

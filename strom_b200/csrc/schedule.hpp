@@ -62,6 +62,8 @@ struct Level {
     int chainCount;
     int groupStart;   // index into Schedule::groups
     int groupCount;
+    int tipsOnly;     // every operand read from memory is a tip and no operation reads a subtree scaler (level 0 of a
+                      // full evaluation): the launch may use the kernel variant without partials-operand code
 };
 
 struct Group {
