@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -104,7 +105,10 @@ struct Engine {
     double* dBlockSums = nullptr;
     unsigned int* dTicket = nullptr;
     double* dOut = nullptr;
-    double* hOut = nullptr;               // pinned, written by the root kernel directly
+    double* hOut = nullptr;               // pinned, written by the root kernel directly: [0] the scalar, [1] a sequence word
+    unsigned long long rootSeq = 0;       // sequence number of the last root launch that targets hOut
+    unsigned long long awaitedSeq = 0;    // ... that readScalar has to see in hOut[1] (0: none outstanding)
+    bool pollResult = true;               // SB200_POLL=0 (tuning aid): wait with cudaStreamSynchronize only
     int rootBlocks = 0;
     // last root-edge call (for replay)
     int lastParent = -1, lastChild = -1, lastMatrix = -1, lastWIdx = 0, lastFIdx = 0, lastRootCum = BEAGLE_OP_NONE;
@@ -205,7 +209,9 @@ struct Engine {
         CK(cudaMalloc(&dTicket, sizeof(unsigned int)));
         CK(cudaMemsetAsync(dTicket, 0, sizeof(unsigned int), stream));
         CK(cudaMalloc(&dOut, sizeof(double)));
-        CK(cudaMallocHost(&hOut, sizeof(double)));
+        CK(cudaMallocHost(&hOut, 2 * sizeof(double)));
+        std::memset(hOut, 0, 2 * sizeof(double));
+        if (const char* f = std::getenv("SB200_POLL")) pollResult = std::atoi(f) != 0;
         if (const char* f = std::getenv("SB200_PDL")) usePdl = std::atoi(f) != 0;   // tuning aid: plain stream order
         if (const char* f = std::getenv("SB200_TIPS_KERNEL")) useTipsKernel = std::atoi(f) != 0;
         CK(cudaStreamSynchronize(stream));
@@ -582,6 +588,13 @@ struct Engine {
         a.blockSums = dBlockSums;
         a.ticket = dTicket;
         a.out = out;
+        a.doneFlag = nullptr;
+        a.doneSeq = 0;
+        awaitedSeq = 0;
+        if (out == hOut) {
+            a.doneFlag = reinterpret_cast<unsigned long long*>(hOut + 1);
+            a.doneSeq = awaitedSeq = ++rootSeq;
+        }
         a.tipStride = tipStride;
         a.P = P;
         a.Ppad = Ppad;
@@ -619,10 +632,29 @@ struct Engine {
     // The root kernel wrote the scalar straight into pinned host memory (hOut is device-accessible through
     // UVA): the 8-byte device->host transfer is part of the kernel, only the stream wait remains.
     int readScalar(double* out) {
-        CK(cudaStreamSynchronize(stream));
+        // The last block of the root kernel stores the scalar and then a sequence word in pinned host memory: polling
+        // that word returns a few microseconds before the stream is reported idle (kernel completion and the
+        // driver's own bookkeeping come after the store).  Everything enqueued earlier is complete by stream order.
+        bool seen = false;
+        if (pollResult && awaitedSeq != 0) {
+            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(hOut + 1);
+            for (unsigned spins = 1;; ++spins) {
+                if (*flag == awaitedSeq) { seen = true; break; }
+                if ((spins & 0x3fff) == 0) {                       // a failed launch or kernel never writes: ask the driver now and then
+                    const cudaError_t q = cudaStreamQuery(stream);
+                    if (q != cudaErrorNotReady) break;             // idle (flag is there) or an error (reported below)
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (!seen) CK(cudaStreamSynchronize(stream));
+        awaitedSeq = 0;
         blockInFlight = false;
         schedInFlight = false;
-        *out = *hOut;
+        *out = *reinterpret_cast<const volatile double*>(hOut);
         return (*out != *out) ? BEAGLE_ERROR_FLOATING_POINT : BEAGLE_SUCCESS;
     }
 };

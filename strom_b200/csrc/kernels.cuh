@@ -103,6 +103,8 @@ struct RootArgs {
     double* blockSums;
     unsigned int* ticket;
     double* out;
+    unsigned long long* doneFlag;    // pinned host word that receives doneSeq after `out` (host memory) was written, or nullptr
+    unsigned long long doneSeq;
     long long tipStride;
     int P;
     int Ppad;
@@ -720,7 +722,8 @@ __device__ __forceinline__ double warpSum(double v) {
 // Block-level sum of `v` (fixed order), then the last block to finish adds the per-block sums in
 // index order, so the result does not depend on scheduling.
 template <int THREADS>
-__device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums, unsigned int* ticket, double* out) {
+__device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums, unsigned int* ticket, double* out,
+                                                     unsigned long long* doneFlag, unsigned long long doneSeq) {
     __shared__ double warpPart[THREADS / 32];
     __shared__ bool isLast;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -745,6 +748,10 @@ __device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums
         if (lane == 0) {
             *out = s;
             *ticket = 0u;
+            if (doneFlag) {                  // the host polls this word instead of waiting for the stream to drain
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long*>(doneFlag) = doneSeq;
+            }
         }
     }
 }
@@ -817,7 +824,7 @@ root_loglik_kernel(const RootArgs<real> A) {
         if (A.cum) ll += A.cum[p];
         v = ll * A.patWeights[p];
     }
-    blockReduceAndFinish<256>(v, A.blockSums, A.ticket, A.out);
+    blockReduceAndFinish<256>(v, A.blockSums, A.ticket, A.out, A.doneFlag, A.doneSeq);
 }
 
 }  // namespace sb200

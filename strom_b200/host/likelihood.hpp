@@ -304,26 +304,36 @@ inline void Likelihood::setModelRateMatrix() {
 // every node's edge is indexed by the node's number, except that the last entry -- preorder[0], whose
 // number 2n-3 is out of range -- uses the root tip's number (reference src/likelihood.hpp:296-355).
 inline void Likelihood::defineOperations(Tree::SharedPtr t) {
-    _operations.clear();
-    _pmatrix_index.clear();
-    _edge_lengths.clear();
-    for (size_t i = t->_levelorder.size(); i-- > 0;) {
-        Node* nd = t->_levelorder[i];
+    // (filled through raw pointers into vectors sized once: this runs on every call, before the GPU has anything
+    // to do, and 9000 push_backs cost more than the engine's whole enqueue on a 738-taxon tree)
+    const size_t nn = t->_levelorder.size();
+    _pmatrix_index.resize(nn);
+    _edge_lengths.resize(nn);
+    _operations.resize(7 * nn);
+    int* pm = nn ? &_pmatrix_index[0] : nullptr;
+    double* el = nn ? &_edge_lengths[0] : nullptr;
+    int* op = nn ? &_operations[0] : nullptr;
+    const int ntaxa = static_cast<int>(_ntaxa);
+    for (size_t i = nn; i-- > 0;) {
+        const Node* nd = t->_levelorder[i];
         assert(nd->_number >= 0);
-        _pmatrix_index.push_back(nd->_number);
-        _edge_lengths.push_back(nd->_edge_length);
+        *pm++ = nd->_number;
+        *el++ = nd->_edge_length;
         if (nd->_left_child) {
             assert(nd->_left_child->_right_sib);
-            _operations.push_back(nd->_number);                          // destination partials
-            _operations.push_back(nd->_number - static_cast<int>(_ntaxa) + 1);   // scaling buffer to write
-            _operations.push_back(BEAGLE_OP_NONE);                       // scaling buffer to read
-            _operations.push_back(nd->_left_child->_number);             // left child partials
-            _operations.push_back(nd->_left_child->_number);             // left child transition matrix
-            _operations.push_back(nd->_left_child->_right_sib->_number); // right child partials (binary tree)
-            _operations.push_back(nd->_left_child->_right_sib->_number); // right child transition matrix
+            const int l = nd->_left_child->_number, r = nd->_left_child->_right_sib->_number;
+            op[0] = nd->_number;                 // destination partials
+            op[1] = nd->_number - ntaxa + 1;     // scaling buffer to write
+            op[2] = BEAGLE_OP_NONE;              // scaling buffer to read
+            op[3] = l;                           // left child partials
+            op[4] = l;                           // left child transition matrix
+            op[5] = r;                           // right child partials (binary tree)
+            op[6] = r;                           // right child transition matrix
+            op += 7;
         }
     }
-    if (!t->_is_rooted) _pmatrix_index[_pmatrix_index.size() - 1] = t->_root->_number;
+    _operations.resize(nn ? static_cast<size_t>(op - &_operations[0]) : 0);
+    if (!t->_is_rooted && nn) _pmatrix_index[nn - 1] = t->_root->_number;
 }
 
 inline void Likelihood::setIncremental(bool on) {
