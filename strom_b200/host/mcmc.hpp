@@ -17,6 +17,7 @@
 //     m = exp(lambda (u - 0.5)), and with probability 1/2 an NNI swap across that edge -- it exercises
 //     topology + edge-length changes through the engine but is not the reference's 8-case proposal.
 #pragma once
+#include <cstdlib>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -444,6 +445,7 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         lik->setDevices(std::vector<int>(1, opt.devices[c % opt.devices.size()]));
         lik->setData(data);
         lik->setModel(model);
+        if (std::getenv("STROM_HOST_NODATA")) lik->useStoredData(false);   // tuning aid: host cost of an iteration without likelihoods
         ch.setLikelihood(lik);
         ch.startTuning();
         ch.setChainIndex(c);
