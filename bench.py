@@ -276,6 +276,13 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
     hd = H.data_from_codes(data.astype(np.int32)[:, cols], compress=True)
     llf, sec = H.loglik(hd, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
     H.data_free(hd)
+    # ... and the same facade compiled as the reference has it: 13 BeagleLib calls per evaluation, library = this engine
+    from strom_b200.build import HOST_13CALL_LIB
+    from strom_b200.host import HostAPI
+    H13 = HostAPI(HOST_13CALL_LIB)
+    hd13 = H13.data_from_codes(data.astype(np.int32)[:, cols], compress=True)
+    llf13, sec13 = H13.loglik(hd13, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
+    H13.data_free(hd13)
     # CPU oracle on the same problem
     tips = data
     one, _, llc = time_oracle(tips, fx["counts"], model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]),
@@ -289,9 +296,10 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
                     ("GTR+I+G4 (pinvar %.2f, %d categories)" % (pinvar, NC) if pinvar > 0 else "GTR+G4"),
         "categories": NC,
         "logL": ll, "logL_13call": ll2, "logL_fused": ll3, "logL_cpu": llc, "golden": None if pinvar > 0 else -144730.8,
-        "evals_per_sec_device": 1000.0 / dev_ms, "evals_per_sec_e2e_13call": 1000.0 / e2e_ms,
+        "evals_per_sec_device": 1000.0 / dev_ms, "evals_per_sec_e2e_13call_python_ctypes": 1000.0 / e2e_ms,
         "evals_per_sec_e2e_fused_call": 1000.0 / fused_ms,
         "evals_per_sec_e2e_cpp_facade": 1.0 / sec, "logL_cpp_facade": llf,
+        "evals_per_sec_e2e_cpp_facade_13_calls": 1.0 / sec13, "logL_cpp_facade_13_calls": llf13,
         "evals_per_sec_device_4_concurrent_chains": 1000.0 / conc_ms,
         "partial_updates_per_sec_device": upd * 1000.0 / dev_ms,
         "cpu_evals_per_sec_1thread": one, "cpu_evals_per_sec_all_threads": allc, "cpu_threads": thr,

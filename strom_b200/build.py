@@ -106,10 +106,28 @@ def build_host_oracle(force: bool = False) -> str:
     return HOST_ORACLE_LIB
 
 
+HOST_13CALL_LIB = os.path.join(HOST_DIR, "libstrom_host_13call.so")
+
+
+def build_host_13call(force: bool = False) -> str:
+    """The host classes exactly as the reference drives BeagleLib -- Likelihood::calcLogLikelihood issuing the 13 calls
+    of include/strom_beagle.h one by one (no engine-level entry point) -- linked to the CUDA engine: the drop-in case."""
+    build_engine()
+    if force or _stale(HOST_13CALL_LIB, host_sources() + [ENGINE_LIB]):
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-pthread",
+               "-o", HOST_13CALL_LIB, os.path.join(HOST_DIR, "capi.cpp"), "-L" + CSRC, "-lstrom_b200", "-Wl,-rpath,$ORIGIN/../csrc"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building libstrom_host_13call.so failed")
+    return HOST_13CALL_LIB
+
+
 def build_all(force: bool = False, verbose: bool = False):
     build_engine(force, verbose)
     build_oracle(force)
     build_host(force)
+    build_host_13call(force)
     build_host_oracle(force)
 
 

@@ -30,6 +30,29 @@ def test_cpp_facade_matches_goldens(hostlib, key, model):
     hostlib.data_free(h)
 
 
+@pytest.fixture(scope="module")
+def hostlib13():
+    # the same host classes compiled WITHOUT the engine-level entry point: Likelihood::calcLogLikelihood issues the
+    # reference's 13 BeagleLib calls one by one (src/likelihood.hpp:409-447) -- and the library behind them is the CUDA engine
+    from strom_b200.build import build_host_13call
+    from strom_b200.host import HostAPI
+    return HostAPI(build_host_13call())
+
+
+@pytest.mark.parametrize("key", ["rbcL", "rbcl10", "rbcl738"])
+@pytest.mark.parametrize("model", ["jc", "gtr_g4", "gtr_i_g4"])
+def test_drop_in_13_call_sequence_matches_goldens(hostlib, hostlib13, key, model):
+    fx = load_golden(key)
+    h13 = _data(hostlib13, fx)
+    ll13, _ = hostlib13.loglik(h13, str(fx["newick"]), *MODEL_ARGS[model], repeats=3)
+    assert rel_err(ll13, float(fx["lnL_" + model])) < 1e-11
+    hostlib13.data_free(h13)
+    h = _data(hostlib, fx)
+    ll, _ = hostlib.loglik(h, str(fx["newick"]), *MODEL_ARGS[model])
+    hostlib.data_free(h)
+    assert ll13 == ll                        # the fused engine call runs the very same kernels
+
+
 @pytest.mark.parametrize("shards", [2, 3, 5])
 def test_pattern_shards_sum_to_the_whole(hostlib, shards):
     # several shards (here all on device 0) = independent instances holding a pattern slice each;
