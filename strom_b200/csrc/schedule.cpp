@@ -3,6 +3,7 @@
 #include "schedule.hpp"
 
 #include <algorithm>
+#include <utility>
 
 namespace sb200 {
 
@@ -108,11 +109,14 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
         return BEAGLE_SUCCESS;
     }
 
-    // Strahler-style levels and chains.
-    std::vector<std::vector<int>> chainOps;          // chain id -> input operation indices, bottom-up
-    std::vector<int> chainLevel;
+    // Strahler-style levels and chains.  (Flat arrays throughout: this runs for every new topology of an MCMC, where a
+    // vector per chain and per group made the planner as expensive as the evaluation it plans.)
+    std::vector<int> chainLevel, chainLen, chainLast;     // per chain: level, operation count, last input operation
     std::vector<int> carriedChild(count, -1);        // which input child (0/1) is carried, -1 none
     std::vector<char> readFromMemory(count, 0);      // produced buffer is re-read from HBM by its parent
+    chainLevel.reserve(count);
+    chainLen.reserve(count);
+    chainLast.reserve(count);
     for (int o = 0; o < count; ++o) {
         classify(ops[o]);
         const int i1 = in1[o], i2 = in2[o];
@@ -126,36 +130,43 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             const int other = carry == 0 ? i2 : i1;
             out.opLevel[o] = out.opLevel[c];
             out.opChain[o] = out.opChain[c];
-            chainOps[out.opChain[o]].push_back(o);
+            ++chainLen[out.opChain[o]];
+            chainLast[out.opChain[o]] = o;
             carriedChild[o] = carry;
             if (other >= 0) readFromMemory[other] = 1;
         } else {
             const int lvl = (i1 >= 0) ? l1 + 1 : 0;   // both in-list with equal level, or neither in-list
             out.opLevel[o] = lvl;
-            out.opChain[o] = static_cast<int>(chainOps.size());
-            chainOps.emplace_back(1, o);
+            out.opChain[o] = static_cast<int>(chainLen.size());
+            chainLen.push_back(1);
+            chainLast.push_back(o);
             chainLevel.push_back(lvl);
             if (i1 >= 0) readFromMemory[i1] = 1;
             if (i2 >= 0) readFromMemory[i2] = 1;
         }
     }
+    // operations of every chain, bottom-up (= list order), back to back
+    const int nChains = static_cast<int>(chainLen.size());
+    std::vector<int> chainBegin(nChains + 1, 0), chainFlat(count), chainFill(nChains);
+    for (int c = 0; c < nChains; ++c) chainBegin[c + 1] = chainBegin[c] + chainLen[c];
+    for (int c = 0; c < nChains; ++c) chainFill[c] = chainBegin[c];
+    for (int o = 0; o < count; ++o) chainFlat[chainFill[out.opChain[o]]++] = o;
 
     // Subtree log-scaler slots: one per chain whose last buffer is re-read from memory by its
     // parent, or that is a root of the forest when there are several roots.
-    const int nChains = static_cast<int>(chainOps.size());
     std::vector<int> slotOfChain(nChains, -1);
     std::vector<int> roots;
     for (int o = 0; o < count; ++o) if (consumers[o] == 0) roots.push_back(o);
     const bool keep = keepSubtreeScalers && accumulate;
     if (keep) {
         // permanent slots, one per partials buffer; every chain end (and, below, every other operation) stores
-        for (int c = 0; c < nChains; ++c) slotOfChain[c] = ops[chainOps[c].back()].destinationPartials - tipCount;
+        for (int c = 0; c < nChains; ++c) slotOfChain[c] = ops[chainLast[c]].destinationPartials - tipCount;
         out.slotCount = partialsBufferCount;
         if (roots.size() > 1)
             for (int r : roots) out.rootSlots.push_back(slotOfChain[out.opChain[r]]);
     } else if (accumulate) {
         for (int c = 0; c < nChains; ++c) {
-            const int last = chainOps[c].back();
+            const int last = chainLast[c];
             const bool isRoot = consumers[last] == 0;
             if (readFromMemory[last] || (isRoot && roots.size() > 1)) slotOfChain[c] = out.slotCount++;
         }
@@ -164,40 +175,65 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
     }
 
     // Emit chains level by level.  Inside a level the chains are dealt, longest first, into the
-    // currently lightest of `groupCount` groups (LPT), and each group's operations are laid out
-    // contiguously: a thread block streams through one group.
+    // currently lightest of `groupCount` groups (LPT; the lowest-numbered one among equals), and each group's
+    // operations are laid out contiguously: a thread block streams through one group.
     int maxLevel = -1;
     for (int l : chainLevel) maxLevel = std::max(maxLevel, l);
     std::vector<int> chainNewId(nChains, -1);
     if (groupsPerLevel < 1) groupsPerLevel = 1;
+    // chains of every level, in chain order
+    std::vector<int> levelBegin(maxLevel + 2, 0), byLevel(nChains);
+    for (int c = 0; c < nChains; ++c) ++levelBegin[chainLevel[c] + 1];
+    for (int l = 0; l <= maxLevel; ++l) levelBegin[l + 1] += levelBegin[l];
+    {
+        std::vector<int> fill(levelBegin.begin(), levelBegin.end() - 1);
+        for (int c = 0; c < nChains; ++c) byLevel[fill[chainLevel[c]]++] = c;
+    }
+    out.ops.reserve(count);
+    out.chains.reserve(nChains);
+    std::vector<int> groupOf(nChains), groupBegin, order;
+    std::vector<std::pair<size_t, int>> heap;         // (load, group): min-heap
     for (int lvl = 0; lvl <= maxLevel; ++lvl) {
-        std::vector<int> ids;
-        for (int c = 0; c < nChains; ++c) if (chainLevel[c] == lvl) ids.push_back(c);
-        std::stable_sort(ids.begin(), ids.end(),
-                         [&](int x, int y) { return chainOps[x].size() > chainOps[y].size(); });
-        const int nGroups = std::max(1, std::min<int>(groupsPerLevel, static_cast<int>(ids.size())));
-        std::vector<std::vector<int>> bins(nGroups);
-        std::vector<size_t> load(nGroups, 0);
-        for (int c : ids) {
-            int best = 0;
-            for (int g = 1; g < nGroups; ++g) if (load[g] < load[best]) best = g;
-            bins[best].push_back(c);
-            load[best] += chainOps[c].size() + 1;     // +1: a chain start costs about one extra step
+        int* ids = byLevel.data() + levelBegin[lvl];
+        const int nIds = levelBegin[lvl + 1] - levelBegin[lvl];
+        std::stable_sort(ids, ids + nIds, [&](int x, int y) { return chainLen[x] > chainLen[y]; });
+        const int nGroups = std::max(1, std::min<int>(groupsPerLevel, nIds));
+        heap.clear();
+        for (int g = 0; g < nGroups; ++g) heap.emplace_back(size_t(0), g);
+        const auto heavier = [](const std::pair<size_t, int>& x, const std::pair<size_t, int>& y) { return x > y; };
+        // (a vector of (0, g) in increasing g already is a min-heap under `heavier`)
+        groupBegin.assign(nGroups + 1, 0);
+        for (int q = 0; q < nIds; ++q) {
+            std::pop_heap(heap.begin(), heap.end(), heavier);
+            std::pair<size_t, int>& lightest = heap.back();
+            groupOf[q] = lightest.second;
+            ++groupBegin[lightest.second + 1];
+            lightest.first += chainLen[ids[q]] + 1;     // +1: a chain start costs about one extra step
+            std::push_heap(heap.begin(), heap.end(), heavier);
         }
-        Level L{static_cast<int>(out.chains.size()), static_cast<int>(ids.size()), static_cast<int>(out.groups.size()), nGroups, 0};
+        for (int g = 0; g < nGroups; ++g) groupBegin[g + 1] += groupBegin[g];
+        order.resize(nIds);
+        {
+            std::vector<int> fill(groupBegin.begin(), groupBegin.end() - 1);
+            for (int q = 0; q < nIds; ++q) order[fill[groupOf[q]]++] = ids[q];       // stable: dealing order inside a group
+        }
+        Level L{static_cast<int>(out.chains.size()), nIds, static_cast<int>(out.groups.size()), nGroups, 0};
         for (int g = 0; g < nGroups; ++g) {
             Group G{static_cast<int>(out.ops.size()), 0};
-            for (int c : bins[g]) {
-                DevChain dc{static_cast<int>(out.ops.size()), static_cast<int>(chainOps[c].size()), slotOfChain[c], 0};
-                const int last = chainOps[c].back();
+            for (int q = groupBegin[g]; q < groupBegin[g + 1]; ++q) {
+                const int c = order[q];
+                const int* cops = chainFlat.data() + chainBegin[c];
+                const int clen = chainLen[c];
+                DevChain dc{static_cast<int>(out.ops.size()), clen, slotOfChain[c], 0};
+                const int last = chainLast[c];
                 if (accumulate && consumers[last] == 0 && roots.size() == 1) {
                     dc.flags |= CHAIN_ADD_TO_CUM;
                     out.scalerRows += 2;
                 }
                 if (dc.sOut >= 0) out.scalerRows += 2;
                 chainNewId[c] = static_cast<int>(out.chains.size());
-                for (size_t j = 0; j < chainOps[c].size(); ++j) {
-                    const int o = chainOps[c][j];
+                for (int j = 0; j < clen; ++j) {
+                    const int o = cops[j];
                     const BeagleOperation& op = ops[o];
                     // scaler that comes with an operand read from memory: its producer's chain slot, or (incremental
                     // plans) the permanent slot of an internal buffer that an earlier call computed
@@ -208,13 +244,13 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
                     };
                     int fl = op.destinationScaleWrite >= 0 ? OP_RESCALE : 0;
                     if (j == 0) fl |= OP_CHAIN_START;
-                    if (j + 1 == chainOps[c].size()) {
+                    if (j + 1 == clen) {
                         fl |= OP_CHAIN_END;
                         if (dc.flags & CHAIN_ADD_TO_CUM) fl |= OP_ADD_TO_CUM;
                     }
-                    int sOut = (j + 1 == chainOps[c].size()) ? dc.sOut : -1;
+                    int sOut = (j + 1 == clen) ? dc.sOut : -1;
                     const int dest = op.destinationPartials - tipCount;
-                    if (keep && j + 1 < chainOps[c].size()) {
+                    if (keep && j + 1 < clen) {
                         fl |= OP_STORE_S;
                         sOut = dest;
                         out.scalerRows += 2;
