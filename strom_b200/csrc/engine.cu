@@ -310,10 +310,15 @@ struct Engine {
     //     blocks (148 SMs x 6 blocks of 128 threads), measured best between 1 and 4 waves: more groups shorten
     //     the longest sequential run of a launch, fewer groups amortise the set-up;
     //   * many tiles (streaming sizes): enough blocks for >= 8 waves, so the last partial wave costs little.
-    int groupsPerLevel() const {
+    int groupsPerLevel(bool tipsLevel = false) const {
         const int tiles = Ppad / patternsPerBlock();
-        int slots = bigTiles() ? 148 * pruneBlocksPerSm(kVariantStream) : 148 * pruneBlocksPerSm(variant()) * 2;
+        const int perSm = pruneBlocksPerSm(variant(), tipsLevel && useTipsKernel);
+        // (tips-only launch of a small instance: ONE wave of its 8 blocks per SM; measured 100.0 / 124.1 us per rbcl738
+        // evaluation with 4 / 5 categories against 101.4 / 127.7 with the two waves of 6 the other launches use)
+        int slots = bigTiles() ? 148 * perSm : (tipsLevel && useTipsKernel) ? 148 * perSm : 148 * perSm * 2;
         if (const char* f = std::getenv("SB200_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
+        if (tipsLevel)
+            if (const char* f = std::getenv("SB200_TIPS_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
         if (tiles * 2 <= slots) return std::max(1, slots / tiles);
         return std::max(1, (8 * slots + tiles - 1) / tiles);
     }
@@ -367,7 +372,8 @@ struct Engine {
             std::rotate(parked.begin(), parked.begin() + 1, parked.end());
         }
         Schedule s;
-        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s, keepSubtreeScalers);
+        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s, keepSubtreeScalers,
+                               groupsPerLevel(true));
         if (rc != BEAGLE_SUCCESS) return rc;
         for (const DevOp& d : s.ops) {
             if (d.a >= 0 && d.a < nTips && !tipSet[d.a]) return BEAGLE_ERROR_OUT_OF_RANGE;

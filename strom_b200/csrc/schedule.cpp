@@ -31,7 +31,7 @@ static void assignTipTipTables(Schedule& out, int tipCount) {
 
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
                   int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out,
-                  bool keepSubtreeScalers) {
+                  bool keepSubtreeScalers, int groupsTipsLevel) {
     out = Schedule();
     const int nbuf = tipCount + partialsBufferCount;
     if (count < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -117,6 +117,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
     chainLevel.reserve(count);
     chainLen.reserve(count);
     chainLast.reserve(count);
+    std::vector<char> levelHasPartialOperand;        // per level: some operation reads an internal buffer from memory
     for (int o = 0; o < count; ++o) {
         classify(ops[o]);
         const int i1 = in1[o], i2 = in2[o];
@@ -144,6 +145,10 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             if (i1 >= 0) readFromMemory[i1] = 1;
             if (i2 >= 0) readFromMemory[i2] = 1;
         }
+        const int lv = out.opLevel[o];
+        if (lv >= static_cast<int>(levelHasPartialOperand.size())) levelHasPartialOperand.resize(lv + 1, 0);
+        if ((carry != 0 && ops[o].child1Partials >= tipCount) || (carry != 1 && ops[o].child2Partials >= tipCount))
+            levelHasPartialOperand[lv] = 1;
     }
     // operations of every chain, bottom-up (= list order), back to back
     const int nChains = static_cast<int>(chainLen.size());
@@ -197,7 +202,8 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
         int* ids = byLevel.data() + levelBegin[lvl];
         const int nIds = levelBegin[lvl + 1] - levelBegin[lvl];
         std::stable_sort(ids, ids + nIds, [&](int x, int y) { return chainLen[x] > chainLen[y]; });
-        const int nGroups = std::max(1, std::min<int>(groupsPerLevel, nIds));
+        const int wanted = (groupsTipsLevel > 0 && !levelHasPartialOperand[lvl]) ? groupsTipsLevel : groupsPerLevel;
+        const int nGroups = std::max(1, std::min<int>(wanted, nIds));
         heap.clear();
         for (int g = 0; g < nGroups; ++g) heap.emplace_back(size_t(0), g);
         const auto heavier = [](const std::pair<size_t, int>& x, const std::pair<size_t, int>& y) { return x > y; };

@@ -88,6 +88,8 @@ struct Schedule {
 };
 
 // Returns BEAGLE_SUCCESS or an error code (index out of range, unsupported scale-read).
+// `groupsTipsLevel` (0 = same as groupsPerLevel): the same for a tips-only launch, whose kernel variant has more
+// resident blocks per SM.
 // `groupsPerLevel`: how many thread-block groups a launch should be split into at most (the engine
 // derives it from the pattern-tile count so that every launch has enough blocks to fill the GPU).
 // `keepSubtreeScalers`: incremental evaluation.  Slot s = (buffer s + tipCount) permanently holds the total
@@ -97,6 +99,6 @@ struct Schedule {
 // the cumulative buffer still receives the whole tree's scaler.  The list must be a forest.
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
                   int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out,
-                  bool keepSubtreeScalers = false);
+                  bool keepSubtreeScalers = false, int groupsTipsLevel = 0);
 
 }  // namespace sb200
