@@ -66,6 +66,7 @@ struct Engine {
     int edgeCap = 0, edgeCount = 0;
     cudaEvent_t blockCopied = nullptr;
     bool blockInFlight = false;
+    bool blockDirty = true;               // host image newer than the device image
     // schedule
     Schedule sched;
     bool schedAccumulate = false;
@@ -217,7 +218,10 @@ struct Engine {
         CK(cudaStreamSynchronize(stream));
     }
 
+    // The host image of the parameter block is about to be modified: wait until a copy that is still reading it has
+    // finished, and remember that the device image is behind (the next kernel that reads it brings it up to date).
     void waitBlockFree() {
+        blockDirty = true;
         if (blockInFlight) {
             CK(cudaEventSynchronize(blockCopied));
             blockInFlight = false;
@@ -246,6 +250,7 @@ struct Engine {
         CK(cudaMemcpyAsync(dBlock, hBlock, blockBytes, cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(blockCopied, stream));
         blockInFlight = true;
+        blockDirty = false;
     }
 
     void launchMatrices() {
@@ -630,6 +635,7 @@ struct Engine {
         if (wIdx < 0 || wIdx >= nEigen || fIdx < 0 || fIdx >= nEigen) return BEAGLE_ERROR_OUT_OF_RANGE;
         if (cumIdx != BEAGLE_OP_NONE && (cumIdx < 0 || cumIdx >= nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
         lastParent = parent; lastChild = child; lastMatrix = matrix; lastWIdx = wIdx; lastFIdx = fIdx; lastRootCum = cumIdx;
+        if (blockDirty) uploadBlock();     // frequencies / category weights set since the last matrix update take effect now
         if (fp32) launchRootT<float>(parent, child, matrix, wIdx, fIdx, cumIdx, out);
         else launchRootT<double>(parent, child, matrix, wIdx, fIdx, cumIdx, out);
         return BEAGLE_SUCCESS;

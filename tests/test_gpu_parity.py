@@ -194,6 +194,31 @@ def test_repeat_calls_and_changed_parameters(engine, oracle):
     oracle.finalize(io)
 
 
+def test_frequencies_and_weights_set_after_the_matrix_update_reach_the_root_call(engine, oracle):
+    # BeagleLib's setters take effect at the next call that reads them: new state frequencies / category weights followed
+    # directly by beagleCalculateEdgeLogLikelihoods (no matrix update in between) must be the ones the root reduction uses
+    fx = random_problem(20, 333, 41)
+    m = named_model("gtr_g4")
+    new_freqs = np.array([0.1, 0.2, 0.3, 0.4])
+    new_probs = np.array([0.4, 0.3, 0.2, 0.1])
+    got = []
+    for api in (engine, oracle):
+        ll0, inst = full_eval(api, fx, m, keep=True)
+        assert api.beagleSetStateFrequencies(inst, 0, new_freqs.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert api.beagleSetCategoryWeights(inst, 0, new_probs.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        zero = np.zeros(1, dtype=np.int32)
+        par = np.array([int(fx["parent"])], dtype=np.int32)
+        out = np.zeros(1)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        assert api.beagleCalculateEdgeLogLikelihoods(inst, ip(par), ip(zero), ip(zero), None, None, ip(zero), ip(zero), ip(zero), 1,
+                                                     out.ctypes.data_as(C.POINTER(C.c_double)), None, None) == 0
+        got.append((ll0, float(out[0])))
+        api.finalize(inst)
+    assert rel_err(got[0][0], got[1][0]) < LOGL_RTOL
+    assert rel_err(got[0][1], got[1][1]) < LOGL_RTOL
+    assert abs(got[0][1] - got[0][0]) > 1.0            # the new numbers did change the result
+
+
 def test_operation_list_in_any_valid_order(engine, oracle):
     # the reference emits reverse level-order; any children-first order must give the same answer
     fx = random_problem(30, 50, 31)
