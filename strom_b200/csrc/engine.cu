@@ -79,8 +79,9 @@ struct Engine {
     long long* dTrace = nullptr;          // tuning builds: per-step clock samples (sb200DebugTrace)
     int* dTTOps = nullptr;                // op index of every tip x tip table
     void* dTT = nullptr;                  // tip x tip tables
-    size_t ttOpsCap = 0, ttCap = 0;
-    size_t opsCap = 0, groupsCap = 0, rootCap = 0;
+    // the four plan arrays above live in ONE allocation, uploaded by one copy: [ops][groups][root slots][table ops]
+    unsigned char* dPlan = nullptr;
+    size_t planCap = 0, ttCap = 0;
     // Plans that are not the active one but still sit in HBM, most recently used last.  An incremental MCMC
     // alternates between the full list (every change of the model) and short path lists: without these the
     // 700-operation plan would be rebuilt and uploaded again after every tree move.
@@ -93,7 +94,8 @@ struct Engine {
         int* dRootSlots = nullptr;
         int* dTTOps = nullptr;
         void* dTT = nullptr;
-        size_t ttOpsCap = 0, ttCap = 0, opsCap = 0, groupsCap = 0, rootCap = 0;
+        unsigned char* dPlan = nullptr;
+        size_t planCap = 0, ttCap = 0;
     };
     static constexpr size_t kParkedPlans = 3;
     std::vector<ParkedPlan> parked;
@@ -141,7 +143,7 @@ struct Engine {
         cudaFree(dTips); cudaFree(dPartials); cudaFree(dMats); cudaFree(dPatWeights);
         for (double* p : dScale) cudaFree(p);
         dScale.clear();
-        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dOps); cudaFree(dGroups); cudaFree(dRootSlots); cudaFree(dTTOps); cudaFree(dTT);
+        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dPlan); cudaFree(dTT);
         freeParkedPlans();
         cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut);
         if (hBlock) cudaFreeHost(hBlock);
@@ -154,7 +156,7 @@ struct Engine {
         evP0 = evP1 = nullptr;
         if (ownStream) cudaStreamDestroy(ownStream);
         dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr;
-        dBlock = nullptr; dOps = nullptr; dGroups = nullptr; dRootSlots = nullptr; dTTOps = nullptr; dTT = nullptr; dBlockSums = nullptr;
+        dBlock = nullptr; dPlan = nullptr; dOps = nullptr; dGroups = nullptr; dRootSlots = nullptr; dTTOps = nullptr; dTT = nullptr; dBlockSums = nullptr;
         dTicket = nullptr; dOut = nullptr; hBlock = nullptr; hSchedStage = nullptr; hOut = nullptr;
         blockCopied = nullptr; schedCopied = nullptr; ownStream = nullptr; stream = nullptr;
     }
@@ -290,15 +292,6 @@ struct Engine {
     }
 
     // ---- (b) ---------------------------------------------------------------------------
-    template <typename T>
-    static void ensureCap(T*& ptr, size_t& cap, size_t need) {
-        if (need <= cap) return;
-        cudaFree(ptr);
-        ptr = nullptr;
-        cap = need + need / 2 + 16;
-        CK(cudaMalloc(&ptr, sizeof(T) * cap));
-    }
-
     bool bigTiles() const {
         bool big = static_cast<long long>(P) * C >= (1LL << 18);
         if (const char* f = std::getenv("SB200_FORCE_R")) big = (f[0] == '2');   // tuning aid
@@ -339,11 +332,9 @@ struct Engine {
         std::swap(dRootSlots, p.dRootSlots);
         std::swap(dTTOps, p.dTTOps);
         std::swap(dTT, p.dTT);
-        std::swap(ttOpsCap, p.ttOpsCap);
+        std::swap(dPlan, p.dPlan);
+        std::swap(planCap, p.planCap);
         std::swap(ttCap, p.ttCap);
-        std::swap(opsCap, p.opsCap);
-        std::swap(groupsCap, p.groupsCap);
-        std::swap(rootCap, p.rootCap);
     }
     void forgetPlans() {
         schedValid = false;
@@ -351,7 +342,7 @@ struct Engine {
     }
     void freeParkedPlans() {
         for (ParkedPlan& p : parked) {
-            cudaFree(p.dOps); cudaFree(p.dGroups); cudaFree(p.dRootSlots); cudaFree(p.dTTOps); cudaFree(p.dTT);
+            cudaFree(p.dPlan); cudaFree(p.dTT);
         }
         parked.clear();
     }
@@ -410,13 +401,18 @@ struct Engine {
         // device arrays may be in use by kernels still queued on the stream: growing them frees
         // memory, so drain first (rare: only when the operation count grows)
         const size_t ttNeed = static_cast<size_t>(sched.tipTipCount) * ttStride(C) * realSize();
-        if (sched.ops.size() > opsCap || sched.groups.size() > groupsCap || sched.rootSlots.size() > rootCap ||
-            ttOps.size() > ttOpsCap || ttNeed > ttCap)
-            CK(cudaStreamSynchronize(stream));
-        ensureCap(dOps, opsCap, sched.ops.size());
-        ensureCap(dGroups, groupsCap, sched.groups.size());
-        ensureCap(dRootSlots, rootCap, sched.rootSlots.size());
-        ensureCap(dTTOps, ttOpsCap, ttOps.size());
+        if (total > planCap || ttNeed > ttCap) CK(cudaStreamSynchronize(stream));
+        if (total > planCap) {
+            cudaFree(dPlan);
+            dPlan = nullptr;
+            planCap = total + total / 2 + 256;
+            CK(cudaMalloc(&dPlan, planCap));
+        }
+        // (48-byte operation records first: every array stays aligned to its element size)
+        dOps = reinterpret_cast<DevOp*>(dPlan);
+        dGroups = reinterpret_cast<Group*>(dPlan + opsB);
+        dRootSlots = reinterpret_cast<int*>(dPlan + opsB + chB);
+        dTTOps = reinterpret_cast<int*>(dPlan + opsB + chB + rtB);
         if (ttNeed > ttCap) {
             cudaFree(dTT);
             dTT = nullptr;
@@ -428,10 +424,7 @@ struct Engine {
         if (chB) std::memcpy(st + opsB, sched.groups.data(), chB);
         if (rtB) std::memcpy(st + opsB + chB, sched.rootSlots.data(), rtB);
         if (ttB) std::memcpy(st + opsB + chB + rtB, ttOps.data(), ttB);
-        if (opsB) CK(cudaMemcpyAsync(dOps, st, opsB, cudaMemcpyHostToDevice, stream));
-        if (chB) CK(cudaMemcpyAsync(dGroups, st + opsB, chB, cudaMemcpyHostToDevice, stream));
-        if (rtB) CK(cudaMemcpyAsync(dRootSlots, st + opsB + chB, rtB, cudaMemcpyHostToDevice, stream));
-        if (ttB) CK(cudaMemcpyAsync(dTTOps, st + opsB + chB + rtB, ttB, cudaMemcpyHostToDevice, stream));
+        if (total) CK(cudaMemcpyAsync(dPlan, st, total, cudaMemcpyHostToDevice, stream));      // one copy for the whole plan
         CK(cudaEventRecord(schedCopied, stream));
         schedInFlight = true;
         const size_t needSlots = 2 * static_cast<size_t>(sched.slotCount) * Ppad;   // (log sum, product) planes

@@ -41,6 +41,9 @@ __host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
 // 100.6 us.)  TIPS = the launch holds only operations whose operands from memory are tips and that read no subtree
 // scalers (level 0 of every full evaluation: 37 % of the bytes of a 1000-taxon evaluation): the partials-operand
 // and scaler-operand code is compiled out, which frees registers for one more resident block per SM.
+#ifndef SB200_SMALL_BPS
+#define SB200_SMALL_BPS 6
+#endif
 #ifndef SB200_STREAM_BPS
 #define SB200_STREAM_BPS 3
 #endif
@@ -48,7 +51,7 @@ enum { kVariantSmall = 0, kVariantStream = 1 };
 __host__ __device__ constexpr int pruneR(int V) { return V == kVariantSmall ? 1 : 2; }
 __host__ __device__ constexpr int pruneThreads(int V) { return V == kVariantSmall ? 128 : 256; }
 __host__ __device__ constexpr int pruneBlocksPerSm(int V, bool tips = false) {
-    return V == kVariantSmall ? (tips ? 8 : 6) : (tips ? 4 : SB200_STREAM_BPS);
+    return V == kVariantSmall ? (tips ? 8 : SB200_SMALL_BPS) : (tips ? 4 : SB200_STREAM_BPS);
 }
 // Lane layout of the (pattern, category) kernels: a warp holds 32/C whole patterns, category fastest.  For
 // C = 1, 2, 4, 8 that is all 32 lanes; for 3, 5 (+I+G4), 6, 7 the last 32 - (32/C)*C lanes (2, 2, 2, 4) idle: they
