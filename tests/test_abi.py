@@ -34,6 +34,19 @@ def test_oracle_exports_the_same_13(oracle):
         assert hasattr(oracle.lib, name)
 
 
+def test_drop_in_host_library_binds_only_the_13_calls():
+    # libstrom_host_13call.so = the host classes compiled as the reference has them; everything it needs from the engine
+    # must be one of the 13 BeagleLib calls (no engine-level entry point), and it loads without a GPU
+    import subprocess
+    from strom_b200.build import build_host_13call
+    path = build_host_13call()
+    ctypes.CDLL(path)
+    out = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True).stdout
+    undefined = {l.split()[-1].split("@")[0] for l in out.splitlines() if l.strip()}
+    wanted = {n for n in undefined if n.startswith(("beagle", "sb200"))}
+    assert wanted and wanted <= set(SIGNATURES), wanted
+
+
 def test_version_string():
     lib = ctypes.CDLL(ENGINE_LIB)
     lib.sb200Version.restype = ctypes.c_char_p
