@@ -264,6 +264,7 @@ HOST_API int strom_incremental_walk(int data_handle, const char* newick, const d
 // lnPrior, TL, 6 exchangeabilities, 4 frequencies, alpha) with the cold chain's samples; returns the row count.
 // `flags`: 1 = every chain draws from its own random stream, 2 = chains are stepped side by side on host threads
 // (one heated chain per GPU; implies 1), 4 = incremental likelihood (only the changed path is re-evaluated).
+// 8 = lockstep: one host thread begins every update on all chains before finishing it on any (implies 1).
 // 0 = the reference's single shared stream, chains in turn, every node recomputed on every call.
 HOST_API int strom_mcmc_ex(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
                            unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
@@ -279,6 +280,7 @@ HOST_API int strom_mcmc_ex(int data_handle, const char* newick, unsigned seed, u
         opt.perChainStreams = (flags & 1u) != 0;
         opt.parallelChains = (flags & 2u) != 0;
         opt.incremental = (flags & 4u) != 0;
+        opt.lockstepChains = (flags & 8u) != 0;
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<TraceRow> tr = runMCMC(dataOf(data_handle), newick, opt);
         if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

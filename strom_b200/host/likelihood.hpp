@@ -41,6 +41,11 @@ class Likelihood {
     void useStoredData(bool using_data) { _using_data = using_data; }
     std::string availableResources();
     double calcLogLikelihood(Tree::SharedPtr t);
+    // The same evaluation in two halves: begin enqueues it on the GPU(s) and returns at once, finish waits for the
+    // scalar.  Between the two the caller may begin evaluations on OTHER Likelihood objects (the heated chains of an
+    // MC3 run sharing a GPU), which then overlap on the device.  calcLogLikelihood = begin + finish.
+    void beginLogLikelihood(Tree::SharedPtr t);
+    double finishLogLikelihood();
 
     void setData(Data::SharedPtr d);
     Data::SharedPtr getData() { return _data; }
@@ -95,6 +100,9 @@ class Likelihood {
     bool _single;
     bool _quiet;
     bool _using_data;
+    bool _pending = false, _pending_on_device = false;   // an evaluation was begun / its scalar is still on the device
+    double _pending_value = 0.0;
+    Tree::SharedPtr _pending_tree;
 
     // what the engine holds from the previous call (incremental evaluation)
     bool _incremental;
@@ -455,7 +463,19 @@ inline void Likelihood::calculatePartials() {
 }
 
 inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
-    if (!_using_data) return 0.0;
+    beginLogLikelihood(t);
+    return finishLogLikelihood();
+}
+
+inline void Likelihood::beginLogLikelihood(Tree::SharedPtr t) {
+    if (_pending) throw XStrom("beginLogLikelihood called twice without finishLogLikelihood");
+    // (_pending is set on every normal way out, never when an exception leaves this function)
+    _pending_on_device = false;
+    _pending_value = 0.0;
+    if (!_using_data) {
+        _pending = true;
+        return;
+    }
     if (t->_is_rooted) throw XStrom("can only compute likelihoods for unrooted trees currently");
     if (!_data) throw XStrom("must call setData before calcLogLikelihood");
 
@@ -465,7 +485,11 @@ inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
     assert(t->_root->_number == 0 && t->_root->_left_child == t->_preorder[0] && !t->_preorder[0]->_right_sib);
 
     if (_incremental) {
-        if (!defineChangedOperations(t)) return _held_log_likelihood;
+        if (!defineChangedOperations(t)) {
+            _pending_value = _held_log_likelihood;
+            _pending = true;
+            return;
+        }
         _remembered = false;                             // until this call has succeeded
     } else {
         defineOperations(t);
@@ -473,10 +497,9 @@ inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
     assert(_pmatrix_index.size() == _edge_lengths.size());
     int index_focal_child = t->_root->_number;           // the root tip
     int index_focal_parent = _incremental ? _buffer_of[t->_preorder[0] - &t->_nodes[0]] : t->_preorder[0]->_number;   // its only child
-    double log_likelihood = 0.0;
 
 #ifdef STROM_B200_ENGINE
-    // one fused call per shard (asynchronous), then the scalars are added in shard order
+    // one fused call per shard (asynchronous); finishLogLikelihood adds the scalars in shard order
     StromEvalArgs args;
     args.stateFrequencies = &_model->_state_freqs[0];
     args.eigenVectors = _model->_eigenvectors;
@@ -496,14 +519,12 @@ inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
         const int code = sb200EvalAsync(inst, &args, NULL);
         if (code != 0) throw XStrom("failed to evaluate the likelihood on the engine. " + errorText(code));
     }
-    for (int inst : _instances) {
-        double part = 0.0;
-        const int code = sb200Finish(inst, &part);
-        if (code != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(code));
-        log_likelihood += part;
-    }
-    if (_incremental) rememberState(t, log_likelihood);
+    _pending_on_device = true;
+    _pending_tree = t;
+    _pending = true;
 #else
+    // the reference's sequence of BeagleLib calls; the last one is synchronous, so the value is known here
+    double log_likelihood = 0.0;
     setModelRateMatrix();
     setDiscreteGammaShape();
     updateTransitionMatrices();
@@ -517,8 +538,33 @@ inline double Likelihood::calcLogLikelihood(Tree::SharedPtr t) {
         if (code != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(code));
         log_likelihood += part;
     }
+    _pending_value = log_likelihood;
+    _pending = true;
 #endif
-    return log_likelihood;
+}
+
+inline double Likelihood::finishLogLikelihood() {
+    if (!_pending) throw XStrom("finishLogLikelihood called without beginLogLikelihood");
+    _pending = false;
+#ifdef STROM_B200_ENGINE
+    if (_pending_on_device) {
+        _pending_on_device = false;
+        double log_likelihood = 0.0;
+        int failed = 0;
+        for (int inst : _instances) {                    // (every shard is drained even if one reports an error)
+            double part = 0.0;
+            const int code = sb200Finish(inst, &part);
+            if (code != 0 && failed == 0) failed = code;
+            log_likelihood += part;
+        }
+        Tree::SharedPtr t = _pending_tree;
+        _pending_tree.reset();
+        if (failed != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(failed));
+        if (_incremental) rememberState(t, log_likelihood);
+        _pending_value = log_likelihood;
+    }
+#endif
+    return _pending_value;
 }
 
 }  // namespace strom

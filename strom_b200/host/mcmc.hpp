@@ -77,16 +77,27 @@ class Updater {
     virtual double calcLogPrior() const = 0;
     double calcLogLikelihood() const { return _likelihood->calcLogLikelihood(_tree_manipulator->getTree()); }
 
-    virtual double update(double prev_lnL) {
+    double update(double prev_lnL) {
+        beginUpdate(prev_lnL);
+        return finishUpdate();
+    }
+    // The two halves of update: everything up to and including the ENQUEUE of the proposal's likelihood, and everything
+    // after its value is known.  A driver may begin the same update on every chain before finishing any, so that the
+    // chains' evaluations overlap on the GPU; each chain still consumes its random stream in the order update() does.
+    void beginUpdate(double prev_lnL) {
         pullCurrentStateFromModel();
-        const double prev_log_prior = calcLogPrior();
+        _prev_lnL = prev_lnL;
+        _prev_log_prior = calcLogPrior();
         proposeNewState();
         pushCurrentStateToModel();
-        double log_likelihood = calcLogLikelihood();
+        _likelihood->beginLogLikelihood(_tree_manipulator->getTree());
+    }
+    double finishUpdate() {
+        double log_likelihood = _likelihood->finishLogLikelihood();
         const double log_prior = calcLogPrior();
         bool accept = true;
         if (log_prior > logMinusInfinity()) {
-            const double log_diff = _log_hastings_ratio + _heating_power * ((log_likelihood + log_prior) - (prev_lnL + prev_log_prior));
+            const double log_diff = _log_hastings_ratio + _heating_power * ((log_likelihood + log_prior) - (_prev_lnL + _prev_log_prior));
             if (_lot->logUniform() > log_diff) accept = false;
         } else {
             accept = false;
@@ -95,7 +106,7 @@ class Updater {
         else {
             revert();
             pushCurrentStateToModel();
-            log_likelihood = prev_lnL;      // the reference does not recompute after a rejection (:216-218)
+            log_likelihood = _prev_lnL;     // the reference does not recompute after a rejection (:216-218)
         }
         tune(accept);
         _log_hastings_ratio = 0.0;
@@ -146,6 +157,7 @@ class Updater {
     bool _tuning = true;
     std::vector<double> _prior_parameters;
     double _heating_power = 1.0;
+    double _prev_lnL = 0.0, _prev_log_prior = 0.0;      // between beginUpdate and finishUpdate
 };
 
 // Updater is a friend of Tree and Node (like in the reference); derived classes reach them through it.
@@ -364,17 +376,22 @@ class Chain {
         _log_likelihood = calcLogLikelihood();
     }
     void nextStep(int) {
-        if (_likelihood->getModel()->getGammaNCateg() > 1) _log_likelihood = _shape_updater->update(_log_likelihood);
-        _log_likelihood = _statefreq_updater->update(_log_likelihood);
-        _log_likelihood = _exchangeability_updater->update(_log_likelihood);
-        _log_likelihood = _tree_updater->update(_log_likelihood);
-        _log_likelihood = _tree_length_updater->update(_log_likelihood);
+        for (Updater* u : stepOrder()) _log_likelihood = u->update(_log_likelihood);
     }
+    // nextStep one updater at a time, each in two halves (see Updater::beginUpdate): k = 0 .. numUpdates()-1
+    size_t numUpdates() const { return stepOrder().size(); }
+    void beginUpdate(size_t k) { stepOrder()[k]->beginUpdate(_log_likelihood); }
+    void finishUpdate(size_t k) { _log_likelihood = stepOrder()[k]->finishUpdate(); }
 
   private:
     std::vector<Updater*> all() const {
         return {_shape_updater.get(), _statefreq_updater.get(), _exchangeability_updater.get(), _tree_updater.get(),
                 _tree_length_updater.get()};
+    }
+    std::vector<Updater*> stepOrder() const {     // gamma shape (if C > 1), state freqs, exchangeabilities, tree, tree length
+        std::vector<Updater*> v = all();
+        if (_likelihood->getModel()->getGammaNCateg() <= 1) v.erase(v.begin());
+        return v;
     }
     Likelihood::SharedPtr _likelihood;
     TreeManip::SharedPtr _tree_manipulator;
@@ -407,6 +424,9 @@ struct McmcOptions {
     bool perChainStreams = false;            // chain c draws from its own stream, seeded from (seed, c); the swap
                                              // proposals keep the master stream.  Changes the trace (documented deviation).
     bool incremental = false;                // Likelihood::setIncremental: tree moves re-evaluate only the changed path (engine builds)
+    bool lockstepChains = false;             // ONE host thread: every update is begun (proposed, likelihood enqueued) on all
+                                             // chains before it is finished on any, so the chains' evaluations overlap on the
+                                             // GPU(s) they share (implies perChainStreams; same trace as perChainStreams alone)
     bool parallelChains = false;             // every chain runs on its own host thread (implies perChainStreams); only the two
                                              // chains of a swap proposal wait for each other.  Same trace as perChainStreams
                                              // alone, whatever the thread timing
@@ -429,7 +449,7 @@ struct SwapMeeting {
 // Strom::run's MCMC branch (src/strom.hpp:486-523): initChains, burn-in with tuning, sampling with swaps.
 inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& newick, const McmcOptions& opt) {
     Lot::SharedPtr lot(new Lot(opt.seed));
-    const bool ownStreams = opt.perChainStreams || opt.parallelChains;
+    const bool ownStreams = opt.perChainStreams || opt.parallelChains || opt.lockstepChains;
     std::vector<Chain> chains(opt.nchains);
     for (unsigned c = 0; c < opt.nchains; ++c) {
         Chain& ch = chains[c];
@@ -576,13 +596,25 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         std::stable_sort(trace.begin() + 1, trace.end(), [](const TraceRow& x, const TraceRow& y) { return x.iteration < y.iteration; });
         return trace;
     }
+    // all chains one iteration on: in turn, or (lockstep) update by update with the likelihoods of all chains in flight
+    auto stepAll = [&](unsigned it) {
+        if (!opt.lockstepChains || opt.nchains == 1) {
+            for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+            return;
+        }
+        const size_t nu = chains[0].numUpdates();          // (same model dimensions in every chain)
+        for (size_t k = 0; k < nu; ++k) {
+            for (Chain& ch : chains) ch.beginUpdate(k);
+            for (Chain& ch : chains) ch.finishUpdate(k);
+        }
+    };
     for (unsigned it = 1; it <= opt.burnin; ++it) {
-        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+        stepAll(it);
         swapChains();
     }
     for (Chain& ch : chains) ch.stopTuning();
     for (unsigned it = 1; it <= opt.niter; ++it) {
-        for (Chain& ch : chains) ch.nextStep(static_cast<int>(it));
+        stepAll(it);
         if (it % opt.samplefreq == 0) sample(it);
         swapChains();
     }

@@ -57,6 +57,25 @@ def test_parallel_chains_match_cpu_call_path_and_turn_order():
     assert rel.max() <= 1e-9
 
 
+@pytest.mark.parametrize("key,extra", [("rbcl10", {}), ("rbcl738", dict(niter=12, burnin=8, samplefreq=4)), ("rbcl10", dict(incremental=True))])
+def test_lockstep_chains_overlap_on_one_gpu_and_keep_the_trace(key, extra):
+    """One host thread begins every update on all chains (proposal, asynchronous engine call) before finishing it on
+    any: the chains' evaluations are in flight together on the GPU they share.  Bit for bit the trace of the chains
+    stepped in turn with a random stream each, and the CPU call path's to tolerance."""
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    kw = dict(niter=150, burnin=100, nchains=4, samplefreq=10, seed=99)
+    kw.update(extra)
+    lock, _ = _run(host(), key, lockstep_chains=True, **kw)
+    turn, _ = _run(host(), key, per_chain_streams=True, **kw)
+    assert np.array_equal(lock, turn)
+    if key != "rbcl738":
+        kw.pop("incremental", None)
+        cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), key, lockstep_chains=True, **kw)
+        rel = np.abs(lock - cpu) / np.maximum(np.abs(cpu), 1e-300)
+        assert rel.max() <= 1e-9
+
+
 @pytest.mark.parametrize("key,kw", [("rbcl10", dict(niter=300, burnin=200, nchains=2, samplefreq=10, seed=13579)),
                                     ("rbcL", dict(niter=150, burnin=100, nchains=1, samplefreq=5, seed=7))])
 def test_incremental_trace_matches_cpu_call_path(key, kw):

@@ -66,6 +66,22 @@ def test_parallel_chains_do_not_depend_on_thread_timing(hostlib):
     hostlib.data_free(h)
 
 
+def test_lockstep_chains_give_the_per_chain_stream_trace(hostlib):
+    """One host thread, every update begun (proposal made, likelihood enqueued) on all chains before it is finished on
+    any: each chain still consumes its own random stream in update() order, so the trace is bit for bit the one of
+    stepping the chains in turn with a stream per chain."""
+    fx, h = _data(hostlib, "rbcl10")
+    kw = dict(seed=2718, niter=120, burnin=60, nchains=4, samplefreq=10)
+    turn, _ = hostlib.mcmc(h, str(fx["newick"]), per_chain_streams=True, **kw)
+    lock, _ = hostlib.mcmc(h, str(fx["newick"]), lockstep_chains=True, **kw)
+    assert np.array_equal(turn, lock)
+    kw1 = dict(seed=5, niter=40, burnin=20, nchains=1, samplefreq=5, ncateg=1)      # one chain, no shape updater
+    a, _ = hostlib.mcmc(h, str(fx["newick"]), **kw1)
+    b, _ = hostlib.mcmc(h, str(fx["newick"]), lockstep_chains=True, **kw1)
+    assert a.shape == b.shape and np.all(np.isfinite(b))
+    hostlib.data_free(h)
+
+
 def test_incremental_walk_driver_on_cpu_call_path(hostlib):
     # on the CPU call path setIncremental has no effect: both evaluations list every node and agree exactly
     from helpers import PAUP_ALPHA, PAUP_PI, PAUP_R
