@@ -41,6 +41,8 @@ __host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
 // 100.6 us.)  TIPS = the launch holds only operations whose operands from memory are tips and that read no subtree
 // scalers (level 0 of every full evaluation: 37 % of the bytes of a 1000-taxon evaluation): the partials-operand
 // and scaler-operand code is compiled out, which frees registers for one more resident block per SM.
+// (tuning aids: resident blocks per SM of the general kernels; 7 / 8 for the small and 4 for the streaming variant were
+// measured and are slower, profiles/r1_negative_results.md)
 #ifndef SB200_SMALL_BPS
 #define SB200_SMALL_BPS 6
 #endif
