@@ -80,6 +80,17 @@ class HostAPI:
         n = nl.value
         return ops[:7 * (n - 2)].reshape(-1, 7).copy(), pidx[:2 * n - 3].copy(), elen[:2 * n - 3].copy(), par.value, out.value.decode()
 
+    def local_move_check(self, newick: str, seed: int = 1, lam: float = 0.5, nsteps: int = 200):
+        """Test hook for the LOCAL move: (take-backs that did not restore the tree, topology changes, worst consistency
+        error of path scaling / Hastings ratio / tree length, final newick)."""
+        self.lib.strom_local_move_check.argtypes = [C.c_char_p, C.c_uint, C.c_double, C.c_int, _IP, _DP, C.c_char_p, C.c_int,
+                                                    C.c_char_p, C.c_int]
+        ch, worst = C.c_int(), C.c_double()
+        out = C.create_string_buffer(1 << 20)
+        bad = self._check(self.lib.strom_local_move_check(newick.encode(), seed, lam, nsteps, C.byref(ch), C.byref(worst), out, 1 << 20,
+                                                          self._err, 1024))
+        return bad, ch.value, worst.value, out.value.decode()
+
     # ---- Model -----------------------------------------------------------------------------
     def model_numbers(self, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0) -> dict:
         f = np.ascontiguousarray(freqs, dtype=np.float64)

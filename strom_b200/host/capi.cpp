@@ -260,6 +260,43 @@ HOST_API int strom_incremental_walk(int data_handle, const char* newick, const d
     } catch (const std::exception& e) { return fail(e, err, errlen); }
 }
 
+// TEST HOOK for the LOCAL move (mcmc.hpp::TreeUpdater): `nsteps` proposals on the tree; each is first made and taken back
+// (the tree must then be exactly the one before: same shape, same 17-digit edge lengths) and then made again and kept.  Returns the number of take-backs that did
+// NOT restore the tree; counts topology-changing proposals, and the largest |focal path after / (m * before) - 1| and
+// |log Hastings - (3 log m - E log(Pac m + 1 - Pac))| with m recovered from the path lengths.
+HOST_API int strom_local_move_check(const char* newick, unsigned seed, double lambda, int nsteps, int* topology_changes,
+                                    double* worst_scale_error, char* final_newick, int final_len, char* err, int errlen) {
+    try {
+        TreeManip::SharedPtr tm(new TreeManip);
+        tm->buildFromNewick(newick, false, false);
+        TreeUpdater up;
+        up.setTreeManip(tm);
+        up.setLot(Lot::SharedPtr(new Lot(seed)));
+        up.setLambda(lambda);
+        int bad = 0, changes = 0;
+        double worst = 0.0;
+        for (int i = 0; i < nsteps; ++i) {
+            const std::string before = up.canonicalForTest();
+            const Lot probe(seed * 7919u + static_cast<unsigned>(i));   // (copied twice: the same six deviates for both proposals)
+            up.setLot(Lot::SharedPtr(new Lot(probe)));
+            up.proposeForTest(true);
+            if (up.canonicalForTest() != before) ++bad;
+            up.setLot(Lot::SharedPtr(new Lot(probe)));          // the same deviates again: the same proposal, kept this time
+            const double TL = tm->calcTreeLength();
+            const double E = static_cast<double>(tm->getTree()->numNodes() - 1);
+            double f0 = 0.0, f1 = 0.0, lh = 0.0;
+            if (up.proposeForTest(false, &f0, &f1, &lh)) ++changes;
+            const double m = f1 / f0, Pac = f0 / TL;
+            worst = std::max(worst, std::fabs(lh - (3.0 * std::log(m) - E * std::log(Pac * m + 1.0 - Pac))));
+            worst = std::max(worst, std::fabs(tm->calcTreeLength() - (TL - f0 + f1)) / TL);
+        }
+        if (topology_changes) *topology_changes = changes;
+        if (worst_scale_error) *worst_scale_error = worst;
+        if (final_newick && final_len > 0) std::snprintf(final_newick, static_cast<size_t>(final_len), "%s", tm->makeNewick(6).c_str());
+        return bad;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
 // Strom::run's MCMC branch on the host classes.  Fills `rows` (max_rows x 15 doubles: iteration, lnL,
 // lnPrior, TL, 6 exchangeabilities, 4 frequencies, alpha) with the cold chain's samples; returns the row count.
 // `flags`: 1 = every chain draws from its own random stream, 2 = chains are stepped side by side on host threads

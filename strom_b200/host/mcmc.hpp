@@ -13,11 +13,12 @@
 // Deliberate differences (these classes are host control flow, outside the rebuilt hot path):
 //   * Lot draws from std::mt19937 / std::gamma_distribution (Boost's generators are not available), so the
 //     streams differ from a real strom build; parity is defined between the two back-ends of THIS code;
-//   * TreeUpdater is a reduced LOCAL move: one random internal edge, its three-edge focal path scaled by
-//     m = exp(lambda (u - 0.5)), and with probability 1/2 an NNI swap across that edge -- it exercises
-//     topology + edge-length changes through the engine but is not the reference's 8-case proposal.
+//   * TreeUpdater is the reference's LOCAL move (same proposal distribution, Hastings ratio and order of the six
+//     uniform deviates), written over the focal path instead of as eight cases.
 #pragma once
+#include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -265,7 +266,18 @@ class TreeLengthUpdater : public Updater {
     double _prev_point = 0.0, _curr_point = 0.0;
 };
 
-// Reduced LOCAL move (see the header comment).
+// The LOCAL move of Larget & Simon with the reference's conventions (src/tree_updater.hpp:110-437), restated over the
+// three-edge focal path instead of as eight drawn cases:
+//
+//        a     b        x = a random internal edge's upper node, a and b its children, y its parent, d its sibling,
+//         \   /         c = y's parent.  The focal path is  T - x - y - (c or d):  its TOP edge belongs to T = a or b
+//          x     d      (1/2 each), its MIDDLE edge to x, its BOTTOM edge to y (towards c) or to d (1/2 each).
+//           \   /       All three are multiplied by m = exp(lambda (u - 1/2)); then one of the two nodes hanging off the
+//            y          path -- the other child of x (1/2) or the other neighbour of y (1/2) -- is cut off and re-attached
+//            |          at a uniform point p of the rescaled path.  If it passes the far junction the topology changes
+//            c          (an NNI: nniNodeSwap with d), otherwise only the three lengths change.
+//
+// Six uniform deviates per proposal, in the reference's order: edge, T, bottom, m, p, which node.
 class TreeUpdater : public Updater {
   public:
     TreeUpdater() { _name = "Tree Topol. and Edge Lengths"; }
@@ -275,41 +287,91 @@ class TreeUpdater : public Updater {
         return -log_num_topologies + calcEdgeLengthPrior();
     }
     void pullCurrentStateFromModel() override {}
+    // (test hook) one proposal outside the MH step, taken back at once if asked; returns true if it changed the topology
+    bool proposeForTest(bool take_back, double* focal_before = nullptr, double* focal_after = nullptr, double* log_hastings = nullptr) {
+        proposeNewState();
+        if (focal_before) *focal_before = _len_top + _len_mid + _len_bot;
+        if (focal_after) *focal_after = _top->getEdgeLength() + _mid->getEdgeLength() + _bot->getEdgeLength();
+        if (log_hastings) *log_hastings = _log_hastings_ratio;
+        const bool changed = _swapped;
+        if (take_back) revert();
+        _log_hastings_ratio = 0.0;
+        return changed;
+    }
+
+    // (test hook) the tree with the children of every node in a fixed order and 17-digit edge lengths: an NNI that is
+    // swapped back leaves the same tree but, like the reference's nniNodeSwap, not always the same order of siblings
+    std::string canonicalForTest() const { return canonical(_tree_manipulator->getTree()->_root); }
 
   private:
+    static std::string canonical(const Node* nd) {
+        char len[40];
+        // (a zero length read from a tree file becomes the 1e-12 floor once a node setter touches it -- reference
+        // src/node.hpp:76-79, also on the way back -- so lengths are compared at the floor)
+        std::snprintf(len, sizeof(len), ":%.17g", std::max(nd->_edge_length, Node::smallestEdgeLength()));
+        if (!nd->_left_child) return std::to_string(nd->_number) + len;
+        std::vector<std::string> kids;
+        for (const Node* c = nd->_left_child; c; c = c->_right_sib) kids.push_back(canonical(c));
+        std::sort(kids.begin(), kids.end());
+        std::string out = "(";
+        for (size_t i = 0; i < kids.size(); ++i) out += (i ? "," : "") + kids[i];
+        return out + ")" + len;      // (internal node numbers are renumbered by every refreshPreorder: left out)
+    }
     void pushCurrentStateToModel() const override {}
     void proposeNewState() override {
-        _x = _tree_manipulator->randomInternalEdge(_lot->uniform());
-        _a = _x->getLeftChild();
-        _b = _a->getRightSib();
-        Node* y = _x->getParent();
-        _d = (_x == y->getLeftChild()) ? _x->getRightSib() : y->getLeftChild();
-        _top = (_lot->uniform() < 0.5) ? _a : _b;
-        _bottom = _d;
+        Node* x = _tree_manipulator->randomInternalEdge(_lot->uniform());
+        Node* a = x->getLeftChild();
+        Node* b = a->getRightSib();
+        Node* y = x->getParent();
+        _d = (x == y->getLeftChild()) ? x->getRightSib() : y->getLeftChild();
+        const bool a_on_path = _lot->uniform() < 0.5;
+        const bool c_on_path = _lot->uniform() < 0.5;
+        _top = a_on_path ? a : b;                         // owners of the three focal edges
+        _mid = x;
+        _bot = c_on_path ? y : _d;
+        Node* other_top = a_on_path ? b : a;
+        // an NNI exchanges d with the child of x that is NOT on the path when the path runs on to c, and with the one
+        // that IS when it ends at d (c cannot move: it is towards the root)
+        _partner = c_on_path ? other_top : _top;
         _len_top = _top->getEdgeLength();
-        _len_mid = _x->getEdgeLength();
-        _len_bot = _bottom->getEdgeLength();
+        _len_mid = _mid->getEdgeLength();
+        _len_bot = _bot->getEdgeLength();
+
         const double m = std::exp(_lambda * (_lot->uniform() - 0.5));
         const double num_edges = static_cast<double>(_tree_manipulator->getTree()->numNodes() - 1);
         const double TL = _tree_manipulator->calcTreeLength();
         const double Pac = (_len_top + _len_mid + _len_bot) / TL;
-        _log_hastings_ratio = 3.0 * std::log(m) - num_edges * std::log(Pac * m + 1.0 - Pac);
-        _top->setEdgeLength(m * _len_top);
-        _x->setEdgeLength(m * _len_mid);
-        _bottom->setEdgeLength(m * _len_bot);
-        _swapped = _lot->uniform() < 0.5;
-        if (_swapped) {
-            _moved = (_top == _a) ? _b : _a;        // the child of x that is NOT on the focal path changes places with d
-            _tree_manipulator->nniNodeSwap(_moved, _d);
+        _log_hastings_ratio = 3.0 * std::log(m) - num_edges * std::log(Pac * m + 1.0 - Pac);   // GammaDir parameterisation (:160-164)
+
+        const double t = m * _len_top, mid = m * _len_mid, bt = m * _len_bot, L = t + mid + bt;
+        double p = _lot->uniform() * L;                   // new attachment point, measured from the top end
+        const double eps = Node::smallestEdgeLength();
+        if (p <= eps) p = eps;
+        else if (L - p <= eps) p = L - eps;
+
+        const bool move_upper = _lot->uniform() < 0.5;    // the node hanging at the top/middle junction, else the middle/bottom one
+        double nt, nm, nb;
+        if (move_upper) {
+            _swapped = p > t + mid;                       // it slid past the lower junction
+            if (_swapped) { nt = t + mid; nm = p - nt; nb = L - p; }
+            else { nt = p; nm = t + mid - p; nb = bt; }
+        } else {
+            _swapped = p < t;                             // it slid past the upper junction
+            if (_swapped) { nt = p; nm = t - p; nb = mid + bt; }
+            else { nt = t; nm = p - t; nb = L - p; }
         }
+        if (_swapped) _tree_manipulator->nniNodeSwap(_partner, _d);
+        _top->setEdgeLength(nt);
+        _mid->setEdgeLength(nm);
+        _bot->setEdgeLength(nb);
     }
     void revert() override {
-        if (_swapped) _tree_manipulator->nniNodeSwap(_d, _moved);   // d now hangs from x, moved from y: swap back
+        if (_swapped) _tree_manipulator->nniNodeSwap(_d, _partner);   // d now hangs from x, the partner from y: swap back
         _top->setEdgeLength(_len_top);
-        _x->setEdgeLength(_len_mid);
-        _bottom->setEdgeLength(_len_bot);
+        _mid->setEdgeLength(_len_mid);
+        _bot->setEdgeLength(_len_bot);
     }
-    Node *_x = nullptr, *_a = nullptr, *_b = nullptr, *_d = nullptr, *_top = nullptr, *_bottom = nullptr, *_moved = nullptr;
+    Node *_d = nullptr, *_top = nullptr, *_mid = nullptr, *_bot = nullptr, *_partner = nullptr;
     double _len_top = 0, _len_mid = 0, _len_bot = 0;
     bool _swapped = false;
 };

@@ -66,6 +66,22 @@ def test_parallel_chains_do_not_depend_on_thread_timing(hostlib):
     hostlib.data_free(h)
 
 
+@pytest.mark.parametrize("key,lam", [("rbcl10", 0.5), ("rbcL", 2.0), ("rbcl738", 0.2)])
+def test_local_move_takes_back_exactly_and_is_consistent(hostlib, key, lam):
+    """TreeUpdater = the reference's LOCAL move (src/tree_updater.hpp:110-437) restated over the focal path: a proposal
+    that is taken back leaves the tree printing exactly as before (17 digits), kept proposals change topology about a
+    third of the time, the tree length changes by exactly the focal path's change, and the Hastings ratio is the
+    reference's 3 log m - E log(Pac m + 1 - Pac) for the m the path was scaled by."""
+    fx = load_golden(key)
+    bad, changes, worst, final = hostlib.local_move_check(str(fx["newick"]), seed=11, lam=lam, nsteps=400)
+    assert bad == 0
+    assert 60 < changes < 220                     # P(topology change) = 1/3 for a uniform attachment point on three similar edges
+    assert worst < 1e-9
+    ops0 = hostlib.tree_ops(str(fx["newick"]))[0]
+    ops1 = hostlib.tree_ops(final)[0]
+    assert ops0.shape == ops1.shape and not np.array_equal(ops0, ops1)      # still a binary tree on the same taxa, a different one
+
+
 def test_lockstep_chains_give_the_per_chain_stream_trace(hostlib):
     """One host thread, every update begun (proposal made, likelihood enqueued) on all chains before it is finished on
     any: each chain still consumes its own random stream in update() order, so the trace is bit for bit the one of
