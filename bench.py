@@ -277,12 +277,16 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
     llf, sec = H.loglik(hd, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
     H.data_free(hd)
     # ... and the same facade compiled as the reference has it: 13 BeagleLib calls per evaluation, library = this engine
-    from strom_b200.build import HOST_13CALL_LIB
-    from strom_b200.host import HostAPI
-    H13 = HostAPI(HOST_13CALL_LIB)
-    hd13 = H13.data_from_codes(data.astype(np.int32)[:, cols], compress=True)
-    llf13, sec13 = H13.loglik(hd13, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
-    H13.data_free(hd13)
+    llf13, sec13 = None, None
+    try:
+        from strom_b200.build import build_host_13call
+        from strom_b200.host import HostAPI
+        H13 = HostAPI(build_host_13call())
+        hd13 = H13.data_from_codes(data.astype(np.int32)[:, cols], compress=True)
+        llf13, sec13 = H13.loglik(hd13, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
+        H13.data_free(hd13)
+    except Exception as e:                       # (this leg is extra evidence: the headline numbers do not depend on it)
+        sys.stderr.write("13-call facade leg skipped: %r\n" % (e,))
     # CPU oracle on the same problem
     tips = data
     one, _, llc = time_oracle(tips, fx["counts"], model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]),
@@ -299,7 +303,7 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
         "evals_per_sec_device": 1000.0 / dev_ms, "evals_per_sec_e2e_13call_python_ctypes": 1000.0 / e2e_ms,
         "evals_per_sec_e2e_fused_call": 1000.0 / fused_ms,
         "evals_per_sec_e2e_cpp_facade": 1.0 / sec, "logL_cpp_facade": llf,
-        "evals_per_sec_e2e_cpp_facade_13_calls": 1.0 / sec13, "logL_cpp_facade_13_calls": llf13,
+        "evals_per_sec_e2e_cpp_facade_13_calls": (1.0 / sec13) if sec13 else None, "logL_cpp_facade_13_calls": llf13,
         "evals_per_sec_device_4_concurrent_chains": 1000.0 / conc_ms,
         "partial_updates_per_sec_device": upd * 1000.0 / dev_ms,
         "cpu_evals_per_sec_1thread": one, "cpu_evals_per_sec_all_threads": allc, "cpu_threads": thr,
