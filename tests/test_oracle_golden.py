@@ -113,3 +113,52 @@ def test_missing_data_equals_marginalisation(oracle):
     assert rel_err(lik([0, 4, 2, 3]), total) < 1e-12
     total0 = sum(lik([s, 1, 2, 3]) for s in range(4))
     assert rel_err(lik([7, 1, 2, 3]), total0) < 1e-12      # any code >= 4 is missing, also at the root tip
+
+
+@pytest.mark.parametrize("ntaxa,seed,model", [(4, 3, "gtr_g4"), (6, 5, "gtr_g4"), (7, 8, "gtr_i_g4"), (5, 9, "jc")])
+def test_brute_force_enumeration_of_internal_states(oracle, ntaxa, seed, model):
+    """Independent of pruning, rescaling and the eigen path: the site likelihood as the plain sum over every assignment of
+    states to the internal nodes, with P(t r_k) = expm(Q t r_k) from the rate matrix itself (scipy), against the oracle's
+    logL on a random tree with missing data."""
+    from scipy.linalg import expm
+    from helpers import JC, PAUP_PI, PAUP_R, random_problem
+    fx = random_problem(ntaxa, 12, seed, missing_frac=0.1, mean_edge=0.2)
+    m = named_model(model)
+    pi, r = (np.array(JC[0]), JC[1]) if model == "jc" else (np.array(PAUP_PI), PAUP_R)
+    R = np.zeros((4, 4))
+    R[np.triu_indices(4, 1)] = r
+    R = R + R.T
+    Q = R * pi[None, :]
+    np.fill_diagonal(Q, 0.0)
+    np.fill_diagonal(Q, -Q.sum(axis=1))
+    Q /= -(pi * np.diag(Q)).sum()                                   # mean rate 1 (reference src/model.hpp:228-229)
+    length_of = {int(mi): float(t) for mi, t in zip(fx["pmatrix_index"], fx["edge_lengths"])}
+    P = {mi: [expm(Q * t * rk) for rk in m["rates"]] for mi, t in length_of.items()}
+    children = {int(op[0]): (int(op[3]), int(op[5])) for op in fx["ops"]}
+    internal = sorted(children)
+    top, data = int(fx["parent"]), fx["data"]
+    total = 0.0
+    for p in range(data.shape[1]):
+        site = 0.0
+        for k, wk in enumerate(m["probs"]):
+            acc = 0.0
+            for code in range(4 ** len(internal)):
+                state = {nd: (code >> (2 * i)) & 3 for i, nd in enumerate(internal)}
+                term = pi[state[top]]
+                s0 = int(data[0, p])
+                term *= P[0][k][state[top], s0] if s0 < 4 else 1.0       # the root tip hangs from `top` by matrix 0
+                for nd, kids in children.items():
+                    for c in kids:
+                        if c in state:
+                            term *= P[c][k][state[nd], state[c]]
+                        else:
+                            s = int(data[c, p])
+                            term *= P[c][k][state[nd], s] if s < 4 else 1.0
+                acc += term
+            site += wk * acc
+        total += fx["counts"][p] * np.log(site)
+    inst = oracle.create(ntaxa, data.shape[1], len(m["rates"]))
+    oracle.set_data(inst, data.astype(np.int32), fx["counts"])
+    ll = oracle.calc_log_likelihood(inst, m, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], top, 0)
+    oracle.finalize(inst)
+    assert rel_err(ll, total) < 1e-11
