@@ -162,3 +162,55 @@ def test_brute_force_enumeration_of_internal_states(oracle, ntaxa, seed, model):
     ll = oracle.calc_log_likelihood(inst, m, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], top, 0)
     oracle.finalize(inst)
     assert rel_err(ll, total) < 1e-11
+
+
+def test_high_precision_replay_of_rbcl10(oracle):
+    """How far the oracle's double arithmetic is from the exact value: the whole rbcl10 GTR+G4 evaluation repeated with
+    40-digit mpmath numbers (P = expm(Q t r_k), plain pruning without rescaling -- nothing underflows at 40 digits)."""
+    mp = pytest.importorskip("mpmath")
+    from helpers import PAUP_PI, PAUP_R
+    mp.mp.dps = 40
+    fx = load_golden("rbcl10")
+    m = named_model("gtr_g4")
+    pi = [mp.mpf(repr(float(x))) for x in PAUP_PI]
+    R = mp.zeros(4)
+    it = iter(PAUP_R)
+    for i in range(4):
+        for j in range(i + 1, 4):
+            R[i, j] = R[j, i] = mp.mpf(repr(float(next(it))))
+    Q = mp.zeros(4)
+    for i in range(4):
+        for j in range(4):
+            if i != j:
+                Q[i, j] = R[i, j] * pi[j]
+        Q[i, i] = -sum(Q[i, j] for j in range(4) if j != i)
+    scale = -sum(pi[i] * Q[i, i] for i in range(4))
+    Q = Q / scale
+    rates = [mp.mpf(repr(float(x))) for x in m["rates"]]
+    probs = [mp.mpf(repr(float(x))) for x in m["probs"]]
+    P = {}
+    for mi, t in zip(fx["pmatrix_index"], fx["edge_lengths"]):
+        P[int(mi)] = [mp.expm(Q * (mp.mpf(repr(float(t))) * rk)) for rk in rates]
+    data, counts, n = fx["data"], fx["counts"], fx["data"].shape[0]
+    total = mp.mpf(0)
+    for p in range(data.shape[1]):
+        site = mp.mpf(0)
+        for k in range(4):
+            part = {}
+            def cond(c, i):                       # conditional likelihood of the subtree below node c given state i above its edge
+                if c < n:
+                    s = int(data[c, p])
+                    return P[c][k][i, s] if s < 4 else mp.mpf(1)
+                return sum(P[c][k][i, j] * part[c][j] for j in range(4))
+            for op in fx["ops"]:
+                d, c1, c2 = int(op[0]), int(op[3]), int(op[5])
+                part[d] = [cond(c1, i) * cond(c2, i) for i in range(4)]
+            top, s0 = int(fx["parent"]), int(data[0, p])
+            site += probs[k] * sum(pi[i] * part[top][i] * (P[0][k][i, s0] if s0 < 4 else 1) for i in range(4))
+        total += mp.mpf(repr(float(counts[p]))) * mp.log(site)
+    inst = oracle.create(n, data.shape[1], 4)
+    oracle.set_data(inst, data.astype(np.int32), counts)
+    ll = oracle.calc_log_likelihood(inst, m, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
+    oracle.finalize(inst)
+    assert abs((mp.mpf(repr(ll)) - total) / total) < mp.mpf("1e-14")                          # observed 1.9e-16
+    assert abs((mp.mpf(repr(float(fx["lnL_gtr_g4"]))) - total) / total) < mp.mpf("1e-14")     # the committed fixture value too
