@@ -126,6 +126,15 @@ STROM_API int sb200DebugSchedule(const BeagleOperation* operations, int operatio
 STROM_API int sb200DebugPlan(const BeagleOperation* operations, int operationCount, int tipCount, int partialsBufferCount,
                              int keepSubtreeScalers, int* planOut);
 
+/* Host-only, needs no GPU: the launches the planner makes of an operation list.  groupsPerLaunch / groupsPerTipsLaunch: the
+ * most thread-block groups a launch (a tips-only launch; 0 = the same) is split into.  launchesOut receives, per launch (at
+ * most maxLaunches), 5 ints: {chains, groups, tips-only (every operand read from memory is a tip and no subtree scaler is
+ * read: the launch may run the kernel variant without partials-operand code), operations, operations of the longest group}.
+ * Returns the number of launches (>= 0) or a negative error code. */
+STROM_API int sb200DebugPlanLaunches(const BeagleOperation* operations, int operationCount, int tipCount, int partialsBufferCount,
+                                     int keepSubtreeScalers, int groupsPerLaunch, int groupsPerTipsLaunch, int maxLaunches,
+                                     int* launchesOut);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1152,6 +1152,33 @@ extern "C" int sb200DebugSchedule(const BeagleOperation* operations, int operati
     }
 }
 
+// Host-only inspection of the launches of a plan (see include/strom_b200.h).
+extern "C" int sb200DebugPlanLaunches(const BeagleOperation* operations, int operationCount, int tipCount, int partialsBufferCount,
+                                      int keepSubtreeScalers, int groupsPerLaunch, int groupsPerTipsLaunch, int maxLaunches,
+                                      int* launchesOut) {
+    try {
+        Schedule s;
+        int rc = buildSchedule(operations, operationCount, tipCount, partialsBufferCount, 1 << 30, 1 << 30, true, groupsPerLaunch, s,
+                               keepSubtreeScalers != 0, groupsPerTipsLaunch);
+        if (rc) return rc;
+        const int n = static_cast<int>(s.levels.size());
+        if (launchesOut)
+            for (int l = 0; l < n && l < maxLaunches; ++l) {
+                const Level& L = s.levels[l];
+                int ops = 0, longest = 0;
+                for (int g = L.groupStart; g < L.groupStart + L.groupCount; ++g) {
+                    ops += s.groups[g].opEnd - s.groups[g].opStart;
+                    longest = std::max(longest, s.groups[g].opEnd - s.groups[g].opStart);
+                }
+                int* r = launchesOut + 5 * l;
+                r[0] = L.chainCount; r[1] = L.groupCount; r[2] = L.tipsOnly; r[3] = ops; r[4] = longest;
+            }
+        return n;
+    } catch (...) {
+        return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
+    }
+}
+
 // Host-only inspection of a plan (see include/strom_b200.h).
 extern "C" int sb200DebugPlan(const BeagleOperation* operations, int operationCount, int tipCount, int partialsBufferCount,
                               int keepSubtreeScalers, int* planOut) {

@@ -49,6 +49,7 @@ class EngineAPI:
             "sb200LastTraffic": (C.c_int, [C.c_int, _DP, _DP]),
             "sb200DebugSchedule": (C.c_int, [_IP, C.c_int, C.c_int, C.c_int, _IP, _IP, _IP]),
             "sb200DebugPlan": (C.c_int, [_IP, C.c_int, C.c_int, C.c_int, C.c_int, _IP]),
+            "sb200DebugPlanLaunches": (C.c_int, [_IP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _IP]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -79,6 +80,16 @@ class EngineAPI:
         r = self.sb200DebugPlan(ops.ctypes.data_as(_IP), n, ntaxa, ntaxa - 2, int(keep_subtree_scalers), out.ctypes.data_as(_IP))
         if r < 0:
             raise beagle.BeagleError("plan", r)
+        return out[:r]
+
+    def plan_launches(self, ops: np.ndarray, ntaxa: int, groups: int = 4, groups_tips: int = 0, keep_subtree_scalers: bool = False):
+        """Launches of a plan [n][5] = chains, groups, tips-only, operations, operations of the longest group -- host-only."""
+        ops = np.ascontiguousarray(ops, dtype=np.int32)
+        out = np.zeros((64, 5), dtype=np.int32)
+        r = self.sb200DebugPlanLaunches(ops.ctypes.data_as(_IP), ops.size // 7, ntaxa, ntaxa - 2, int(keep_subtree_scalers), groups,
+                                        groups_tips, 64, out.ctypes.data_as(_IP))
+        if r < 0:
+            raise beagle.BeagleError("plan launches", r)
         return out[:r]
 
     def schedule(self, ops: np.ndarray, ntaxa: int):

@@ -161,3 +161,21 @@ def test_incremental_plans_keep_every_subtree_scaler(E, key):
                 outside += operand not in dirty
     assert outside >= 1 or len(sub) == 1                               # siblings along the path come with their old scalers
     assert len({r[7] for r in path.tolist()}) == 1                     # one path = one chain = one launch
+
+
+def test_launches_tips_only_flag_and_group_counts(E):
+    """Level 0 of a full evaluation reads nothing but tips (its launch may run the kernel variant without partials-operand
+    code, with its own group count); an incremental list whose operands are partials of earlier calls does not qualify."""
+    fx = load_golden("rbcl738")
+    L = E.plan_launches(fx["ops"], 738, groups=44, groups_tips=29)
+    assert L.shape == (6, 5) and L[:, 3].sum() == 736
+    assert L[0, 2] == 1 and not L[1:, 2].any()                      # only the first launch is tips-only
+    assert L[0, 1] == 29 and L[1, 1] == 44                          # the tips-only launch got its own group count
+    assert L[-1, 0] == 1 and L[-1, 1] == 1 and L[-1, 4] == L[-1, 3]   # one chain at the top: one group, run in sequence
+    assert np.all(L[:, 4] * L[:, 1] >= L[:, 3])                     # the longest group bounds the mean
+    same = E.plan_launches(fx["ops"], 738, groups=44)               # 0 = the same count for every launch
+    assert same[0, 1] == 44 and same[0, 2] == 1
+    tail = E.plan_launches(fx["ops"][-20:], 738, groups=44, groups_tips=29, keep_subtree_scalers=True)
+    assert tail[:, 3].sum() == 20 and not tail[:, 2].any()          # operands are buffers an earlier call left: not tips-only
+    small = random_problem(4, 3, 1)
+    assert E.plan_launches(small["ops"], 4, groups=8, groups_tips=8)[0, 2] == 1
