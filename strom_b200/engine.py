@@ -40,6 +40,7 @@ class EngineAPI:
             "sb200Eval": (C.c_int, [C.c_int, C.POINTER(StromEvalArgs), _DP]),
             "sb200EvalAsync": (C.c_int, [C.c_int, C.POINTER(StromEvalArgs), C.c_void_p]),
             "sb200ReplayAsync": (C.c_int, [C.c_int, C.c_void_p]),
+            "sb200Finish": (C.c_int, [C.c_int, _DP]),
             "sb200Synchronize": (C.c_int, [C.c_int]),
             "sb200SetProfiling": (C.c_int, [C.c_int, C.c_int]),
             "sb200SetSubtreeScalers": (C.c_int, [C.c_int, C.c_int]),
@@ -186,6 +187,17 @@ class ShardedLikelihood:
                 sum_over_ranks(self.out)
 
     def calc_log_likelihood(self, args: EvalArgs) -> float:
+        if not self.distributed:
+            # one GPU: the root kernel writes the scalar into pinned host memory and sb200Finish polls for it
+            self.E.check(self.E.sb200EvalAsync(self.inst, C.byref(args.c), None), "evaluate")
+            res = C.c_double()
+            code = self.E.sb200Finish(self.inst, C.byref(res))
+            if code not in (0, -8):
+                self.E.check(code, "finish")
+            v = res.value
+            if code == -8 or v != v:
+                raise beagle.BeagleError("failed to calculate edge logLikelihoods", -8)
+            return v
         self.eval_async(args)
         with self.torch.cuda.stream(self.stream):
             v = float(self.out.item())      # device -> host read of the scalar, synchronises the stream
