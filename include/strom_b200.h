@@ -37,6 +37,8 @@ typedef struct {
     int           rootParentBuffer;      /* preorder[0] number, src/likelihood.hpp:427 */
     int           rootChildBuffer;       /* root tip number,   src/likelihood.hpp:424 */
     int           rootMatrix;            /* = rootChildBuffer, src/likelihood.hpp:433 */
+    int           categoryCount;         /* entries of categoryRates / categoryWeights; must equal the instance's
+                                            category count (0 = not checked) */
 } StromEvalArgs;
 
 /* Library version string (static storage). */
@@ -52,6 +54,10 @@ STROM_API int sb200SetStream(int instance, void* cudaStream);
 /* Tip upload from 1-byte codes (0..3, anything else = missing). */
 STROM_API int sb200SetTipStatesU8(int instance, int tipIndex, const unsigned char* inStates);
 
+/* All tips in one call: inStates[tip * patternCount + pattern], 1-byte codes as above (one strided copy instead of a copy
+ * per taxon; reference path: the per-taxon loop of Likelihood::setTipStates, src/likelihood.hpp:228-247). */
+STROM_API int sb200SetAllTipStatesU8(int instance, const unsigned char* inStates);
+
 /* One whole Likelihood::calcLogLikelihood: parameter upload, all transition matrices, all
  * partials with rescaling, root-edge reduction, scalar back on the host.  Synchronises. */
 STROM_API int sb200Eval(int instance, const StromEvalArgs* args, double* outLogLikelihood);
@@ -60,6 +66,18 @@ STROM_API int sb200Eval(int instance, const StromEvalArgs* args, double* outLogL
  * pattern slice is left in *deviceOut (a device pointer to one double) in stream order, or, when
  * deviceOut is NULL, in the instance's own result slot, to be collected with sb200Finish. */
 STROM_API int sb200EvalAsync(int instance, const StromEvalArgs* args, double* deviceOut);
+
+/* The evaluations of `count` instances (the heated chains of a Metropolis-coupled run: same data, one tree and model
+ * each; the reference steps them one after the other, src/strom.hpp:316-324) as ONE set of kernel launches: the
+ * instance is a grid dimension of every kernel, so eight 738-taxon trees cost the launches -- and fill the GPU far
+ * better than -- one.  args[i] belongs to instances[i]; all instances must live on one device and share the category
+ * count and the precision; they run on the first instance's stream from this call on.  Lists longer than 8 are cut
+ * into sets of 8.  Every scalar is collected with sb200Finish(instances[i]).  Nothing is enqueued if any argument is
+ * rejected. */
+STROM_API int sb200EvalBatchAsync(int count, const int* instances, const StromEvalArgs* args);
+
+/* sb200ReplayAsync for a set of instances that were last evaluated together by sb200EvalBatchAsync. */
+STROM_API int sb200ReplayBatchAsync(int count, const int* instances);
 
 /* Waits for the instance's stream and returns the scalar of the last evaluation that used the
  * instance's own result slot (BEAGLE_ERROR_FLOATING_POINT if it is NaN).  With one instance per

@@ -6,6 +6,10 @@
 //
 // Replaces what strom reaches through Likelihood (reference src/likelihood.hpp:165-448) and
 // Model::setBeagle* (reference src/model.hpp:315-354).
+//
+// Every kernel takes a *set* of up to kMaxBatch instances (same device, stream, category count and precision): the
+// single-instance entry points launch a set of one, sb200EvalBatchAsync launches the heated chains of an MC3 run as
+// ONE set of launches (reference loop: src/strom.hpp:316-324 steps the chains one after the other).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -23,6 +27,15 @@
 #include "kernels.cuh"
 #include "schedule.hpp"
 
+#if defined(SB200_NVTX)
+#include <nvtx3/nvToolsExt.h>
+#define SB200_RANGE_PUSH(name) nvtxRangePushA(name)
+#define SB200_RANGE_POP() nvtxRangePop()
+#else
+#define SB200_RANGE_PUSH(name) ((void)0)
+#define SB200_RANGE_POP() ((void)0)
+#endif
+
 namespace sb200 {
 
 struct CudaFail {
@@ -34,8 +47,52 @@ struct CudaFail {
         if (_e != cudaSuccess) throw CudaFail{_e};   \
     } while (0)
 
-static int g_device = 0;
+// Device new instances are created on when beagleCreateInstance gets no resource list: the calling thread's choice
+// (sb200SetDevice), else the last choice any thread made.
+static std::atomic<int> g_defaultDevice{0};
+static thread_local int t_device = -1;
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards (a torch process, or
+// a host thread driving several shards, must not find its current device changed by a library call).
+struct DeviceGuard {
+    int previous = -1;
+    bool switched = false;
+    cudaError_t enter(int device) {
+        cudaError_t e = cudaGetDevice(&previous);
+        if (e != cudaSuccess) return e;
+        if (previous != device) {
+            e = cudaSetDevice(device);
+            if (e != cudaSuccess) return e;
+            switched = true;
+        }
+        return cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(previous);
+    }
+};
+
+static int envInt(const char* name, int fallback) {
+    const char* f = std::getenv(name);
+    return f ? std::atoi(f) : fallback;
+}
+
+// Launch on `stream`; `dependent`: the kernel follows another kernel of the same evaluation and may be scheduled
+// while that one drains (programmatic dependent launch, see pdlWait in kernels.cuh).
+template <typename... KArgs, typename... Args>
+static void launchK(cudaStream_t stream, bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
 
 // Host image of the per-call parameter block; mirrored 1:1 in HBM and refreshed by ONE copy.
 struct ParamBlockHeader {
@@ -44,11 +101,13 @@ struct ParamBlockHeader {
 
 struct Engine {
     int device = 0;
+    int smCount = 148;
     bool fp32 = false;
     int nTips = 0, nPartials = 0, nCompact = 0, P = 0, nEigen = 0, nMat = 0, C = 0, nScale = 0;
     int Ppad = 0;                         // pattern axis padded to whole thread-block tiles in every buffer
     long long tipStride = 0;
     cudaStream_t ownStream = nullptr, stream = nullptr;
+    int batchHint = 1;                    // evaluations launched side by side with this one (shapes the plan's launches)
 
     // HBM
     uint8_t* dTips = nullptr;
@@ -71,11 +130,13 @@ struct Engine {
     Schedule sched;
     bool schedAccumulate = false;
     bool schedValid = false;
+    int schedHint = 1;                    // batchHint the active plan's launches were shaped for
     std::vector<BeagleOperation> schedOps;
     DevOp* dOps = nullptr;
     Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
     bool keepSubtreeScalers = false;      // incremental evaluation: permanent per-buffer subtree scaler slots (sb200SetSubtreeScalers)
+    std::vector<char> slotValid;          // ... and which of them hold the scaler of the partials now in the buffer
     long long* dTrace = nullptr;          // tuning builds: per-step clock samples (sb200DebugTrace)
     int* dTTOps = nullptr;                // op index of every tip x tip table
     void* dTT = nullptr;                  // tip x tip tables
@@ -88,6 +149,7 @@ struct Engine {
     struct ParkedPlan {
         Schedule sched;
         bool accumulate = false, valid = false;
+        int hint = 1;
         std::vector<BeagleOperation> key;
         DevOp* dOps = nullptr;
         Group* dGroups = nullptr;
@@ -116,6 +178,7 @@ struct Engine {
     // last root-edge call (for replay)
     int lastParent = -1, lastChild = -1, lastMatrix = -1, lastWIdx = 0, lastFIdx = 0, lastRootCum = BEAGLE_OP_NONE;
     std::vector<char> tipSet;
+    std::vector<unsigned char> tipStage;  // host staging of one tip row (int32 -> byte codes)
     long launches = 0;
     double algBytes = 0, schedBytes = 0;
     // optional CUDA-event timing of the pruning launches (bench.py's roofline leg)
@@ -124,6 +187,10 @@ struct Engine {
     double partialsMsSum = 0;
     long partialsCalls = 0;
     bool evPending = false;
+    bool usePdl = true;
+    bool useTipsKernel = true;            // SB200_TIPS_KERNEL=0 (tuning aid): tips-only launches run the general kernel
+    int forceVariant = -1;                // SB200_VARIANT (tuning aid): every launch of a small instance runs this thread shape
+    int wideMinWarps = 0;                 // small instances: a level runs the wide thread shape from this many warps up
 
     size_t realSize() const { return fp32 ? 4 : 8; }
     ParamBlockHeader* hHeader() { return reinterpret_cast<ParamBlockHeader*>(hBlock); }
@@ -138,14 +205,16 @@ struct Engine {
     ~Engine() { destroy(); }
 
     void destroy() {
-        cudaSetDevice(device);
-        if (ownStream) cudaStreamSynchronize(ownStream);
+        DeviceGuard guard;
+        guard.enter(device);
+        if (stream) cudaStreamSynchronize(stream);
+        if (ownStream && ownStream != stream) cudaStreamSynchronize(ownStream);
         cudaFree(dTips); cudaFree(dPartials); cudaFree(dMats); cudaFree(dPatWeights);
         for (double* p : dScale) cudaFree(p);
         dScale.clear();
         cudaFree(dSlots); cudaFree(dBlock); cudaFree(dPlan); cudaFree(dTT);
         freeParkedPlans();
-        cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut);
+        cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut); cudaFree(dTrace);
         if (hBlock) cudaFreeHost(hBlock);
         if (hSchedStage) cudaFreeHost(hSchedStage);
         if (hOut) cudaFreeHost(hOut);
@@ -155,7 +224,7 @@ struct Engine {
         if (evP1) cudaEventDestroy(evP1);
         evP0 = evP1 = nullptr;
         if (ownStream) cudaStreamDestroy(ownStream);
-        dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr;
+        dTips = nullptr; dPartials = nullptr; dMats = nullptr; dPatWeights = nullptr; dSlots = nullptr; dTrace = nullptr;
         dBlock = nullptr; dPlan = nullptr; dOps = nullptr; dGroups = nullptr; dRootSlots = nullptr; dTTOps = nullptr; dTT = nullptr; dBlockSums = nullptr;
         dTicket = nullptr; dOut = nullptr; hBlock = nullptr; hSchedStage = nullptr; hOut = nullptr;
         blockCopied = nullptr; schedCopied = nullptr; ownStream = nullptr; stream = nullptr;
@@ -173,17 +242,15 @@ struct Engine {
 
     void init() {
         CK(cudaSetDevice(device));
+        CK(cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
         stream = ownStream;
         CK(cudaEventCreateWithFlags(&blockCopied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
-        // pattern axis padded to a whole number of thread-block tiles of every kernel that walks it
-        // (pruning tile = patternsPerBlock(), root kernel = rootPatternsPerBlock(C)) and of 16, the granularity of
-        // the bulk L2 prefetches of 1-byte tip rows
+        // pattern axis padded to a whole number of thread-block tiles of every kernel that walks it: the pruning shapes
+        // hold 32 .. 256 patterns per block, the root kernel 128
         {
-            auto lcm = [](int a, int b) { int x = a, y = b; while (y) { const int t = x % y; x = y; y = t; } return a / x * b; };
-            int unit = lcm(lcm(patternsPerBlock(), rootPatternsPerBlock(C)), 16);
-            if ((C & (C - 1)) == 0) unit = std::max(unit, 128);
+            const int unit = bigTiles() ? 256 : 128;
             Ppad = ((P + unit - 1) / unit) * unit;
         }
         tipStride = Ppad;
@@ -207,16 +274,18 @@ struct Engine {
         std::memset(hBlock, 0, blockBytes);
         CK(cudaMalloc(&dBlock, blockBytes));
         for (int k = 0; k < kMaxCategories; ++k) hHeader()->rates[k] = 1.0;
-        rootBlocks = Ppad / rootPatternsPerBlock(C);
+        rootBlocks = Ppad / rootPatternsPerBlock();
         CK(cudaMalloc(&dBlockSums, sizeof(double) * rootBlocks));
         CK(cudaMalloc(&dTicket, sizeof(unsigned int)));
         CK(cudaMemsetAsync(dTicket, 0, sizeof(unsigned int), stream));
         CK(cudaMalloc(&dOut, sizeof(double)));
         CK(cudaMallocHost(&hOut, 2 * sizeof(double)));
         std::memset(hOut, 0, 2 * sizeof(double));
-        if (const char* f = std::getenv("SB200_POLL")) pollResult = std::atoi(f) != 0;
-        if (const char* f = std::getenv("SB200_PDL")) usePdl = std::atoi(f) != 0;   // tuning aid: plain stream order
-        if (const char* f = std::getenv("SB200_TIPS_KERNEL")) useTipsKernel = std::atoi(f) != 0;
+        pollResult = envInt("SB200_POLL", 1) != 0;
+        usePdl = envInt("SB200_PDL", 1) != 0;                 // tuning aid: plain stream order
+        useTipsKernel = envInt("SB200_TIPS_KERNEL", 1) != 0;
+        forceVariant = envInt("SB200_VARIANT", -1);
+        wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 8 * smCount);
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -255,23 +324,27 @@ struct Engine {
         blockDirty = false;
     }
 
-    void launchMatrices() {
-        if (edgeCount == 0) return;
-        const long long threads = static_cast<long long>(edgeCount) * C * 16;
-        const int blocks = static_cast<int>((threads + 255) / 256);
-        if (fp32)
-            transition_matrices_kernel<float><<<blocks, 256, 0, stream>>>(dModel(0), dRates(), dMidx(), dElen(), edgeCount, C,
-                                                                          static_cast<float*>(dMats));
-        else
-            transition_matrices_kernel<double><<<blocks, 256, 0, stream>>>(dModel(0), dRates(), dMidx(), dElen(), edgeCount,
-                                                                           C, static_cast<double*>(dMats));
-        CK(cudaGetLastError());
-        ++launches;
+    MatJob matJob() const {
+        MatJob j;
+        j.model = dModel(0);
+        j.rates = dRates();
+        j.matrixIndex = dMidx();
+        j.edgeLength = dElen();
+        j.mats = dMats;
+        j.count = edgeCount;
+        j.pad = 0;
+        return j;
+    }
+
+    int checkEdges(const int* idx, int count) const {
+        for (int u = 0; u < count; ++u)
+            if (idx[u] < 0 || idx[u] >= nMat) return BEAGLE_ERROR_OUT_OF_RANGE;
+        return BEAGLE_SUCCESS;
     }
 
     int setEdges(const int* idx, const double* len, int count) {
-        for (int u = 0; u < count; ++u)
-            if (idx[u] < 0 || idx[u] >= nMat) return BEAGLE_ERROR_OUT_OF_RANGE;
+        const int rc = checkEdges(idx, count);
+        if (rc) return rc;
         waitBlockFree();
         if (count > edgeCap) {
             // grow the block, preserving the model part
@@ -292,33 +365,45 @@ struct Engine {
     }
 
     // ---- (b) ---------------------------------------------------------------------------
+    // Streaming sizes run one thread shape (kVarStream) on every launch; small instances choose per launch between the
+    // wide and the narrow shape (kernels.cuh).  Fixed at creation: it sets the pattern padding.
     bool bigTiles() const {
         bool big = static_cast<long long>(P) * C >= (1LL << 18);
-        if (const char* f = std::getenv("SB200_FORCE_R")) big = (f[0] == '2');   // tuning aid
+        if (const char* f = std::getenv("SB200_FORCE_BIG")) big = (f[0] == '1');   // tuning aid
         return big;
     }
-    // which prune_chains_kernel variant this instance runs (fixed at creation: it sets the pattern padding)
-    int variant() const { return bigTiles() ? kVariantStream : kVariantSmall; }
-    int patternsPerBlock() const {
-        return prunePatternsPerBlock(C, variant());
-    }
-    // How many groups a launch's chains are dealt into.  Every block pays a fixed set-up (operation words,
-    // first images and operands: two dependent trips to L2/HBM), so as few groups as possible -- but:
-    //   * few pattern tiles (latency-bound sizes such as rbcl738, 40 tiles of 32 patterns): TWO waves of resident
-    //     blocks (148 SMs x 6 blocks of 128 threads), measured best between 1 and 4 waves: more groups shorten
-    //     the longest sequential run of a launch, fewer groups amortise the set-up;
+    int blocksPerSm(int V, bool tips) const { return varBlocksPerSm(C, V, tips && useTipsKernel, static_cast<int>(realSize())); }
+
+    // Shape and group count of a launch.  Every block pays a fixed set-up (operation words, first images and
+    // operands: dependent trips to L2/HBM), so as few groups as possible -- but:
+    //   * few pattern tiles (latency-bound sizes such as rbcl738): TWO waves of resident blocks, measured best
+    //     between 1 and 4 waves: more groups shorten the longest sequential run of a launch, fewer groups amortise
+    //     the set-up; a launch with enough independent chains to give every warp scheduler several warps runs the
+    //     wide shape (all categories in one thread: a quarter of the instructions per pattern x category), the
+    //     others, at the top of the tree, the narrow shape (a warp per category: a shorter step);
     //   * many tiles (streaming sizes): enough blocks for >= 8 waves, so the last partial wave costs little.
-    int groupsPerLevel(bool tipsLevel = false) const {
-        const int tiles = Ppad / patternsPerBlock();
-        const int perSm = pruneBlocksPerSm(variant(), tipsLevel && useTipsKernel);
-        // (tips-only launch of a small instance: ONE wave of its 8 blocks per SM; measured 100.0 / 124.1 us per rbcl738
-        // evaluation with 4 / 5 categories against 101.4 / 127.7 with the two waves of 6 the other launches use)
-        int slots = bigTiles() ? 148 * perSm : (tipsLevel && useTipsKernel) ? 148 * perSm : 148 * perSm * 2;
-        if (const char* f = std::getenv("SB200_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
-        if (tipsLevel)
-            if (const char* f = std::getenv("SB200_TIPS_SLOTS")) slots = std::max(1, std::atoi(f));   // tuning aid
-        if (tiles * 2 <= slots) return std::max(1, slots / tiles);
-        return std::max(1, (8 * slots + tiles - 1) / tiles);
+    LevelChoice chooseLevel(int chainCount, bool tipsCandidate) const {
+        LevelChoice c;
+        if (bigTiles()) {
+            c.variant = kVarStream;
+            const int tiles = Ppad / varPatterns(C, kVarStream, static_cast<int>(realSize()));
+            int slots = smCount * blocksPerSm(kVarStream, tipsCandidate);
+            slots = envInt("SB200_SLOTS", slots);
+            if (tiles * 2 <= slots) c.groups = std::max(1, slots / tiles);
+            else c.groups = std::max(1, (8 * slots + tiles - 1) / tiles);
+            return c;
+        }
+        const int K = std::max(1, batchHint);
+        const long wideWarps = static_cast<long>(K) * chainCount * (Ppad / varPatterns(C, kVarWide, static_cast<int>(realSize()))) * varWarps(C, kVarWide, static_cast<int>(realSize()));
+        c.variant = wideWarps >= wideMinWarps ? kVarWide : kVarNarrow;
+        if (forceVariant == kVarWide || forceVariant == kVarNarrow) c.variant = forceVariant;
+        const int tiles = Ppad / varPatterns(C, c.variant, static_cast<int>(realSize()));
+        const int waves = tipsCandidate && useTipsKernel ? 1 : 2;
+        int slots = smCount * blocksPerSm(c.variant, tipsCandidate) * waves;
+        slots = envInt("SB200_SLOTS", slots);
+        if (tipsCandidate) slots = envInt("SB200_TIPS_SLOTS", slots);
+        c.groups = std::max(1, slots / (tiles * K));
+        return c;
     }
 
     // active plan <-> parked plan (pointer and vector swaps only)
@@ -326,6 +411,7 @@ struct Engine {
         std::swap(sched, p.sched);
         std::swap(schedAccumulate, p.accumulate);
         std::swap(schedValid, p.valid);
+        std::swap(schedHint, p.hint);
         std::swap(schedOps, p.key);
         std::swap(dOps, p.dOps);
         std::swap(dGroups, p.dGroups);
@@ -346,39 +432,56 @@ struct Engine {
         }
         parked.clear();
     }
+    void setBatchHint(int k) { batchHint = k < 1 ? 1 : k; }   // (plans are keyed by it: the launch shapes of small instances depend on it)
+
+    // Incremental plans (keepSubtreeScalers): an internal operand that the list does not produce brings the subtree
+    // scaler an earlier call left in its permanent slot -- which must exist.
+    std::vector<char> producedScratch;
+    int checkSlots(const Schedule& s) {
+        if (slotValid.size() != static_cast<size_t>(nPartials)) slotValid.assign(nPartials, 0);
+        producedScratch.assign(nPartials, 0);
+        for (const DevOp& d : s.ops) producedScratch[d.dest] = 1;
+        for (const DevOp& d : s.ops) {
+            if (d.sa >= 0 && d.a >= nTips && !producedScratch[d.a - nTips] && !slotValid[d.a - nTips]) return BEAGLE_ERROR_OUT_OF_RANGE;
+            if (d.sb >= 0 && d.b >= nTips && !producedScratch[d.b - nTips] && !slotValid[d.b - nTips]) return BEAGLE_ERROR_OUT_OF_RANGE;
+        }
+        return BEAGLE_SUCCESS;
+    }
 
     int prepareSchedule(const BeagleOperation* ops, int count, bool accumulate) {
         // same operation list as last call (the common case: 4 of strom's 5 updaters do not touch the
         // topology): reuse the plan that is already in HBM.  One memcmp of 28 bytes per operation.
-        auto same = [&](bool valid, bool acc, const std::vector<BeagleOperation>& key) {
-            return valid && acc == accumulate && static_cast<int>(key.size()) == count &&
+        const int hint = bigTiles() ? 1 : batchHint;
+        auto same = [&](bool valid, bool acc, int h, const std::vector<BeagleOperation>& key) {
+            return valid && acc == accumulate && h == hint && static_cast<int>(key.size()) == count &&
                    (count == 0 || std::memcmp(key.data(), ops, sizeof(BeagleOperation) * count) == 0);
         };
-        if (same(schedValid, schedAccumulate, schedOps)) return BEAGLE_SUCCESS;
+        if (same(schedValid, schedAccumulate, schedHint, schedOps)) return BEAGLE_SUCCESS;
         for (size_t i = parked.size(); i-- > 0;)
-            if (same(parked[i].valid, parked[i].accumulate, parked[i].key)) {
+            if (same(parked[i].valid, parked[i].accumulate, parked[i].hint, parked[i].key)) {
                 swapPlan(parked[i]);                                   // the plan that was active takes its place ...
                 std::rotate(parked.begin() + i, parked.begin() + i + 1, parked.end());   // ... as the most recently used
                 return BEAGLE_SUCCESS;
             }
+        Schedule s;
+        const LevelPolicy policy = [this](int chains, bool tips) { return chooseLevel(chains, tips); };
+        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, policy, s, keepSubtreeScalers);
+        if (rc != BEAGLE_SUCCESS) return rc;
+        for (const DevOp& d : s.ops) {
+            if (d.a >= 0 && d.a < nTips && !tipSet[d.a]) return BEAGLE_ERROR_OUT_OF_RANGE;
+            if (d.b < nTips && !tipSet[d.b]) return BEAGLE_ERROR_OUT_OF_RANGE;
+        }
         // miss: park the active plan; the new one is built over the least recently used set of device arrays
         if (schedValid) {
             if (parked.size() < kParkedPlans) parked.insert(parked.begin(), ParkedPlan());
             swapPlan(parked.front());
             std::rotate(parked.begin(), parked.begin() + 1, parked.end());
         }
-        Schedule s;
-        int rc = buildSchedule(ops, count, nTips, nPartials, nMat, nScale, accumulate, groupsPerLevel(), s, keepSubtreeScalers,
-                               groupsPerLevel(true));
-        if (rc != BEAGLE_SUCCESS) return rc;
-        for (const DevOp& d : s.ops) {
-            if (d.a >= 0 && d.a < nTips && !tipSet[d.a]) return BEAGLE_ERROR_OUT_OF_RANGE;
-            if (d.b < nTips && !tipSet[d.b]) return BEAGLE_ERROR_OUT_OF_RANGE;
-        }
         schedValid = false;
         sched = std::move(s);
         schedOps.assign(ops, ops + count);
         schedAccumulate = accumulate;
+        schedHint = hint;
         // stage + upload
         const size_t opsB = sizeof(DevOp) * sched.ops.size();
         const size_t chB = sizeof(Group) * sched.groups.size();
@@ -400,7 +503,7 @@ struct Engine {
         }
         // device arrays may be in use by kernels still queued on the stream: growing them frees
         // memory, so drain first (rare: only when the operation count grows)
-        const size_t ttNeed = static_cast<size_t>(sched.tipTipCount) * ttStride(C) * realSize();
+        const size_t ttNeed = static_cast<size_t>(sched.tipTipCount) * ttStride(C, static_cast<int>(realSize())) * realSize();
         if (total > planCap || ttNeed > ttCap) CK(cudaStreamSynchronize(stream));
         if (total > planCap) {
             cudaFree(dPlan);
@@ -434,6 +537,7 @@ struct Engine {
             dSlots = nullptr;
             slotCapacity = needSlots + needSlots / 4;
             CK(cudaMalloc(&dSlots, sizeof(double) * slotCapacity));
+            slotValid.assign(slotValid.size(), 0);
         }
         // traffic bookkeeping (bytes), SURVEY.md section 8(d)
         const double b = static_cast<double>(realSize());
@@ -446,39 +550,9 @@ struct Engine {
         return BEAGLE_SUCCESS;
     }
 
-    // Launch on the engine's stream; `dependent`: the kernel follows another kernel of the same evaluation and may
-    // be scheduled while that one drains (programmatic dependent launch, see pdlWait in kernels.cuh).
-    bool usePdl = true;
-    bool useTipsKernel = true;            // SB200_TIPS_KERNEL=0 (tuning aid): tips-only launches run the general kernel
-    template <typename... KArgs, typename... Args>
-    void launchK(void (*kernel)(KArgs...), dim3 grid, dim3 block, bool dependent, Args&&... args) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid;
-        cfg.blockDim = block;
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = (dependent && usePdl) ? 1 : 0;
-        CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
-    }
-
-    template <typename real, int CC, int V, bool TIPS>
-    void launchLevelV(const PruneArgs<real>& a, const Level& L, int cumMode) {
-        dim3 grid(Ppad / prunePatternsPerBlock(CC, V), L.groupCount);
-        launchK(prune_chains_kernel<real, CC, V, TIPS>, grid, dim3(pruneThreads(V)), true, a, L.groupStart, cumMode);
-    }
-    template <typename real, int CC>
-    void launchLevelCG(const PruneArgs<real>& a, const Level& L, int cumMode, int v) {
-        const bool tips = L.tipsOnly != 0 && useTipsKernel;
-        if (v == kVariantStream) tips ? launchLevelV<real, CC, kVariantStream, true>(a, L, cumMode) : launchLevelV<real, CC, kVariantStream, false>(a, L, cumMode);
-        else tips ? launchLevelV<real, CC, kVariantSmall, true>(a, L, cumMode) : launchLevelV<real, CC, kVariantSmall, false>(a, L, cumMode);
-    }
-
+    // Arguments of the pruning launches of the active plan (and the bookkeeping of the cumulative buffer's reset).
     template <typename real>
-    void launchPartialsT(int cumIdx) {
+    PruneArgs<real> pruneArgs(int cumIdx) {
         double* cum = nullptr;
         int cumMode = 0;
         if (cumIdx != BEAGLE_OP_NONE) {
@@ -505,45 +579,18 @@ struct Engine {
         a.ops = dOps;
         a.groups = dGroups;
         a.tipStride = tipStride;
-        a.P = P;
         a.Ppad = Ppad;
         a.nTips = nTips;
-        if (sched.tipTipCount > 0) {
-            launchK(tiptip_tables_kernel<real>, dim3(sched.tipTipCount), dim3(128), true, static_cast<const DevOp*>(dOps),
-                    static_cast<const int*>(dTTOps), static_cast<const real*>(dMats), C, static_cast<real*>(dTT));
-            CK(cudaGetLastError());
-            ++launches;
-        }
-        const int v = variant();
-        int traceLevel = -1, levelIndex = 0;
-        if (const char* f = std::getenv("SB200_TRACE_LEVEL")) traceLevel = std::atoi(f);   // tuning aid (needs -DSB200_TRACE)
-        long long* const traceBuf = a.trace;
-        for (const Level& L : sched.levels) {
-            a.trace = (traceLevel < 0 || traceLevel == levelIndex) ? traceBuf : nullptr;
-            ++levelIndex;
-            if (L.groupCount == 0) continue;
-            switch (C) {
-                case 1: launchLevelCG<real, 1>(a, L, cumMode, v); break;
-                case 2: launchLevelCG<real, 2>(a, L, cumMode, v); break;
-                case 4: launchLevelCG<real, 4>(a, L, cumMode, v); break;
-                case 8: launchLevelCG<real, 8>(a, L, cumMode, v); break;
-                case 3: launchLevelCG<real, 3>(a, L, cumMode, v); break;
-                case 5: launchLevelCG<real, 5>(a, L, cumMode, v); break;
-                case 6: launchLevelCG<real, 6>(a, L, cumMode, v); break;
-                case 7: launchLevelCG<real, 7>(a, L, cumMode, v); break;
-            }
-            CK(cudaGetLastError());
-            ++launches;
-        }
-        if (cum && !sched.rootSlots.empty()) {
-            const int nr = static_cast<int>(sched.rootSlots.size());
-            int mode = 0;
-            if (scaleZeroPending[cumIdx]) { mode = 1; scaleZeroPending[cumIdx] = 0; }
-            launchK(fold_roots_kernel, dim3((Ppad + 255) / 256), dim3(256), true, static_cast<const double*>(a.slotAcc),
-                    static_cast<const double*>(a.slotProd), static_cast<const int*>(dRootSlots), nr, cum, Ppad, mode);
-            CK(cudaGetLastError());
-            ++launches;
-        }
+        a.cumMode = cumMode;
+        a.pad = 0;
+        return a;
+    }
+
+    // permanent subtree-scaler slots written / invalidated by a launch of the active plan
+    void noteSlotsAfterPartials(bool accumulate) {
+        if (!keepSubtreeScalers) return;
+        if (slotValid.size() != static_cast<size_t>(nPartials)) slotValid.assign(nPartials, 0);
+        for (const DevOp& d : sched.ops) slotValid[d.dest] = (accumulate && !sched.sequential) ? 1 : 0;
     }
 
     void collectProfile() {
@@ -556,27 +603,20 @@ struct Engine {
         evPending = false;
     }
 
-    void launchPartials(int cumIdx) {
-        lastCumIndex = cumIdx;
-        if (profiling) {
-            collectProfile();
-            if (!evP0) {
-                CK(cudaEventCreate(&evP0));
-                CK(cudaEventCreate(&evP1));
-            }
-            CK(cudaEventRecord(evP0, stream));
-        }
-        if (fp32) launchPartialsT<float>(cumIdx);
-        else launchPartialsT<double>(cumIdx);
-        if (profiling) {
-            CK(cudaEventRecord(evP1, stream));
-            evPending = true;
-        }
+    // ---- (c) ---------------------------------------------------------------------------
+    int checkRoot(int parent, int child, int matrix, int wIdx, int fIdx, int cumIdx) const {
+        const int nbuf = nTips + nPartials;
+        if (parent < nTips || parent >= nbuf || child < 0 || child >= nbuf || matrix < 0 || matrix >= nMat)
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (child < nTips && !tipSet[child]) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (wIdx < 0 || wIdx >= nEigen || fIdx < 0 || fIdx >= nEigen) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (cumIdx != BEAGLE_OP_NONE && (cumIdx < 0 || cumIdx >= nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        return BEAGLE_SUCCESS;
     }
 
-    // ---- (c) ---------------------------------------------------------------------------
     template <typename real>
-    void launchRootT(int parent, int child, int matrix, int wIdx, int fIdx, int cumIdx, double* out) {
+    RootArgs<real> rootArgs(int parent, int child, int matrix, int wIdx, int fIdx, int cumIdx, double* out) {
+        lastParent = parent; lastChild = child; lastMatrix = matrix; lastWIdx = wIdx; lastFIdx = fIdx; lastRootCum = cumIdx;
         RootArgs<real> a;
         a.partials = static_cast<const real*>(dPartials);
         a.tips = dTips;
@@ -606,32 +646,9 @@ struct Engine {
         a.parent = parent;
         a.child = child;
         a.matrix = matrix;
-        switch (C) {
-            case 1: launchK(root_loglik_kernel<real, 1>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 2: launchK(root_loglik_kernel<real, 2>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 4: launchK(root_loglik_kernel<real, 4>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 8: launchK(root_loglik_kernel<real, 8>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 3: launchK(root_loglik_kernel<real, 3>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 5: launchK(root_loglik_kernel<real, 5>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 6: launchK(root_loglik_kernel<real, 6>, dim3(rootBlocks), dim3(256), true, a); break;
-            case 7: launchK(root_loglik_kernel<real, 7>, dim3(rootBlocks), dim3(256), true, a); break;
-        }
-        CK(cudaGetLastError());
-        ++launches;
-    }
-
-    int launchRoot(int parent, int child, int matrix, int wIdx, int fIdx, int cumIdx, double* out) {
-        const int nbuf = nTips + nPartials;
-        if (parent < nTips || parent >= nbuf || child < 0 || child >= nbuf || matrix < 0 || matrix >= nMat)
-            return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (child < nTips && !tipSet[child]) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (wIdx < 0 || wIdx >= nEigen || fIdx < 0 || fIdx >= nEigen) return BEAGLE_ERROR_OUT_OF_RANGE;
-        if (cumIdx != BEAGLE_OP_NONE && (cumIdx < 0 || cumIdx >= nScale)) return BEAGLE_ERROR_OUT_OF_RANGE;
-        lastParent = parent; lastChild = child; lastMatrix = matrix; lastWIdx = wIdx; lastFIdx = fIdx; lastRootCum = cumIdx;
-        if (blockDirty) uploadBlock();     // frequencies / category weights set since the last matrix update take effect now
-        if (fp32) launchRootT<float>(parent, child, matrix, wIdx, fIdx, cumIdx, out);
-        else launchRootT<double>(parent, child, matrix, wIdx, fIdx, cumIdx, out);
-        return BEAGLE_SUCCESS;
+        a.blocks = rootBlocks;
+        a.pad = 0;
+        return a;
     }
 
     // The root kernel wrote the scalar straight into pinned host memory (hOut is device-accessible through
@@ -665,6 +682,194 @@ struct Engine {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Launch sets: K instances side by side (blockIdx.z / .y = instance).  All instances of a set live on one device and
+// run on the first one's stream; they share the category count and the precision.
+// ---------------------------------------------------------------------------------------------
+static void launchMatricesSet(Engine* const* es, int K) {
+    Engine& L = *es[0];
+    MatBatch mb;
+    int maxCount = 0;
+    for (int z = 0; z < kMaxBatch; ++z) {
+        mb.j[z] = es[z < K ? z : 0]->matJob();
+        if (z >= K) mb.j[z].count = 0;
+        maxCount = std::max(maxCount, mb.j[z].count);
+    }
+    if (maxCount == 0) return;
+    const long long threads = static_cast<long long>(maxCount) * L.C * 16;
+    const dim3 grid(static_cast<unsigned>((threads + 255) / 256), K);
+    SB200_RANGE_PUSH("sb200 A: transition matrices");
+    if (L.fp32) launchK(L.stream, false, transition_matrices_kernel<float>, grid, dim3(256), mb, L.C);
+    else launchK(L.stream, false, transition_matrices_kernel<double>, grid, dim3(256), mb, L.C);
+    SB200_RANGE_POP();
+    CK(cudaGetLastError());
+    ++L.launches;
+}
+
+template <typename real, int CC, int V>
+static void launchLevelV(Engine& L, const PruneBatch<real>& pb, dim3 grid, bool tips) {
+    if (tips) launchK(L.stream, L.usePdl, prune_chains_kernel<real, CC, V, true>, grid, dim3(varThreads(CC, V, sizeof(real))), pb);
+    else launchK(L.stream, L.usePdl, prune_chains_kernel<real, CC, V, false>, grid, dim3(varThreads(CC, V, sizeof(real))), pb);
+}
+template <typename real, int CC>
+static void launchLevelC(Engine& L, const PruneBatch<real>& pb, int tilesOf[3], int maxGroups, int K, int V, bool tips) {
+    const dim3 grid(tilesOf[V], maxGroups, K);
+    if (V == kVarStream) launchLevelV<real, CC, kVarStream>(L, pb, grid, tips);
+    else if (V == kVarWide) launchLevelV<real, CC, kVarWide>(L, pb, grid, tips);
+    else launchLevelV<real, CC, kVarNarrow>(L, pb, grid, tips);
+}
+
+template <typename real>
+static void launchPartialsSetT(Engine* const* es, int K, const int* cumIdx) {
+    Engine& L = *es[0];
+    const int C = L.C;
+    PruneArgs<real> args[kMaxBatch];
+    TableBatch<real> tb;
+    int maxTT = 0;
+    size_t maxLevels = 0;
+    for (int z = 0; z < K; ++z) {
+        Engine& E = *es[z];
+        args[z] = E.template pruneArgs<real>(cumIdx[z]);
+        maxLevels = std::max(maxLevels, E.sched.levels.size());
+    }
+    for (int z = 0; z < kMaxBatch; ++z) {
+        Engine& E = *es[z < K ? z : 0];
+        tb.j[z].ops = E.dOps;
+        tb.j[z].ttOps = E.dTTOps;
+        tb.j[z].mats = static_cast<const real*>(E.dMats);
+        tb.j[z].tables = static_cast<real*>(E.dTT);
+        tb.j[z].count = z < K ? E.sched.tipTipCount : 0;
+        tb.j[z].pad = 0;
+        maxTT = std::max(maxTT, tb.j[z].count);
+    }
+    SB200_RANGE_PUSH("sb200 B: partials");
+    if (maxTT > 0) {
+        launchK(L.stream, L.usePdl, tiptip_tables_kernel<real>, dim3(maxTT, K), dim3(128), tb, C);
+        CK(cudaGetLastError());
+        ++L.launches;
+    }
+    int tilesOf[3];
+    for (int v = 0; v < 3; ++v) tilesOf[v] = L.Ppad / varPatterns(C, v, sizeof(real));
+    const int traceLevel = envInt("SB200_TRACE_LEVEL", -1);   // tuning aid (needs -DSB200_TRACE)
+    for (size_t l = 0; l < maxLevels; ++l) {
+        // the instances' launches number l, grouped by (thread shape, tips-only): normally ONE launch
+        bool done[kMaxBatch] = {false};
+        for (int z0 = 0; z0 < K; ++z0) {
+            if (done[z0]) continue;
+            if (l >= es[z0]->sched.levels.size() || es[z0]->sched.levels[l].groupCount == 0) { done[z0] = true; continue; }
+            const Level& L0 = es[z0]->sched.levels[l];
+            const int V = L0.variant;
+            const bool tips = L0.tipsOnly != 0 && L.useTipsKernel;
+            PruneBatch<real> pb;
+            int maxGroups = 0, n = 0;
+            for (int z = z0; z < K; ++z) {
+                if (done[z] || l >= es[z]->sched.levels.size()) continue;
+                const Level& Lz = es[z]->sched.levels[l];
+                if (Lz.groupCount == 0) { done[z] = true; continue; }
+                if (Lz.variant != V || (Lz.tipsOnly != 0 && L.useTipsKernel) != tips) continue;
+                pb.a[n] = args[z];
+                pb.a[n].trace = (traceLevel < 0 || traceLevel == static_cast<int>(l)) ? args[z].trace : nullptr;
+                pb.groupBase[n] = Lz.groupStart;
+                pb.groupCount[n] = Lz.groupCount;
+                maxGroups = std::max(maxGroups, Lz.groupCount);
+                done[z] = true;
+                ++n;
+            }
+            for (int q = n; q < kMaxBatch; ++q) { pb.a[q] = pb.a[0]; pb.groupBase[q] = 0; pb.groupCount[q] = 0; }
+            switch (C) {
+                case 1: launchLevelC<real, 1>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 2: launchLevelC<real, 2>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 3: launchLevelC<real, 3>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 4: launchLevelC<real, 4>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 5: launchLevelC<real, 5>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 6: launchLevelC<real, 6>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 7: launchLevelC<real, 7>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+                case 8: launchLevelC<real, 8>(L, pb, tilesOf, maxGroups, n, V, tips); break;
+            }
+            CK(cudaGetLastError());
+            ++L.launches;
+        }
+    }
+    for (int z = 0; z < K; ++z) {
+        Engine& E = *es[z];
+        if (args[z].cum && !E.sched.rootSlots.empty()) {
+            const int nr = static_cast<int>(E.sched.rootSlots.size());
+            int mode = 0;
+            if (E.scaleZeroPending[cumIdx[z]]) { mode = 1; E.scaleZeroPending[cumIdx[z]] = 0; }
+            launchK(L.stream, L.usePdl, fold_roots_kernel, dim3((E.Ppad + 255) / 256), dim3(256), static_cast<const double*>(args[z].slotAcc),
+                    static_cast<const double*>(args[z].slotProd), static_cast<const int*>(E.dRootSlots), nr, args[z].cum, E.Ppad, mode);
+            CK(cudaGetLastError());
+            ++L.launches;
+        }
+        E.noteSlotsAfterPartials(E.schedAccumulate);
+    }
+    SB200_RANGE_POP();
+}
+
+static void launchPartialsSet(Engine* const* es, int K, const int* cumIdx) {
+    Engine& L = *es[0];
+    for (int z = 0; z < K; ++z) es[z]->lastCumIndex = cumIdx[z];
+    if (L.profiling) {
+        L.collectProfile();
+        if (!L.evP0) {
+            CK(cudaEventCreate(&L.evP0));
+            CK(cudaEventCreate(&L.evP1));
+        }
+        CK(cudaEventRecord(L.evP0, L.stream));
+    }
+    if (L.fp32) launchPartialsSetT<float>(es, K, cumIdx);
+    else launchPartialsSetT<double>(es, K, cumIdx);
+    if (L.profiling) {
+        CK(cudaEventRecord(L.evP1, L.stream));
+        L.evPending = true;
+    }
+}
+
+struct RootCall {
+    int parent, child, matrix, wIdx, fIdx, cumIdx;
+    double* out;
+};
+
+template <typename real>
+static void launchRootSetT(Engine* const* es, int K, const RootCall* rc) {
+    Engine& L = *es[0];
+    RootBatch<real> rb;
+    int maxBlocks = 0;
+    for (int z = 0; z < K; ++z) {
+        rb.a[z] = es[z]->template rootArgs<real>(rc[z].parent, rc[z].child, rc[z].matrix, rc[z].wIdx, rc[z].fIdx, rc[z].cumIdx, rc[z].out);
+        maxBlocks = std::max(maxBlocks, rb.a[z].blocks);
+    }
+    for (int z = K; z < kMaxBatch; ++z) { rb.a[z] = rb.a[0]; rb.a[z].blocks = 0; }
+    const dim3 grid(maxBlocks, K), block(rootPatternsPerBlock());
+    SB200_RANGE_PUSH("sb200 C: root edge log-likelihood");
+    switch (L.C) {
+        case 1: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 1>, grid, block, rb); break;
+        case 2: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 2>, grid, block, rb); break;
+        case 3: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 3>, grid, block, rb); break;
+        case 4: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 4>, grid, block, rb); break;
+        case 5: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 5>, grid, block, rb); break;
+        case 6: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 6>, grid, block, rb); break;
+        case 7: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 7>, grid, block, rb); break;
+        case 8: launchK(L.stream, L.usePdl, root_loglik_kernel<real, 8>, grid, block, rb); break;
+    }
+    SB200_RANGE_POP();
+    CK(cudaGetLastError());
+    ++L.launches;
+}
+
+// Validates, then launches.  Frequencies / category weights set since the last matrix update take effect now.
+static int launchRootSet(Engine* const* es, int K, const RootCall* rc) {
+    for (int z = 0; z < K; ++z) {
+        const int code = es[z]->checkRoot(rc[z].parent, rc[z].child, rc[z].matrix, rc[z].wIdx, rc[z].fIdx, rc[z].cumIdx);
+        if (code) return code;
+    }
+    for (int z = 0; z < K; ++z)
+        if (es[z]->blockDirty) es[z]->uploadBlock();
+    if (es[0]->fp32) launchRootSetT<float>(es, K, rc);
+    else launchRootSetT<double>(es, K, rc);
+    return BEAGLE_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
 // instance table
 // ---------------------------------------------------------------------------------------------
 static std::mutex g_mu;
@@ -684,15 +889,17 @@ static int mapCuda(cudaError_t e) {
     return BEAGLE_ERROR_GENERAL;
 }
 
-// Runs `body` on instance `id` with its device current; converts every failure into a code.
+// Runs `body` with `device` current (the caller's current device is restored afterwards); converts every failure into a code.
 template <typename F>
-static int withEngine(int id, F&& body) {
-    Engine* E = getEngine(id);
-    if (!E) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+static int onDevice(int device, F&& body) {
     try {
-        cudaError_t e = cudaSetDevice(E->device);
-        if (e != cudaSuccess) return mapCuda(e);
-        return body(*E);
+        DeviceGuard guard;
+        cudaError_t e = guard.enter(device);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return mapCuda(e);
+        }
+        return body();
     } catch (const CudaFail& f) {
         cudaGetLastError();
         return mapCuda(f.err);
@@ -702,6 +909,12 @@ static int withEngine(int id, F&& body) {
         return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
     }
 }
+template <typename F>
+static int withEngine(int id, F&& body) {
+    Engine* E = getEngine(id);
+    if (!E) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+    return onDevice(E->device, [&]() { return body(*E); });
+}
 
 static void fillCmat(const double* evec, const double* ivec, double* cmat) {
     int l = 0;
@@ -710,25 +923,68 @@ static void fillCmat(const double* evec, const double* ivec, double* cmat) {
             for (int x = 0; x < 4; ++x) cmat[l++] = evec[i * 4 + x] * ivec[x * 4 + j];
 }
 
-static int evalCommon(Engine& E, const StromEvalArgs* a, double* deviceOut) {
-    if (!a || a->edgeCount < 0 || a->operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
-    int rc = E.setEdges(a->matrixIndices, a->edgeLengths, a->edgeCount);
-    if (rc) return rc;
-    DevModel* m = E.hModel(0);
-    std::memcpy(m->freqs, a->stateFrequencies, sizeof(double) * 4);
-    fillCmat(a->eigenVectors, a->inverseEigenVectors, m->cmat);
-    std::memcpy(m->evals, a->eigenValues, sizeof(double) * 4);
-    std::memcpy(m->weights, a->categoryWeights, sizeof(double) * E.C);
-    std::memcpy(E.hHeader()->rates, a->categoryRates, sizeof(double) * E.C);
-    if (E.nScale < 1) return BEAGLE_ERROR_OUT_OF_RANGE;
-    E.uploadBlock();
-    E.launchMatrices();          // the GPU starts on the matrices while the host checks / rebuilds the plan
-    rc = E.prepareSchedule(a->operations, a->operationCount, true);
-    if (rc) return rc;
-    E.scaleBuffer(0);
-    E.scaleZeroPending[0] = 1;
-    E.launchPartials(0);
-    return E.launchRoot(a->rootParentBuffer, a->rootChildBuffer, a->rootMatrix, 0, 0, 0, deviceOut ? deviceOut : E.hOut);
+// One whole evaluation of every instance of the set: parameter blocks up, then ONE set of launches.  Everything is
+// validated before any instance's parameter block is touched or anything is enqueued.
+static int evalSet(Engine* const* es, int K, const StromEvalArgs* args, double* const* deviceOut) {
+    Engine& L = *es[0];
+    for (int z = 0; z < K; ++z) {
+        Engine& E = *es[z];
+        const StromEvalArgs& a = args[z];
+        if (a.edgeCount < 0 || a.operationCount < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (!a.stateFrequencies || !a.eigenVectors || !a.inverseEigenVectors || !a.eigenValues || !a.categoryRates || !a.categoryWeights)
+            return BEAGLE_ERROR_OUT_OF_RANGE;
+        if ((a.edgeCount > 0 && (!a.matrixIndices || !a.edgeLengths)) || (a.operationCount > 0 && !a.operations)) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (a.categoryCount != 0 && a.categoryCount != E.C) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (E.nScale < 1) return BEAGLE_ERROR_OUT_OF_RANGE;
+        if (E.device != L.device || E.C != L.C || E.fp32 != L.fp32) return BEAGLE_ERROR_OUT_OF_RANGE;
+        int rc = E.checkEdges(a.matrixIndices, a.edgeCount);
+        if (rc) return rc;
+        rc = E.checkRoot(a.rootParentBuffer, a.rootChildBuffer, a.rootMatrix, 0, 0, 0);
+        if (rc) return rc;
+    }
+    // the set runs on the first instance's stream: an instance that joins drains its own stream once and stays
+    for (int z = 1; z < K; ++z) {
+        Engine& E = *es[z];
+        if (E.stream != L.stream) {
+            CK(cudaStreamSynchronize(E.stream));
+            E.stream = L.stream;
+        }
+    }
+    for (int z = 0; z < K; ++z) es[z]->setBatchHint(K);
+    // plans first (host work; a new topology also enqueues its plan upload), so that a rejected list leaves no trace
+    for (int z = 0; z < K; ++z) {
+        const int rc = es[z]->prepareSchedule(args[z].operations, args[z].operationCount, true);
+        if (rc) return rc;
+        if (es[z]->keepSubtreeScalers) {
+            const int sc = es[z]->checkSlots(es[z]->sched);
+            if (sc) return sc;
+        }
+    }
+    for (int z = 0; z < K; ++z) {
+        Engine& E = *es[z];
+        const StromEvalArgs& a = args[z];
+        const int rc = E.setEdges(a.matrixIndices, a.edgeLengths, a.edgeCount);
+        if (rc) return rc;
+        DevModel* m = E.hModel(0);
+        std::memcpy(m->freqs, a.stateFrequencies, sizeof(double) * 4);
+        fillCmat(a.eigenVectors, a.inverseEigenVectors, m->cmat);
+        std::memcpy(m->evals, a.eigenValues, sizeof(double) * 4);
+        std::memcpy(m->weights, a.categoryWeights, sizeof(double) * E.C);
+        std::memcpy(E.hHeader()->rates, a.categoryRates, sizeof(double) * E.C);
+        E.uploadBlock();
+    }
+    launchMatricesSet(es, K);
+    int cumIdx[kMaxBatch];
+    RootCall rc[kMaxBatch];
+    for (int z = 0; z < K; ++z) {
+        es[z]->scaleBuffer(0);
+        es[z]->scaleZeroPending[0] = 1;
+        cumIdx[z] = 0;
+        rc[z] = RootCall{args[z].rootParentBuffer, args[z].rootChildBuffer, args[z].rootMatrix, 0, 0, 0,
+                         (deviceOut && deviceOut[z]) ? deviceOut[z] : es[z]->hOut};
+    }
+    launchPartialsSet(es, K, cumIdx);
+    return launchRootSet(es, K, rc);
 }
 
 }  // namespace sb200
@@ -784,7 +1040,7 @@ extern "C" int beagleCreateInstance(int tipCount, int partialsBufferCount, int c
         return BEAGLE_ERROR_OUT_OF_RANGE;
     if (categoryCount > kMaxCategories) return BEAGLE_ERROR_NO_IMPLEMENTATION;
     if (compactBufferCount < tipCount) return BEAGLE_ERROR_NO_IMPLEMENTATION;   // tips are compact states only
-    int device = g_device;
+    int device = t_device >= 0 ? t_device : g_defaultDevice.load();
     if (resourceList && resourceCount > 0) device = resourceList[0];
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -798,13 +1054,13 @@ extern "C" int beagleCreateInstance(int tipCount, int partialsBufferCount, int c
     E->fp32 = (requirementFlags & BEAGLE_FLAG_PRECISION_SINGLE) != 0;
     E->nTips = tipCount; E->nPartials = partialsBufferCount; E->nCompact = compactBufferCount; E->P = patternCount;
     E->nEigen = eigenBufferCount; E->nMat = matrixBufferCount; E->C = categoryCount; E->nScale = scaleBufferCount;
-    try {
-        E->init();
-    } catch (const CudaFail& f) {
-        cudaGetLastError();
-        return mapCuda(f.err);
-    } catch (...) {
-        return BEAGLE_ERROR_UNIDENTIFIED_EXCEPTION;
+    {
+        Engine* raw = E.get();
+        const int rc = onDevice(device, [&]() {
+            raw->init();
+            return static_cast<int>(BEAGLE_SUCCESS);
+        });
+        if (rc != BEAGLE_SUCCESS) return rc;
     }
     if (returnInfo) {
         returnInfo->resourceNumber = device;
@@ -831,6 +1087,11 @@ extern "C" int beagleFinalizeInstance(int instance) {
         if (instance < 0 || instance >= static_cast<int>(g_inst.size()) || !g_inst[instance])
             return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
         E = std::move(g_inst[instance]);
+        for (auto& other : g_inst)                        // instances that joined this one's stream (launch sets) go back to their own
+            if (other && other->stream == E->ownStream) {
+                cudaStreamSynchronize(other->stream);
+                other->stream = other->ownStream;
+            }
     }
     E.reset();
     return BEAGLE_SUCCESS;
@@ -838,14 +1099,16 @@ extern "C" int beagleFinalizeInstance(int instance) {
 
 static int setTipsCommon(Engine& E, int tipIndex, const int* s32, const unsigned char* s8) {
     if (tipIndex < 0 || tipIndex >= E.nTips || tipIndex >= E.nCompact) return BEAGLE_ERROR_OUT_OF_RANGE;
-    std::vector<unsigned char> codes(static_cast<size_t>(E.P));
+    // (pageable source: cudaMemcpyAsync returns once the bytes sit in the driver's staging memory, so the row buffer can
+    // be reused at once and no stream wait is needed per tip; later work on the stream is ordered behind the copy)
+    std::vector<unsigned char>& codes = E.tipStage;
+    codes.resize(static_cast<size_t>(E.P));
     if (s32)
         for (int j = 0; j < E.P; ++j) codes[j] = (s32[j] >= 0 && s32[j] < 4) ? static_cast<unsigned char>(s32[j]) : 4;
     else
         for (int j = 0; j < E.P; ++j) codes[j] = s8[j] < 4 ? s8[j] : 4;
     CK(cudaMemcpyAsync(E.dTips + static_cast<size_t>(tipIndex) * E.tipStride, codes.data(), static_cast<size_t>(E.P),
                        cudaMemcpyHostToDevice, E.stream));
-    CK(cudaStreamSynchronize(E.stream));   // pageable source: make the copy's completion explicit
     E.tipSet[tipIndex] = 1;
     E.forgetPlans();
     return BEAGLE_SUCCESS;
@@ -859,6 +1122,26 @@ extern "C" int beagleSetTipStates(int instance, int tipIndex, const int* inState
 extern "C" int sb200SetTipStatesU8(int instance, int tipIndex, const unsigned char* inStates) {
     if (!inStates) return BEAGLE_ERROR_OUT_OF_RANGE;
     return withEngine(instance, [&](Engine& E) { return setTipsCommon(E, tipIndex, nullptr, inStates); });
+}
+
+// All tips in one call: codes[tip * patternCount + pattern], one strided copy (row pitch = the padded pattern axis).
+extern "C" int sb200SetAllTipStatesU8(int instance, const unsigned char* inStates) {
+    if (!inStates) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        if (E.nTips == 0) return static_cast<int>(BEAGLE_SUCCESS);
+        if (E.nCompact < E.nTips) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        std::vector<unsigned char>& codes = E.tipStage;
+        const size_t n = static_cast<size_t>(E.nTips) * E.P;
+        codes.resize(n);
+        for (size_t q = 0; q < n; ++q) codes[q] = inStates[q] < 4 ? inStates[q] : 4;
+        CK(cudaMemcpy2DAsync(E.dTips, static_cast<size_t>(E.tipStride), codes.data(), static_cast<size_t>(E.P), static_cast<size_t>(E.P),
+                             static_cast<size_t>(E.nTips), cudaMemcpyHostToDevice, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        std::vector<unsigned char>().swap(codes);
+        E.tipSet.assign(E.nTips, 1);
+        E.forgetPlans();
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
 }
 
 extern "C" int beagleSetPatternWeights(int instance, const double* w) {
@@ -921,7 +1204,8 @@ extern "C" int beagleUpdateTransitionMatrices(int instance, int eigenIndex, cons
         int rc = E.setEdges(probabilityIndices, edgeLengths, count);
         if (rc) return rc;
         E.uploadBlock();
-        E.launchMatrices();
+        Engine* es[1] = {&E};
+        launchMatricesSet(es, 1);
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }
@@ -941,9 +1225,15 @@ extern "C" int beagleUpdatePartials(int instance, const BeagleOperation* operati
     return withEngine(instance, [&](Engine& E) {
         if (cumulativeScaleIndex != BEAGLE_OP_NONE && (cumulativeScaleIndex < 0 || cumulativeScaleIndex >= E.nScale))
             return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        E.setBatchHint(1);
         int rc = E.prepareSchedule(operations, operationCount, cumulativeScaleIndex != BEAGLE_OP_NONE);
         if (rc) return rc;
-        E.launchPartials(cumulativeScaleIndex);
+        if (E.keepSubtreeScalers && cumulativeScaleIndex != BEAGLE_OP_NONE) {
+            rc = E.checkSlots(E.sched);
+            if (rc) return rc;
+        }
+        Engine* es[1] = {&E};
+        launchPartialsSet(es, 1, &cumulativeScaleIndex);
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }
@@ -958,8 +1248,10 @@ extern "C" int beagleCalculateEdgeLogLikelihoods(int instance, const int* parent
         !stateFrequenciesIndices || !cumulativeScaleIndices || !outSumLogLikelihood)
         return BEAGLE_ERROR_OUT_OF_RANGE;
     return withEngine(instance, [&](Engine& E) {
-        int rc = E.launchRoot(parentBufferIndices[0], childBufferIndices[0], probabilityIndices[0],
-                              categoryWeightsIndices[0], stateFrequenciesIndices[0], cumulativeScaleIndices[0], E.hOut);
+        Engine* es[1] = {&E};
+        const RootCall rc1{parentBufferIndices[0], childBufferIndices[0], probabilityIndices[0], categoryWeightsIndices[0],
+                           stateFrequenciesIndices[0], cumulativeScaleIndices[0], E.hOut};
+        int rc = launchRootSet(es, 1, &rc1);
         if (rc) return rc;
         return E.readScalar(outSumLogLikelihood);
     });
@@ -977,7 +1269,8 @@ extern "C" int sb200SetDevice(int device) {
         return BEAGLE_ERROR_NO_RESOURCE;
     }
     if (device < 0 || device >= n) return BEAGLE_ERROR_NO_RESOURCE;
-    g_device = device;
+    t_device = device;
+    g_defaultDevice.store(device);
     return BEAGLE_SUCCESS;
 }
 
@@ -990,16 +1283,48 @@ extern "C" int sb200SetStream(int instance, void* cudaStream) {
 }
 
 extern "C" int sb200Eval(int instance, const StromEvalArgs* args, double* outLogLikelihood) {
-    if (!outLogLikelihood) return BEAGLE_ERROR_OUT_OF_RANGE;
+    if (!outLogLikelihood || !args) return BEAGLE_ERROR_OUT_OF_RANGE;
     return withEngine(instance, [&](Engine& E) {
-        int rc = evalCommon(E, args, nullptr);
+        Engine* es[1] = {&E};
+        int rc = evalSet(es, 1, args, nullptr);
         if (rc) return rc;
         return E.readScalar(outLogLikelihood);
     });
 }
 
 extern "C" int sb200EvalAsync(int instance, const StromEvalArgs* args, double* deviceOut) {
-    return withEngine(instance, [&](Engine& E) { return evalCommon(E, args, deviceOut); });
+    if (!args) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return withEngine(instance, [&](Engine& E) {
+        Engine* es[1] = {&E};
+        double* outs[1] = {deviceOut};
+        return evalSet(es, 1, args, outs);
+    });
+}
+
+// Up to kMaxBatch instances per set of launches; longer lists are cut into sets.
+template <typename F>
+static int forSets(int count, const int* instances, F&& body) {
+    if (count < 1 || !instances) return BEAGLE_ERROR_OUT_OF_RANGE;
+    std::vector<Engine*> es(static_cast<size_t>(count));
+    for (int i = 0; i < count; ++i) {
+        es[i] = getEngine(instances[i]);
+        if (!es[i]) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
+        for (int j = 0; j < i; ++j)
+            if (es[j] == es[i]) return BEAGLE_ERROR_OUT_OF_RANGE;            // an instance holds ONE evaluation at a time
+    }
+    return onDevice(es[0]->device, [&]() {
+        for (int first = 0; first < count; first += kMaxBatch) {
+            const int K = std::min(kMaxBatch, count - first);
+            const int rc = body(es.data() + first, K, first);
+            if (rc) return rc;
+        }
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
+extern "C" int sb200EvalBatchAsync(int count, const int* instances, const StromEvalArgs* args) {
+    if (!args) return BEAGLE_ERROR_OUT_OF_RANGE;
+    return forSets(count, instances, [&](Engine* const* es, int K, int first) { return evalSet(es, K, args + first, nullptr); });
 }
 
 extern "C" int sb200Finish(int instance, double* outLogLikelihood) {
@@ -1007,15 +1332,34 @@ extern "C" int sb200Finish(int instance, double* outLogLikelihood) {
     return withEngine(instance, [&](Engine& E) { return E.readScalar(outLogLikelihood); });
 }
 
+static int replaySet(Engine* const* es, int K, double* const* deviceOut) {
+    int cumIdx[kMaxBatch];
+    RootCall rc[kMaxBatch];
+    for (int z = 0; z < K; ++z) {
+        Engine& E = *es[z];
+        if (!E.schedValid || E.lastParent < 0) return static_cast<int>(BEAGLE_ERROR_GENERAL);
+        if (E.device != es[0]->device || E.C != es[0]->C || E.fp32 != es[0]->fp32 || E.stream != es[0]->stream)
+            return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
+        cumIdx[z] = E.lastCumIndex;
+        if (E.lastCumIndex != BEAGLE_OP_NONE) E.scaleZeroPending[E.lastCumIndex] = 1;
+        rc[z] = RootCall{E.lastParent, E.lastChild, E.lastMatrix, E.lastWIdx, E.lastFIdx, E.lastRootCum,
+                         (deviceOut && deviceOut[z]) ? deviceOut[z] : E.hOut};
+    }
+    launchMatricesSet(es, K);
+    launchPartialsSet(es, K, cumIdx);
+    return launchRootSet(es, K, rc);
+}
+
 extern "C" int sb200ReplayAsync(int instance, double* deviceOut) {
     return withEngine(instance, [&](Engine& E) {
-        if (!E.schedValid || E.lastParent < 0) return static_cast<int>(BEAGLE_ERROR_GENERAL);
-        E.launchMatrices();
-        if (E.lastCumIndex != BEAGLE_OP_NONE) E.scaleZeroPending[E.lastCumIndex] = 1;
-        E.launchPartials(E.lastCumIndex);
-        return E.launchRoot(E.lastParent, E.lastChild, E.lastMatrix, E.lastWIdx, E.lastFIdx, E.lastRootCum,
-                            deviceOut ? deviceOut : E.hOut);
+        Engine* es[1] = {&E};
+        double* outs[1] = {deviceOut};
+        return replaySet(es, 1, outs);
     });
+}
+
+extern "C" int sb200ReplayBatchAsync(int count, const int* instances) {
+    return forSets(count, instances, [&](Engine* const* es, int K, int) { return replaySet(es, K, nullptr); });
 }
 
 extern "C" int sb200Synchronize(int instance) {
@@ -1031,16 +1375,21 @@ extern "C" int sb200GetPartials(int instance, int bufferIndex, double* out) {
     if (!out) return BEAGLE_ERROR_OUT_OF_RANGE;
     return withEngine(instance, [&](Engine& E) {
         if (bufferIndex < E.nTips || bufferIndex >= E.nTips + E.nPartials) return static_cast<int>(BEAGLE_ERROR_OUT_OF_RANGE);
-        const size_t n = static_cast<size_t>(E.P) * E.C * 4;
+        // HBM holds [category][Ppad][4]; the caller gets BeagleLib's [pattern][category][4] ... as documented in the header
         const size_t stride = static_cast<size_t>(E.Ppad) * E.C * 4;
+        std::vector<double> full(stride);
         CK(cudaStreamSynchronize(E.stream));
         if (E.fp32) {
-            std::vector<float> tmp(n);
-            CK(cudaMemcpy(tmp.data(), static_cast<float*>(E.dPartials) + stride * (bufferIndex - E.nTips), n * 4, cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < n; ++i) out[i] = tmp[i];
+            std::vector<float> tmp(stride);
+            CK(cudaMemcpy(tmp.data(), static_cast<float*>(E.dPartials) + stride * (bufferIndex - E.nTips), stride * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < stride; ++i) full[i] = tmp[i];
         } else {
-            CK(cudaMemcpy(out, static_cast<double*>(E.dPartials) + stride * (bufferIndex - E.nTips), n * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(full.data(), static_cast<double*>(E.dPartials) + stride * (bufferIndex - E.nTips), stride * 8, cudaMemcpyDeviceToHost));
         }
+        for (int p = 0; p < E.P; ++p)
+            for (int k = 0; k < E.C; ++k)
+                for (int i = 0; i < 4; ++i)
+                    out[(static_cast<size_t>(p) * E.C + k) * 4 + i] = full[(static_cast<size_t>(k) * E.Ppad + p) * 4 + i];
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }
@@ -1071,7 +1420,7 @@ extern "C" int sb200GetTransitionMatrix(int instance, int matrixIndex, double* o
             CK(cudaMemcpy(full.data(), static_cast<double*>(E.dMats) + n * matrixIndex, n * 8, cudaMemcpyDeviceToHost));
         }
         for (int k = 0; k < E.C; ++k)
-            for (int e = 0; e < 16; ++e) out[k * 16 + e] = full[rmIndex(E.C, k, e)];
+            for (int e = 0; e < 16; ++e) out[k * 16 + e] = full[pmIndex(k, e)];
         return static_cast<int>(BEAGLE_SUCCESS);
     });
 }
@@ -1102,6 +1451,7 @@ extern "C" __attribute__((visibility("default"))) int sb200DebugTrace(int instan
         if (!E.dTrace) {
             CK(cudaMalloc(&E.dTrace, sizeof(long long) * 480));
             CK(cudaMemset(E.dTrace, 0, sizeof(long long) * 480));
+            E.forgetPlans();
         }
         if (out) {
             CK(cudaStreamSynchronize(E.stream));
@@ -1116,6 +1466,7 @@ extern "C" int sb200SetSubtreeScalers(int instance, int enable) {
         const bool on = enable != 0;
         if (on != E.keepSubtreeScalers) {
             E.keepSubtreeScalers = on;
+            E.slotValid.assign(E.nPartials, 0);
             E.forgetPlans();                           // every plan depends on it
         }
         return static_cast<int>(BEAGLE_SUCCESS);

@@ -1,4 +1,4 @@
-// kernels.cuh -- the three hand-written sm_100a kernels of the tree-likelihood hot path.
+// kernels.cuh -- the hand-written sm_100a kernels of the tree-likelihood hot path.
 //
 //   (a) transition_matrices_kernel : BeagleLib beagleUpdateTransitionMatrices
 //                                     (reference call site src/likelihood.hpp:357-370)
@@ -8,15 +8,18 @@
 //                                     (reference call site src/likelihood.hpp:418-447)
 //
 // HBM layout (pattern axis padded to Ppad = whole thread-block tiles, so no kernel needs tail predicates):
-//   partials [buffer][Ppad][category][state]  one pattern x category = 4 reals = one 256-bit load (FP64)
+//   partials [buffer][category][Ppad][state]  CATEGORY-MAJOR: the 32 lanes of a warp hold 32 consecutive patterns of
+//                                             ONE category, one pattern x category = 4 reals = one 256-bit load (FP64),
+//                                             a warp-wide load is 1 KB contiguous
 //   tips     [tip][Ppad]                      1-byte codes 0..4 (4 = missing; padding is 4)
-//   matrices [matrix][36*C]                   already in the shared-memory image the pruning kernel wants:
-//              16*C reals  row-major P_k[i][j], interleaved over categories as [(i*4+j)/2][k][(i*4+j)%2]
-//                          (the C category lanes of a warp read C consecutive 16-byte words: no bank conflict)
-//              20*C reals  tip table T[k][i][s] = P_k[i][s], column s=4 all ones (the missing state); state
-//                          fastest so that the 16 lanes of a shared-memory pass (4 patterns x 4 categories)
-//                          fall into distinct banks for s <= 3
+//   matrices [matrix][category][36]           16 reals row-major P_k[i][j], then the 20 reals of the tip table
+//                                             T_k[s][i] = P_k[i][s] (a COLUMN of P per tip state; s = 4, the missing state,
+//                                             all ones).  Every lane of a warp reads the same matrix words: shared-memory
+//                                             broadcast, one wavefront per 128-bit read
 //   log-scalers [slot][Ppad] FP64 (cumulative buffers and per-chain subtree sums)
+//
+// Every kernel takes up to kMaxBatch independent evaluations (the heated chains of an MC3 run) side by side: the
+// evaluation index is a grid dimension, so K trees cost ONE set of launches (sb200EvalBatchAsync).
 //
 // The work is an HBM-bound 4x4 matrix-vector product (about 0.6 flop/byte): no tensor cores.
 #pragma once
@@ -29,46 +32,60 @@ namespace sb200 {
 
 constexpr int kMaxCategories = 8;
 constexpr int kMatStride = 36;      // reals per (matrix, category)
-// tip x tip table of one operation: 25 (stateA, stateB) combinations x C categories x 4 states of
-// rescaled partials, followed by the 25 rescaling maxima (padded to 32)
-__host__ __device__ constexpr int ttStride(int C) { return 100 * C + 32; }
-// Threads per block of the (pattern, category) pruning kernel.  Streaming sizes (R = 2 patterns per thread): 256
-// threads, 3 blocks per SM.  Small pattern counts (R = 1): 128 threads, 6 blocks per SM -- a step is bound by the
-// latency of one warp's instruction stream and by the block barrier, so smaller blocks and twice as many groups
-// per launch shorten the sequential part (rbcl738: 108.6 -> 100.9 us per evaluation).
-// Variants (template parameter V of prune_chains_kernel): patterns per thread R, threads per block, blocks per SM.
-// (A third variant, 64 threads x 2 patterns for small pattern counts, was measured and dropped: rbcl738 104.4 vs
-// 100.6 us.)  TIPS = the launch holds only operations whose operands from memory are tips and that read no subtree
-// scalers (level 0 of every full evaluation: 37 % of the bytes of a 1000-taxon evaluation): the partials-operand
-// and scaler-operand code is compiled out, which frees registers for one more resident block per SM.
-// (tuning aids: resident blocks per SM of the general kernels; 7 / 8 for the small and 4 for the streaming variant were
-// measured and are slower, profiles/r1_negative_results.md)
-#ifndef SB200_SMALL_BPS
-#define SB200_SMALL_BPS 6
+constexpr int kMaxBatch = 8;        // evaluations per launch set
+
+// tip x tip table of one operation: 25 (stateA, stateB) entries of C categories x 4 states of rescaled partials, each
+// entry padded by 16 bytes (entries of different state pairs then start in different shared-memory bank groups: the
+// lanes of a warp read entries of different pairs), followed by the 25 rescaling maxima (padded to 32).
+__host__ __device__ constexpr int ttEntry(int C, int realBytes) { return 4 * C + 16 / realBytes; }
+__host__ __device__ constexpr int ttStride(int C, int realBytes) { return 25 * ttEntry(C, realBytes) + 32; }
+
+// ------------------------------------------------------------------------------------------
+// Shapes of the pruning kernel (template parameter V).  A thread owns ONE pattern and CPT of the C categories; a
+// warp = 32 consecutive patterns x CPT categories; NCW = C / CPT warps cover a pattern sub-tile; a block holds TP
+// sub-tiles.
+//   kVarStream  streaming sizes: all categories in the thread (matrix reads are warp-wide broadcasts, the per-pattern
+//               maximum over categories never leaves the registers, the reciprocal is taken once per pattern), 8 warps;
+//   kVarWide    the same thread shape in 4-warp blocks, for launches of small instances that have enough independent
+//               chains to fill the GPU (the lower levels of rbcl738, or several evaluations batched);
+//   kVarNarrow  one category per thread (a warp per category, maxima exchanged through shared memory): C times the
+//               warps and a C times shorter dependent instruction stream per step, for launches with few chains
+//               (the top of the tree), where a step is bound by the latency of one warp's instructions.
+// ------------------------------------------------------------------------------------------
+enum { kVarStream = 0, kVarWide = 1, kVarNarrow = 2 };
+// categories per thread of the stream / wide shapes: what the register file carries without spilling (two FP64 or four
+// FP32 operand vectors per operand); a category count that does not divide leaves the last warp's spare slots repeating
+// the last category (5 = 2+2+1 in FP64, 3+2 in FP32)
+#ifndef SB200_CPT64
+#define SB200_CPT64 2
 #endif
-#ifndef SB200_STREAM_BPS
-#define SB200_STREAM_BPS 3
+#ifndef SB200_CPT32
+#define SB200_CPT32 4
 #endif
-enum { kVariantSmall = 0, kVariantStream = 1 };
-__host__ __device__ constexpr int pruneR(int V) { return V == kVariantSmall ? 1 : 2; }
-__host__ __device__ constexpr int pruneThreads(int V) { return V == kVariantSmall ? 128 : 256; }
-__host__ __device__ constexpr int pruneBlocksPerSm(int V, bool tips = false) {
-    return V == kVariantSmall ? (tips ? 8 : SB200_SMALL_BPS) : (tips ? 4 : SB200_STREAM_BPS);
+__host__ __device__ constexpr int cptWide(int C, int realBytes) {
+    return realBytes == 8 ? (C < SB200_CPT64 ? C : SB200_CPT64)
+                          : (C <= SB200_CPT32 ? C : (C == 5 || C == 6) ? 3 : SB200_CPT32);
 }
-// Lane layout of the (pattern, category) kernels: a warp holds 32/C whole patterns, category fastest.  For
-// C = 1, 2, 4, 8 that is all 32 lanes; for 3, 5 (+I+G4), 6, 7 the last 32 - (32/C)*C lanes (2, 2, 2, 4) idle: they
-// shadow lane 0's pattern so that every address they form is valid, and never store.
-__host__ __device__ constexpr int patternsPerWarp(int C) { return 32 / C; }
-__host__ __device__ constexpr int prunePatternsPerBlock(int C, int V) { return (pruneThreads(V) / 32) * patternsPerWarp(C) * pruneR(V); }
-__host__ __device__ constexpr int rootPatternsPerBlock(int C) { return (256 / 32) * patternsPerWarp(C); }
-// Maximum over the C category lanes of a pattern when C is not a power of two: lane k first holds the maximum
-// of `cover` lanes k, k+1, ... (cyclically); taking lane k+step's value, step = min(cover, C-cover), extends
-// that to cover+step lanes.  catSteps(C) rounds; catStep(C, s) is the step of round s.
-__host__ __device__ constexpr int catSteps(int C) { return C <= 1 ? 0 : C <= 2 ? 1 : C <= 4 ? 2 : 3; }
-__host__ __device__ constexpr int catStep(int C, int s) {
-    const int cover = (1 << s) < C ? (1 << s) : C;
-    return cover < C - cover ? cover : C - cover;
+__host__ __device__ constexpr int varCPT(int C, int V, int realBytes) { return V == kVarNarrow ? 1 : cptWide(C, realBytes); }
+__host__ __device__ constexpr int varNCW(int C, int V, int realBytes) { return (C + varCPT(C, V, realBytes) - 1) / varCPT(C, V, realBytes); }
+__host__ __device__ constexpr int varTP(int C, int V, int realBytes) {
+    return V == kVarNarrow ? 1
+         : V == kVarStream ? (8 / varNCW(C, V, realBytes) > 0 ? 8 / varNCW(C, V, realBytes) : 1)
+                           : (4 / varNCW(C, V, realBytes) > 0 ? 4 / varNCW(C, V, realBytes) : 1);
 }
+__host__ __device__ constexpr int varWarps(int C, int V, int realBytes) { return varNCW(C, V, realBytes) * varTP(C, V, realBytes); }
+__host__ __device__ constexpr int varThreads(int C, int V, int realBytes) { return 32 * varWarps(C, V, realBytes); }
+__host__ __device__ constexpr int varPatterns(int C, int V, int realBytes) { return 32 * varTP(C, V, realBytes); }   // patterns per block
+#ifndef SB200_REG_BUDGET
+#define SB200_REG_BUDGET 80
+#endif
+__host__ __device__ constexpr int varBlocksPerSm(int C, int V, bool tips, int realBytes) {
+    // registers per thread the kernel is compiled for: 64 for the tips-only variants, 80 otherwise
+    const int regs = tips ? 64 : SB200_REG_BUDGET;
+    const int byRegs = 65536 / (regs * varThreads(C, V, realBytes));
+    return byRegs < 1 ? 1 : byRegs > 16 ? 16 : byRegs;
+}
+__host__ __device__ constexpr int rootPatternsPerBlock() { return 128; }
 
 // Per-eigen-index model block, resident in HBM and refreshed once per evaluation.
 struct DevModel {
@@ -91,9 +108,43 @@ struct PruneArgs {
     const DevOp* ops;
     const Group* groups;
     long long tipStride;
-    int P;
     int Ppad;
     int nTips;
+    int cumMode;                     // 1: the root chain overwrites the cumulative buffer (reset fused away), 0: adds
+    int pad;
+};
+template <typename real>
+struct PruneBatch {
+    PruneArgs<real> a[kMaxBatch];
+    int groupBase[kMaxBatch];        // first group of this launch in a[z].groups
+    int groupCount[kMaxBatch];       // blocks with blockIdx.y >= groupCount[z] have nothing to do
+};
+
+struct MatJob {
+    const DevModel* model;
+    const double* rates;
+    const int* matrixIndex;
+    const double* edgeLength;
+    void* mats;
+    int count;
+    int pad;
+};
+struct MatBatch {
+    MatJob j[kMaxBatch];
+};
+
+template <typename real>
+struct TableJob {
+    const DevOp* ops;
+    const int* ttOps;
+    const real* mats;
+    real* tables;
+    int count;
+    int pad;
+};
+template <typename real>
+struct TableBatch {
+    TableJob<real> j[kMaxBatch];
 };
 
 template <typename real>
@@ -117,6 +168,12 @@ struct RootArgs {
     int parent;                      // buffer index
     int child;                       // buffer index (tip or partials)
     int matrix;
+    int blocks;                      // blocks of this evaluation (grid.x may be larger in a batch)
+    int pad;
+};
+template <typename real>
+struct RootBatch {
+    RootArgs<real> a[kMaxBatch];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -154,8 +211,8 @@ template <typename real> __device__ __forceinline__ real rmax(real a, real b) { 
 // ------------------------------------------------------------------------------------------
 // matrix image indexing (see the layout note at the top of this file)
 // ------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ constexpr int rmIndex(int C, int k, int e) { return (((e >> 1) * C + k) << 1) + (e & 1); }
-__host__ __device__ __forceinline__ constexpr int tipIndex(int C, int k, int s, int i) { return 16 * C + k * 20 + i * 5 + s; }
+__host__ __device__ __forceinline__ constexpr int pmIndex(int k, int e) { return k * kMatStride + e; }                     // P_k[i][j], e = 4i+j
+__host__ __device__ __forceinline__ constexpr int tipIndex(int k, int s, int i) { return k * kMatStride + 16 + s * 4 + i; }   // P_k[i][s]
 
 __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
@@ -175,29 +232,28 @@ __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_
 __device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
-// (a) transition matrices: one thread per (edge, category, matrix entry)
+// (a) transition matrices: one thread per (edge, category, matrix entry); blockIdx.y = evaluation of the batch
 // ------------------------------------------------------------------------------------------
 template <typename real>
 __global__ void __launch_bounds__(256)
-transition_matrices_kernel(const DevModel* __restrict__ model, const double* __restrict__ rates,
-                           const int* __restrict__ matrixIndex, const double* __restrict__ edgeLength,
-                           int count, int C, real* __restrict__ mats) {
+transition_matrices_kernel(const __grid_constant__ MatBatch B, const int C) {
     pdlLaunchDependents();
+    const MatJob& J = B.j[blockIdx.y];
     const int flat = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = flat & 15, uk = flat >> 4;
-    if (uk >= count * C) return;
+    if (uk >= J.count * C) return;
     const int u = uk / C, k = uk - u * C;
     const int i = e >> 2, j = e & 3;
-    const double t = edgeLength[u] * rates[k];
-    const double* c = model->cmat + e * 4;
+    const double t = J.edgeLength[u] * J.rates[k];
+    const double* c = J.model->cmat + e * 4;
     double sum = 0.0;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) sum += c[x] * exp(model->evals[x] * t);
+    for (int x = 0; x < 4; ++x) sum += c[x] * exp(J.model->evals[x] * t);
     const real v = static_cast<real>(sum > 0.0 ? sum : 0.0);
-    real* base = mats + static_cast<size_t>(matrixIndex[u]) * C * kMatStride;
-    base[rmIndex(C, k, e)] = v;                            // P_k[i][j]
-    base[tipIndex(C, k, j, i)] = v;                        // T[k][s=j][i]
-    if (j == 0) base[tipIndex(C, k, 4, i)] = real(1);      // missing state
+    real* base = static_cast<real*>(J.mats) + static_cast<size_t>(J.matrixIndex[u]) * C * kMatStride;
+    base[pmIndex(k, e)] = v;                               // P_k[i][j]
+    base[tipIndex(k, j, i)] = v;                           // T_k[s=j][i]
+    if (j == 0) base[tipIndex(k, 4, i)] = real(1);         // missing state
 }
 
 // ------------------------------------------------------------------------------------------
@@ -208,20 +264,22 @@ transition_matrices_kernel(const DevModel* __restrict__ model, const double* __r
 // ------------------------------------------------------------------------------------------
 template <typename real>
 __global__ void __launch_bounds__(128)
-tiptip_tables_kernel(const DevOp* __restrict__ ops, const int* __restrict__ ttOps, const real* __restrict__ mats, int C,
-                     real* __restrict__ tables) {
+tiptip_tables_kernel(const __grid_constant__ TableBatch<real> B, const int C) {
     __shared__ real tab[100 * kMaxCategories];
     __shared__ real mx[32];
     pdlLaunchDependents();
-    const DevOp op = ops[ttOps[blockIdx.x]];      // (plan data: uploaded by a copy, not produced by a kernel)
-    pdlWait();                                    // the matrices are
-    const real* ma = mats + static_cast<size_t>(op.ma) * C * kMatStride;
-    const real* mb = mats + static_cast<size_t>(op.mb) * C * kMatStride;
+    const TableJob<real>& J = B.j[blockIdx.y];
+    if (static_cast<int>(blockIdx.x) >= J.count) return;
+    const DevOp op = J.ops[J.ttOps[blockIdx.x]];      // (plan data: uploaded by a copy, not produced by a kernel)
+    pdlWait();                                        // the matrices are
+    const real* ma = J.mats + static_cast<size_t>(op.ma) * C * kMatStride;
+    const real* mb = J.mats + static_cast<size_t>(op.mb) * C * kMatStride;
     const int n = 100 * C;
+    const int TTE = ttEntry(C, sizeof(real));
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
         const int combo = q / (4 * C), rem = q - combo * 4 * C, k = rem >> 2, i = rem & 3;
         const int sA = combo / 5, sB = combo - sA * 5;
-        tab[q] = ma[tipIndex(C, k, sA, i)] * mb[tipIndex(C, k, sB, i)];
+        tab[q] = ma[tipIndex(k, sA, i)] * mb[tipIndex(k, sB, i)];
     }
     __syncthreads();
     if (threadIdx.x < 25) {
@@ -234,14 +292,14 @@ tiptip_tables_kernel(const DevOp* __restrict__ ops, const int* __restrict__ ttOp
         mx[threadIdx.x] = m;
     }
     __syncthreads();
-    real* out = tables + static_cast<size_t>(blockIdx.x) * ttStride(C);
+    real* out = J.tables + static_cast<size_t>(blockIdx.x) * ttStride(C, sizeof(real));
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        const int combo = q / (4 * C);
+        const int combo = q / (4 * C), rem = q - combo * 4 * C;
         real v = tab[q];
         if (op.flags & OP_RESCALE) v *= real(1) / mx[combo];
-        out[q] = v;
+        out[combo * TTE + rem] = v;
     }
-    if (threadIdx.x < 32) out[n + threadIdx.x] = threadIdx.x < 25 ? mx[threadIdx.x] : real(1);
+    if (threadIdx.x < 32) out[25 * TTE + threadIdx.x] = threadIdx.x < 25 ? mx[threadIdx.x] : real(1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -249,40 +307,33 @@ tiptip_tables_kernel(const DevOp* __restrict__ ops, const int* __restrict__ ttOp
 //
 // A thread block owns one tile of patterns and one *group* of operations of the current launch
 // and streams through the group as ONE software-pipelined loop.  Per step a thread
-//   - reads its category's two 4x4 matrices from shared memory (image staged by cp.async one
-//     step ahead, one __syncthreads per step),
-//   - takes operand B from registers (256-bit load or 1-byte tip state requested one step ahead),
+//   - reads the 4x4 matrices of its categories from shared memory (every lane the same words: broadcast;
+//     images staged by cp.async two steps ahead),
+//   - takes operand B from registers (256-bit loads or a 1-byte tip state requested one step ahead),
 //   - takes operand A from the partials it produced in the previous step (still in registers), or,
 //     at the start of a chain, from memory,
-//   - multiplies, rescales by the per-pattern maximum over categories and states (C-lane shuffle),
-//     writes the 4 new partials with one 256-bit store.
+//   - multiplies, rescales by the per-pattern maximum over categories and states (in registers; across the
+//     category warps of the narrow shape through shared memory), writes the new partials with 256-bit stores.
+// ONE block barrier per step, placed between the maximum and the rescaling: it publishes the next step's
+// matrix image, retires the previous one and (narrow shape) carries the maxima.
 // The log of each rescaling maximum is NOT taken per step: the maxima are multiplied into a running
 // product that is folded into a log sum only before it could underflow, chains hand (log sum,
 // product) pairs to their parents, and only the chain ending at the root takes one log per pattern.
-//     C in {1,2,4,8}: one thread per (pattern, category), R patterns per thread.
 // ------------------------------------------------------------------------------------------
-template <typename real, int C>
-__device__ __forceinline__ void factorPartial(const real* __restrict__ sm, int k, const real (&v)[4], real (&F)[4]) {
+template <typename real>
+__device__ __forceinline__ void matVec(const real* __restrict__ P, const real (&v)[4], real (&F)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        real s = sm[rmIndex(C, k, i * 4 + 0)] * v[0];
-        s += sm[rmIndex(C, k, i * 4 + 1)] * v[1];
-        s += sm[rmIndex(C, k, i * 4 + 2)] * v[2];
-        s += sm[rmIndex(C, k, i * 4 + 3)] * v[3];
+        real s = P[i * 4 + 0] * v[0];
+        s += P[i * 4 + 1] * v[1];
+        s += P[i * 4 + 2] * v[2];
+        s += P[i * 4 + 3] * v[3];
         F[i] = s;
     }
 }
 
-template <typename real, int C>
-__device__ __forceinline__ void factorTip(const real* __restrict__ sm, int k, int state, real (&F)[4]) {
-    const real* T = sm + tipIndex(C, k, state, 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) F[i] = T[i * 5];
-}
-
 // Branch-free reciprocal for the rescaling (argument is a normal number in (0, ~1]; the caller routes
 // anything smaller than 1e-290 to an exact division): hardware seed + Newton steps, < 1 ulp error.
-// Branch-free matters: it lets the compiler interleave the R independent rescalings of a thread.
 __device__ __forceinline__ double fastRcp(double m) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(m));
@@ -303,19 +354,7 @@ __device__ __forceinline__ float fastRcp(float m) {
 // Rare path of the deferred log: fold the running product (and the factor that would have
 // underflowed it) into the log sum.  Kept out of line so the hot loop carries no log() code.
 __device__ __noinline__ double foldedLog(double prod, double factor) { return log(prod) + log(factor); }
-__device__ __forceinline__ void foldProduct(double& acc, double& prod, double factor) {
-    acc += foldedLog(prod, factor);
-    prod = 1.0;
-}
 __device__ __noinline__ double scalerTotal(double acc, double prod) { return acc + log(prod); }
-
-// (acc, prod) *= factor, keeping prod >= 1e-200.  `factor` may be denormal (then prod*factor
-// rounds to 0 and the fold path takes the logs separately).
-__device__ __forceinline__ void accumulateFactor(double& acc, double& prod, double factor) {
-    const double t = prod * factor;
-    if (t < 1e-200) foldProduct(acc, prod, factor);
-    else prod = t;
-}
 
 constexpr int kOpChunk = 256;                  // operations of a group held in shared memory at a time
 #ifndef SB200_PREFETCH_AHEAD
@@ -325,45 +364,63 @@ constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // steps between an opera
 constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
 
 template <typename real, int C, int V, bool TIPS>
-__global__ void __launch_bounds__(pruneThreads(V), pruneBlocksPerSm(V, TIPS))
-prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumMode) {
-    constexpr int R = pruneR(V);
-    constexpr int kPruneThreads = pruneThreads(V);
-    constexpr int LPW = patternsPerWarp(C);              // patterns per warp
-    constexpr bool kAllLanes = LPW * C == 32;
-    constexpr bool kPow2 = (C & (C - 1)) == 0;
-    constexpr int G = (kPruneThreads / 32) * LPW;        // patterns per pass
+__global__ void __launch_bounds__(varThreads(C, V, sizeof(real)), varBlocksPerSm(C, V, TIPS, sizeof(real)))
+prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
+    constexpr int CPT = varCPT(C, V, sizeof(real));      // categories per thread
+    constexpr int NCW = varNCW(C, V, sizeof(real));      // category warps per pattern sub-tile
+    constexpr int TP = varTP(C, V, sizeof(real));        // pattern sub-tiles (32 patterns) per block
+    constexpr int THREADS = varThreads(C, V, sizeof(real));
+    constexpr int G = 32 * TP;                           // patterns per block
     constexpr int MSZ = kMatStride * C;                  // reals per operand image
     constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
     constexpr int NCH = MSZ / CHUNK;                     // 16-byte chunks per operand image
-    constexpr int TTS = ttStride(C);                     // reals per tip x tip table
+    constexpr int TTE = ttEntry(C, sizeof(real));
+    constexpr int TTS = ttStride(C, sizeof(real));       // reals per tip x tip table
     constexpr int NTT = TTS / CHUNK;                     // 16-byte chunks per table
     constexpr int IMG = TTS > 2 * MSZ ? TTS : 2 * MSZ;   // shared image of one step: two matrices OR one table
-    constexpr int NSTG = (IMG / CHUNK + kPruneThreads - 1) / kPruneThreads;   // staging chunks per thread
-    constexpr unsigned TILE_BYTES = G * R * C * 4 * sizeof(real);
+    constexpr int NSTG = (IMG / CHUNK + THREADS - 1) / THREADS;   // staging chunks per thread
+    constexpr bool kSingleWarp = THREADS == 32;
     __shared__ __align__(16) real sm[2][IMG];
     __shared__ int4 sops[kOpChunk * kOpWords];
-    __shared__ double sAcc[R][kPruneThreads];            // log part of the running scaler (touched rarely)
+    __shared__ double sAcc[THREADS];                     // log part of the running scaler (touched rarely)
+    __shared__ real smax[2][NCW > 1 ? THREADS : 1];      // narrow shape: per-warp maxima of a step, double-buffered
 
+#ifdef SB200_Z0
+    const int z = 0;
+#else
+    const int z = blockIdx.z;
+#endif
+    pdlLaunchDependents();
+    if (static_cast<int>(blockIdx.y) >= B.groupCount[z]) return;
+    const PruneArgs<real>& A = B.a[z];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const bool active = kAllLanes || lane < LPW * C;     // (idle lanes shadow the warp's first pattern, category 0)
-    const int k = active ? lane % C : 0;
-    const int g = (tid >> 5) * LPW + (active ? lane / C : 0);
-    int catSrc[3];                                       // source lanes of the category maximum (C not a power of two)
-#pragma unroll
-    for (int s = 0; s < 3; ++s) catSrc[s] = lane - k + (k + catStep(C, s)) % C;
-    pdlLaunchDependents();
-    const Group grp = A.groups[groupBase + blockIdx.y];
+    const int warp = tid >> 5;
+    const int kb = (warp % NCW) * CPT;                   // first category of this thread
+    const int sp = warp / NCW;                           // pattern sub-tile of this warp
+    constexpr bool kEven = NCW * CPT == C;               // otherwise the last category warp repeats category C-1 in its spare slots
+    const bool scalerWarp = NCW == 1 || kb == 0;         // the warp that keeps a pattern's log-scalers
+    const Group grp = A.groups[B.groupBase[z] + blockIdx.y];
     const int nOps = grp.opEnd - grp.opStart;
     const int Ppad = A.Ppad;
-    const size_t tile0 = static_cast<size_t>(blockIdx.x) * (G * R);   // first pattern of this block's tile
-    const size_t bufStride = static_cast<size_t>(Ppad) * C * 4;
-    real* const pmine = A.partials + ((tile0 + g) * C + k) * 4;       // r-th pattern of this thread: + r*G*C*4
-    const uint8_t* const tmine = A.tips + tile0 + g;
-    double* const accMine = A.slotAcc + tile0 + g;
-    double* const prodMine = A.slotProd + tile0 + g;
+    const int nTips = A.nTips;
+    const size_t tile0 = static_cast<size_t>(blockIdx.x) * G;       // first pattern of this block's tile
+    const size_t pat = tile0 + sp * 32 + lane;                      // this thread's pattern
+    const size_t catStride = static_cast<size_t>(Ppad) * 4;         // reals between categories
+    const size_t bufStride = catStride * C;
+    auto kcat = [&](int c) { return kEven ? kb + c : min(kb + c, C - 1); };               // category of slot c
+    auto catOff = [&](int c) { return static_cast<size_t>(kcat(c) - kb) * catStride; };     // ... relative to pmine
+    real* const pmine = A.partials + (static_cast<size_t>(kb) * Ppad + pat) * 4;   // category c of this thread: + c*catStride
+    const uint8_t* const tmine = A.tips + pat;
+    double* const accMine = A.slotAcc + pat;
+    double* const prodMine = A.slotProd + pat;
+    const long long tipStride = A.tipStride;
+    const real* const mats = A.mats;
 
+    auto blockSync = [&]() {
+        if (kSingleWarp) __syncwarp();
+        else __syncthreads();
+    };
     // ---- helpers ---------------------------------------------------------------------------
     // matrix images (or the tip x tip table) of one operation -> sm[buf], 16 bytes per cp.async
     auto stage = [&](int buf, const int4& w0, const int4& w1, int tt) {
@@ -371,331 +428,278 @@ prune_chains_kernel(const PruneArgs<real> A, const int groupBase, const int cumM
             const real* src = A.ttTables + static_cast<size_t>(tt) * TTS;
 #pragma unroll
             for (int s = 0; s < NSTG; ++s) {
-                const int c = tid + s * kPruneThreads;
+                const int c = tid + s * THREADS;
                 if (c < NTT) cpAsync16(&sm[buf][c * CHUNK], src + c * CHUNK);
             }
         } else {
 #pragma unroll
             for (int s = 0; s < NSTG; ++s) {
-                const int c = tid + s * kPruneThreads;
+                const int c = tid + s * THREADS;
                 if (c < 2 * NCH) {
                     const int o = c >= NCH ? 1 : 0;
-                    cpAsync16(&sm[buf][c * CHUNK], A.mats + static_cast<size_t>(o ? w1.x : w0.z) * MSZ + (c - o * NCH) * CHUNK);
+                    cpAsync16(&sm[buf][c * CHUNK], mats + static_cast<size_t>(o ? w1.x : w0.z) * MSZ + (c - o * NCH) * CHUNK);
                 }
             }
         }
         cpAsyncCommit();
     };
-    auto fetchTip = [&](int src, int (&state)[R]) {
-        const uint8_t* t = tmine + static_cast<size_t>(src) * A.tipStride;
+    auto fetchPartial = [&](int src, real (&v)[CPT][4]) {
+        const real* base = pmine + static_cast<size_t>(src - nTips) * bufStride;
 #pragma unroll
-        for (int r = 0; r < R; ++r) state[r] = t[r * G];
+        for (int c = 0; c < CPT; ++c) ld4(base + catOff(c), v[c]);
     };
-    auto fetchPartial = [&](int src, real (&v)[R][4]) {
-        const real* base = pmine + static_cast<size_t>(src - A.nTips) * bufStride;
-#pragma unroll
-        for (int r = 0; r < R; ++r) ld4(base + r * (G * C * 4), v[r]);
-    };
-    auto loadSlot = [&](int slot, double (&a)[R], double (&pr)[R]) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            a[r] = accMine[static_cast<size_t>(slot) * Ppad + r * G];
-            pr[r] = prodMine[static_cast<size_t>(slot) * Ppad + r * G];
-        }
-    };
-    // L2 prefetch of everything an operation will read from HBM (one bulk request per tile, issued by one
-    // thread kPrefetchAhead steps early): the register loads one step ahead then hit L2.  (Dealing the requests
-    // to lane 0 of different warps was measured and is slower: 104.9 vs 101.3 us on rbcl738.)
-    // Bulk requests are 16-byte granular: the 1-byte tip codes of a tile that does not start / end on such a
-    // boundary are asked for with the neighbouring bytes; rows are padded to a multiple of 16.
-    constexpr bool kTipAligned = (G * R) % 16 == 0;
-    const size_t tipLo = kTipAligned ? tile0 : (tile0 & ~static_cast<size_t>(15));
-    const unsigned tipBytes = kTipAligned ? G * R : static_cast<unsigned>(((tile0 + G * R + 15) & ~static_cast<size_t>(15)) - tipLo);
+    // L2 prefetch of everything an operation will read from HBM (bulk requests per tile, issued by a few threads
+    // kPrefetchAhead steps early): the register loads one step ahead then hit L2.  Requests are 16-byte granular
+    // (a tile of 32*TP one-byte tip codes or 8-byte scalers always is).
     auto prefetchOperands = [&](const int4& w0, const int4& w1) {
-        const real* ptile = A.partials + tile0 * C * 4;
-        if (TIPS || (w1.w & OP_B_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * A.tipStride + tipLo, tipBytes);
-        else bulkPrefetchL2(ptile + static_cast<size_t>(w0.w - A.nTips) * bufStride, TILE_BYTES);
-        if (!TIPS && w1.z >= 0) {
-            bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
-            bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.z) * Ppad + tile0, G * R * 8);
-        }
-        if (w1.w & OP_CHAIN_START) {
-            if (TIPS || (w1.w & OP_A_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * A.tipStride + tipLo, tipBytes);
-            else bulkPrefetchL2(ptile + static_cast<size_t>(w0.y - A.nTips) * bufStride, TILE_BYTES);
-            if (!TIPS && w1.y >= 0) {
-                bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
-                bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.y) * Ppad + tile0, G * R * 8);
+        // thread q < C asks for category q of the partials operand(s); thread C for the tips and scalers
+        if (tid < C) {
+            const real* ptile = A.partials + (static_cast<size_t>(tid) * Ppad + tile0) * 4;
+            constexpr unsigned kTileBytes = G * 4 * sizeof(real);
+            if (!TIPS && !(w1.w & OP_B_TIP)) bulkPrefetchL2(ptile + static_cast<size_t>(w0.w - nTips) * bufStride, kTileBytes);
+            if (!TIPS && (w1.w & OP_CHAIN_START) && !(w1.w & OP_A_TIP))
+                bulkPrefetchL2(ptile + static_cast<size_t>(w0.y - nTips) * bufStride, kTileBytes);
+        } else if (tid == C) {
+            if (TIPS || (w1.w & OP_B_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * tipStride + tile0, G);
+            if (!TIPS && w1.z >= 0) {
+                bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.z) * Ppad + tile0, G * 8);
+                bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.z) * Ppad + tile0, G * 8);
+            }
+            if (w1.w & OP_CHAIN_START) {
+                if (TIPS || (w1.w & OP_A_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * tipStride + tile0, G);
+                if (!TIPS && w1.y >= 0) {
+                    bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.y) * Ppad + tile0, G * 8);
+                    bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.y) * Ppad + tile0, G * 8);
+                }
             }
         }
     };
 
-    const bool writer = active && k == 0;               // the lane that stores a pattern's scalers
-    real X[R][4], Y[R][4];
-    int sX[R], sY[R];
-    double prod[R], pendAcc[R], pendProd[R];             // pend*: scaler of the next step's sibling chain, if any
-#pragma unroll
-    for (int r = 0; r < R; ++r) { sAcc[r][tid] = 0.0; prod[r] = 1.0; pendAcc[r] = 0.0; pendProd[r] = 1.0; sX[r] = 0; sY[r] = 0; }
+    real X[CPT][4], Y[CPT][4];
+    int sX = 0, sY = 0;
+    double prod = 1.0, pendAcc = 0.0, pendProd = 1.0;    // pend*: scaler of the next step's sibling chain, if any
+    sAcc[tid] = 0.0;
 
+    // (acc, prod) *= factor, keeping prod >= 1e-200.  `factor` may be denormal (then prod*factor rounds to 0 and
+    // the fold path takes the logs separately).
+    auto accumulate = [&](double addAcc, double factor) {
+        const double t = prod * factor;
+        if (addAcc != 0.0) sAcc[tid] += addAcc;
+        if (t < 1e-200) {
+            sAcc[tid] += foldedLog(prod, factor);
+            prod = 1.0;
+        } else {
+            prod = t;
+        }
+    };
     // operand A of a chain start, and the scaler of the chain that produced it
     auto startChain = [&](const int4& w0, const int4& w1) {
-        if (TIPS || (w1.w & OP_A_TIP)) fetchTip(w0.y, sX);
+        if (TIPS || (w1.w & OP_A_TIP)) sX = tmine[static_cast<size_t>(w0.y) * tipStride];
         else fetchPartial(w0.y, X);
-        if (!TIPS && w1.y >= 0) {
-            double a[R], pr[R];
-            loadSlot(w1.y, a, pr);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double acc = sAcc[r][tid] + a[r];
-                accumulateFactor(acc, prod[r], pr[r]);
-                sAcc[r][tid] = acc;
-            }
+        if (!TIPS && w1.y >= 0 && scalerWarp) {
+            const double a = accMine[static_cast<size_t>(w1.y) * Ppad];
+            const double pr = prodMine[static_cast<size_t>(w1.y) * Ppad];
+            accumulate(a, pr);
         }
     };
     // operand B (and its chain's scaler) of an operation, one step ahead of its use
     auto fetchB = [&](const int4& w0, const int4& w1) {
-        if (TIPS || (w1.w & OP_B_TIP)) fetchTip(w0.w, sY);
+        if (TIPS || (w1.w & OP_B_TIP)) sY = tmine[static_cast<size_t>(w0.w) * tipStride];
         else fetchPartial(w0.w, Y);
-        if (!TIPS && w1.z >= 0) loadSlot(w1.z, pendAcc, pendProd);
+        if (!TIPS && w1.z >= 0 && scalerWarp) {
+            pendAcc = accMine[static_cast<size_t>(w1.z) * Ppad];
+            pendProd = prodMine[static_cast<size_t>(w1.z) * Ppad];
+        }
     };
 
-    // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
 #ifdef SB200_TRACE
 #ifndef SB200_TRACE_TID
 #define SB200_TRACE_TID 0
 #endif
-#define SB200_TICK(slot) if (A.trace && tid == SB200_TRACE_TID && blockIdx.x == 0 && blockIdx.y == 0 && j < 60) A.trace[j * 8 + (slot)] = clock64();
+#define SB200_TICK(slot) if (A.trace && tid == SB200_TRACE_TID && blockIdx.x == 0 && blockIdx.y == 0 && z == 0 && j < 60) A.trace[j * 8 + (slot)] = clock64();
 #else
 #define SB200_TICK(slot)
 #endif
-    auto step = [&](const int j, const int nc, const int4& w0, const int4& w1, const int4& n0, const int4& n1) {
+    // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
+    // On entry image j is visible to the whole block and image j+1 is on its way.
+    auto step = [&](const int j, const int nc) {
         SB200_TICK(0)
-        cpAsyncWaitAll();
-        SB200_TICK(1)
-        __syncthreads();          // images of step j visible; everyone is done with step j-1's image
-        SB200_TICK(2)
         const bool more = j + 1 < nc;
+        const int4 w0 = sops[j * kOpWords], w1 = sops[j * kOpWords + 1];
         const int flags = w1.w;
-        if (more) stage((j + 1) & 1, n0, n1, (n1.w & OP_TIPTIP) ? sops[(j + 1) * kOpWords + 2].y : -1);
-        if (kPrefetchAhead > 0 && tid == 0 && j + 1 + kPrefetchAhead < nc)
+        if (kPrefetchAhead > 0 && tid <= C && j + 1 + kPrefetchAhead < nc)
             prefetchOperands(sops[(j + 1 + kPrefetchAhead) * kOpWords], sops[(j + 1 + kPrefetchAhead) * kOpWords + 1]);
         const real* sa = sm[j & 1];
         const real* sb = sa + MSZ;
-        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
-        double mfac[R];                                      // this step's rescaling maxima (1 when not rescaled)
-        SB200_TICK(6)
+        double mfac;                                         // this step's rescaling maximum (1 when not rescaled)
+        real m = real(1);
 
         if (flags & OP_TIPTIP) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
-            int combo[R];
+            const int combo = sX * 5 + sY;
+            if (more) fetchB(sops[(j + 1) * kOpWords], sops[(j + 1) * kOpWords + 1]);
+            const real* T = sa + combo * TTE;
 #pragma unroll
-            for (int r = 0; r < R; ++r) combo[r] = sX[r] * 5 + sY[r];
-            if (more) fetchB(n0, n1);
+            for (int c = 0; c < CPT; ++c) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const real* T = sa + (combo[r] * C + k) * 4;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) X[r][i] = T[i];
-                mfac[r] = static_cast<double>(sa[100 * C + combo[r]]);
+                for (int i = 0; i < 4; ++i) X[c][i] = T[kcat(c) * 4 + i];
             }
+            mfac = static_cast<double>(sa[25 * TTE + combo]);
         } else {
-            // factor of operand A (from registers, or tip table at a chain start), then operand B
+            // factor of operand A (from registers, or a column of P at a chain start with a tip), then operand B
             if (!TIPS && (flags & OP_A_TIP)) {       // (TIPS: a chain start with a tip for A is a tip x tip operation)
 #pragma unroll
-                for (int r = 0; r < R; ++r) factorTip<real, C>(sa, k, sX[r], X[r]);
+                for (int c = 0; c < CPT; ++c) {
+                    const real* T = sa + tipIndex(kcat(c), sX, 0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X[c][i] = T[i];
+                }
             } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
+                for (int c = 0; c < CPT; ++c) {
                     real F[4];
-                    factorPartial<real, C>(sa, k, X[r], F);
+                    matVec<real>(sa + pmIndex(kcat(c), 0), X[c], F);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[r][i] = F[i];
+                    for (int i = 0; i < 4; ++i) X[c][i] = F[i];
                 }
             }
-            SB200_TICK(7)
+            SB200_TICK(1)
             if (TIPS || (flags & OP_B_TIP)) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    real F[4];
-                    factorTip<real, C>(sb, k, sY[r], F);
+                for (int c = 0; c < CPT; ++c) {
+                    const real* T = sb + tipIndex(kcat(c), sY, 0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
+                    for (int i = 0; i < 4; ++i) X[c][i] *= T[i];
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
+                for (int c = 0; c < CPT; ++c) {
                     real F[4];
-                    factorPartial<real, C>(sb, k, Y[r], F);
+                    matVec<real>(sb + pmIndex(kcat(c), 0), Y[c], F);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[r][i] *= F[i];
+                    for (int i = 0; i < 4; ++i) X[c][i] *= F[i];
                 }
             }
-            if (!TIPS && w1.z >= 0) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    double acc = sAcc[r][tid] + pendAcc[r];
-                    accumulateFactor(acc, prod[r], pendProd[r]);
-                    sAcc[r][tid] = acc;
-                }
-            }
-            SB200_TICK(3)
+            if (!TIPS && w1.z >= 0 && scalerWarp) accumulate(pendAcc, pendProd);
+            SB200_TICK(2)
             // next step's operand B is requested now; the rescaling below hides its latency
-            if (more) fetchB(n0, n1);
-
+            if (more) fetchB(sops[(j + 1) * kOpWords], sops[(j + 1) * kOpWords + 1]);
             if (flags & OP_RESCALE) {
-                // stage-major over the R patterns: R independent dependency chains, no branch in between
-                real m[R];
+                m = rmax(rmax(X[0][0], X[0][1]), rmax(X[0][2], X[0][3]));
 #pragma unroll
-                for (int r = 0; r < R; ++r) m[r] = rmax(rmax(X[r][0], X[r][1]), rmax(X[r][2], X[r][3]));
-                if (kPow2) {
-#pragma unroll
-                    for (int off = 1; off < C; off <<= 1) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_xor_sync(0xffffffffu, m[r], off));
-                    }
-                } else {
-#pragma unroll
-                    for (int s = 0; s < catSteps(C); ++s) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) m[r] = rmax(m[r], __shfl_sync(0xffffffffu, m[r], catSrc[s]));
-                    }
-                }
-                // below this the hardware reciprocal seed (flush-to-zero) is not usable: exact division instead
-                constexpr real kTiny = sizeof(real) == 4 ? real(1e-30) : real(1e-290);
-                bool tiny = false;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    m[r] = (m[r] == real(0)) ? real(1) : m[r];
-                    tiny |= m[r] < kTiny;
-                }
-                real inv[R];
-                if (!tiny) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) inv[r] = fastRcp(m[r]);
-                } else {                                     // denormal-range maximum: exact division
-#pragma unroll
-                    for (int r = 0; r < R; ++r) inv[r] = real(1) / m[r];
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) X[r][i] *= inv[r];
-                    mfac[r] = static_cast<double>(m[r]);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) mfac[r] = 1.0;
+                for (int c = 1; c < CPT; ++c) m = rmax(m, rmax(rmax(X[c][0], X[c][1]), rmax(X[c][2], X[c][3])));
+                if (NCW > 1) smax[j & 1][tid] = m;
             }
+            mfac = 1.0;
         }
+        SB200_TICK(3)
+        if (more) cpAsyncWaitAll();   // (my part of) image j+1 has landed
+        blockSync();                  // image j+1 and this step's maxima visible; everyone is done with image j
         SB200_TICK(4)
-        if (active) {
-            if (flags & OP_CHAIN_END) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) st4(dest + r * (G * C * 4), X[r]);
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) st4Stream(dest + r * (G * C * 4), X[r]);
-            }
+        if (j + 2 < nc) {
+            const int4 s0 = sops[(j + 2) * kOpWords], s1 = sops[(j + 2) * kOpWords + 1];
+            stage(j & 1, s0, s1, (s1.w & OP_TIPTIP) ? sops[(j + 2) * kOpWords + 2].y : -1);
         }
-        {
-            // deferred log: multiply the maxima, fold into the log sum only before an underflow
-            double t[R];
-            bool low = false;
+        if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) {
+            if (NCW > 1) {
+                const real* q = &smax[j & 1][(sp * NCW) * 32 + lane];
+                m = q[0];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                t[r] = prod[r] * mfac[r];
-                low |= t[r] < 1e-200;
+                for (int w = 1; w < NCW; ++w) m = rmax(m, q[w * 32]);
             }
-            if (!low) {
+            // below kTiny the hardware reciprocal seed (flush-to-zero) is not usable: exact division instead
+            constexpr real kTiny = sizeof(real) == 4 ? real(1e-30) : real(1e-290);
+            m = (m == real(0)) ? real(1) : m;
+            const real inv = (m < kTiny) ? real(1) / m : fastRcp(m);
 #pragma unroll
-                for (int r = 0; r < R; ++r) prod[r] = t[r];
-            } else {
+            for (int c = 0; c < CPT; ++c) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (t[r] < 1e-200) {
-                        sAcc[r][tid] += foldedLog(prod[r], mfac[r]);
-                        prod[r] = 1.0;
-                    } else {
-                        prod[r] = t[r];
-                    }
-                }
+                for (int i = 0; i < 4; ++i) X[c][i] *= inv;
             }
+            mfac = static_cast<double>(m);
         }
-        if (flags & OP_STORE_S) {
-            // incremental plans: every node keeps the log-scaler of its subtree (the chain carries on)
-            const int sKeep = sops[j * kOpWords + 2].x;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double a = sAcc[r][tid], pr = prod[r];
-                if (pr < 1e-100) {
-                    a += foldedLog(pr, 1.0);
-                    pr = 1.0;
-                }
-                if (writer) {
-                    accMine[static_cast<size_t>(sKeep) * Ppad + r * G] = a;
-                    prodMine[static_cast<size_t>(sKeep) * Ppad + r * G] = pr;
-                }
-            }
-        }
-        if (flags & OP_CHAIN_END) {
-            const int sOut = sops[j * kOpWords + 2].x;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double a = sAcc[r][tid];
-                if (sOut >= 0) {
-                    if (prod[r] < 1e-100) {                 // keep a parent's product of two stored factors normal
-                        a += foldedLog(prod[r], 1.0);
-                        prod[r] = 1.0;
-                    }
-                    if (writer) {
-                        accMine[static_cast<size_t>(sOut) * Ppad + r * G] = a;
-                        prodMine[static_cast<size_t>(sOut) * Ppad + r * G] = prod[r];
-                    }
-                }
-                if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr && writer) {
-                    const double total = scalerTotal(a, prod[r]);
-                    double* c = A.cum + tile0 + g + r * G;
-                    if (cumMode) *c = total;
-                    else *c += total;
-                }
-                sAcc[r][tid] = 0.0;
-                prod[r] = 1.0;
-            }
-        }
-        if (more && (n1.w & OP_CHAIN_START)) startChain(n0, n1);
         SB200_TICK(5)
+        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
+        if (flags & OP_CHAIN_END) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+                if (kEven || kb + c < C) st4(dest + catOff(c), X[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+                if (kEven || kb + c < C) st4Stream(dest + catOff(c), X[c]);
+        }
+        if (scalerWarp) {
+            // deferred log: multiply the maxima, fold into the log sum only before an underflow
+            {
+                const double t = prod * mfac;
+                if (t < 1e-200) {
+                    sAcc[tid] += foldedLog(prod, mfac);
+                    prod = 1.0;
+                } else {
+                    prod = t;
+                }
+            }
+            if (flags & (OP_STORE_S | OP_CHAIN_END)) {
+                // a chain end hands its subtree log-scaler to the parent chain (and resets); incremental plans keep
+                // every node's (OP_STORE_S: store and carry on)
+                const int sOut = sops[j * kOpWords + 2].x;
+                double a = sAcc[tid];
+                if (sOut >= 0) {
+                    if (prod < 1e-100) {                     // keep a parent's product of two stored factors normal
+                        a += foldedLog(prod, 1.0);
+                        prod = 1.0;
+                        if (!(flags & OP_CHAIN_END)) sAcc[tid] = a;
+                    }
+                    accMine[static_cast<size_t>(sOut) * Ppad] = a;
+                    prodMine[static_cast<size_t>(sOut) * Ppad] = prod;
+                }
+                if (flags & OP_CHAIN_END) {
+                    if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr) {
+                        const double total = scalerTotal(a, prod);
+                        double* c = A.cum + pat;
+                        if (A.cumMode) *c = total;
+                        else *c += total;
+                    }
+                    sAcc[tid] = 0.0;
+                    prod = 1.0;
+                }
+            }
+        }
+        if (more) {
+            const int4 n1 = sops[(j + 1) * kOpWords + 1];
+            if (n1.w & OP_CHAIN_START) startChain(sops[(j + 1) * kOpWords], n1);
+        }
+        SB200_TICK(6)
     };
 
     // ---- the group, a chunk of operations at a time (one chunk unless the group is very long) ---------
     for (int chunk0 = 0; chunk0 < nOps; chunk0 += kOpChunk) {
         const int nc = min(kOpChunk, nOps - chunk0);
-        if (chunk0 > 0) __syncthreads();
+        if (chunk0 > 0) blockSync();
         {
             const int4* gops = reinterpret_cast<const int4*>(A.ops + grp.opStart + chunk0);
-            for (int w = tid; w < nc * kOpWords; w += kPruneThreads) sops[w] = gops[w];
+            for (int w = tid; w < nc * kOpWords; w += THREADS) sops[w] = gops[w];
         }
-        __syncthreads();
+        blockSync();
         if (chunk0 == 0) pdlWait();   // the plan is in shared memory; everything below reads what earlier kernels wrote
-        int4 a0 = sops[0], a1 = sops[1];
+        const int4 a0 = sops[0], a1 = sops[1];
         stage(0, a0, a1, (a1.w & OP_TIPTIP) ? sops[2].y : -1);
+        if (nc > 1) {
+            const int4 s0 = sops[kOpWords], s1 = sops[kOpWords + 1];
+            stage(1, s0, s1, (s1.w & OP_TIPTIP) ? sops[kOpWords + 2].y : -1);
+        }
         if (a1.w & OP_CHAIN_START) startChain(a0, a1);       // (a later chunk may begin in mid-chain: A is carried)
         fetchB(a0, a1);
-        if (kPrefetchAhead > 0 && tid == 0) {
+        if (kPrefetchAhead > 0 && tid <= C) {
 #pragma unroll
             for (int a = 1; a <= kPrefetchAhead; ++a)
                 if (a < nc) prefetchOperands(sops[a * kOpWords], sops[a * kOpWords + 1]);
         }
-        // two steps per iteration with the operation words ping-ponging between (a0,a1) and (b0,b1): no copies
-        int j = 0;
-        for (; j + 1 < nc; j += 2) {
-            const int4 b0 = sops[(j + 1) * kOpWords], b1 = sops[(j + 1) * kOpWords + 1];
-            step(j, nc, a0, a1, b0, b1);
-            if (j + 2 < nc) {
-                a0 = sops[(j + 2) * kOpWords];
-                a1 = sops[(j + 2) * kOpWords + 1];
-            }
-            step(j + 1, nc, b0, b1, a0, a1);
-        }
-        if (j < nc) step(j, nc, a0, a1, a0, a1);
+        cpAsyncWaitAll();
+        blockSync();                  // images 0 and 1 visible
+#pragma unroll 1
+        for (int j = 0; j < nc; ++j) step(j, nc);
     }
 }
 
@@ -727,7 +731,7 @@ __device__ __forceinline__ double warpSum(double v) {
 // Block-level sum of `v` (fixed order), then the last block to finish adds the per-block sums in
 // index order, so the result does not depend on scheduling.
 template <int THREADS>
-__device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums, unsigned int* ticket, double* out,
+__device__ __forceinline__ void blockReduceAndFinish(double v, int nBlocks, double* blockSums, unsigned int* ticket, double* out,
                                                      unsigned long long* doneFlag, unsigned long long doneSeq) {
     __shared__ double warpPart[THREADS / 32];
     __shared__ bool isLast;
@@ -742,13 +746,13 @@ __device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums
         blockSums[blockIdx.x] = s;
         __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
-        isLast = (t == gridDim.x - 1);
+        isLast = (t == static_cast<unsigned int>(nBlocks) - 1u);
     }
     __syncthreads();
     if (isLast && w == 0) {
         __threadfence();
         double s = 0.0;
-        for (unsigned int i = lane; i < gridDim.x; i += 32) s += reinterpret_cast<volatile double*>(blockSums)[i];
+        for (int i = lane; i < nBlocks; i += 32) s += reinterpret_cast<volatile double*>(blockSums)[i];
         s = warpSum(s);
         if (lane == 0) {
             *out = s;
@@ -761,75 +765,72 @@ __device__ __forceinline__ void blockReduceAndFinish(double v, double* blockSums
     }
 }
 
-// Shared-memory tables of the root edge: W[k][s][i] = pi_i * w_k * P_k[i][s] (tip child),
-// M[k][i][j] = P_k[i][j] and fw[k][i] = pi_i * w_k (partials child).
-template <typename real, int C, int THREADS>
-__device__ __forceinline__ void loadRootTables(const RootArgs<real>& A, double* W, double* M, double* fw) {
-    const int tid = threadIdx.x;
-    const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
-    for (int q = tid; q < C * 20; q += THREADS) {
-        const int kk = q / 20, e = q - kk * 20, s = e >> 2, i = e & 3;
-        W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[tipIndex(C, kk, s, i)]);
-    }
-    for (int q = tid; q < C * 16; q += THREADS) M[q] = static_cast<double>(mat[rmIndex(C, q >> 4, q & 15)]);
-    for (int q = tid; q < C * 4; q += THREADS) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
-    __syncthreads();
-}
-
+// thread = pattern; the categories are added in category order inside the thread
 template <typename real, int C>
-__global__ void __launch_bounds__(256)
-root_loglik_kernel(const RootArgs<real> A) {
-    constexpr int LPW = patternsPerWarp(C);
-    constexpr int G = rootPatternsPerBlock(C);
-    constexpr bool kPow2 = (C & (C - 1)) == 0;
-    __shared__ double W[C * 20];
-    __shared__ double M[C * 16];
-    __shared__ double fw[C * 4];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const bool active = LPW * C == 32 || lane < LPW * C;  // (idle lanes shadow the warp's first pattern)
-    const int k = active ? lane % C : 0, g = (tid >> 5) * LPW + (active ? lane / C : 0);
-    const bool childTip = A.child < A.nTips;
+__global__ void __launch_bounds__(rootPatternsPerBlock())
+root_loglik_kernel(const __grid_constant__ RootBatch<real> B) {
+    constexpr int THREADS = rootPatternsPerBlock();
+    __shared__ double W[C * 20];             // W[k][s][i] = pi_i * w_k * P_k[i][s]   (tip child)
+    __shared__ double M[C * 16];             // M[k][i][j] = P_k[i][j]                 (partials child)
+    __shared__ double fw[C * 4];             // fw[k][i] = pi_i * w_k
     pdlLaunchDependents();
+    const RootArgs<real>& A = B.a[blockIdx.y];
+    if (static_cast<int>(blockIdx.x) >= A.blocks) return;
+    const int tid = threadIdx.x;
+    const bool childTip = A.child < A.nTips;
     pdlWait();
-    loadRootTables<real, C, 256>(A, W, M, fw);
-
-    const int p = blockIdx.x * G + g;                     // < Ppad
-    const size_t bufStride = static_cast<size_t>(A.Ppad) * C * 4;
-    real par[4];
-    ld4(A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + (static_cast<size_t>(p) * C + k) * 4, par);
-    double term = 0.0;
+    {
+        const real* mat = A.mats + static_cast<size_t>(A.matrix) * C * kMatStride;
+        for (int q = tid; q < C * 20; q += THREADS) {
+            const int kk = q / 20, e = q - kk * 20, s = e >> 2, i = e & 3;
+            W[q] = A.model->freqs[i] * A.catWeights[kk] * static_cast<double>(mat[tipIndex(kk, s, i)]);
+        }
+        for (int q = tid; q < C * 16; q += THREADS) M[q] = static_cast<double>(mat[pmIndex(q >> 4, q & 15)]);
+        for (int q = tid; q < C * 4; q += THREADS) fw[q] = A.model->freqs[q & 3] * A.catWeights[q >> 2];
+        __syncthreads();
+    }
+    const int p = blockIdx.x * THREADS + tid;             // < Ppad
+    const size_t catStride = static_cast<size_t>(A.Ppad) * 4;
+    const size_t bufStride = catStride * C;
+    const real* par = A.partials + static_cast<size_t>(A.parent - A.nTips) * bufStride + static_cast<size_t>(p) * 4;
+    double site = 0.0;
     if (childTip) {
         const int s = A.tips[static_cast<size_t>(A.child) * A.tipStride + p];
-        const double* w = W + (k * 5 + s) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) term += static_cast<double>(par[i]) * w[i];
+        for (int k = 0; k < C; ++k) {
+            real pv[4];
+            ld4(par + k * catStride, pv);
+            const double* w = W + (k * 5 + s) * 4;
+            double term = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) term += static_cast<double>(pv[i]) * w[i];
+            site += term;
+        }
     } else {
-        real chv[4];
-        ld4(A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + (static_cast<size_t>(p) * C + k) * 4, chv);
+        const real* chp = A.partials + static_cast<size_t>(A.child - A.nTips) * bufStride + static_cast<size_t>(p) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double sj = 0.0;
+        for (int k = 0; k < C; ++k) {
+            real pv[4], chv[4];
+            ld4(par + k * catStride, pv);
+            ld4(chp + k * catStride, chv);
+            double term = 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sj += M[k * 16 + i * 4 + j] * static_cast<double>(chv[j]);
-            term += sj * static_cast<double>(par[i]) * fw[k * 4 + i];
+            for (int i = 0; i < 4; ++i) {
+                double sj = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sj += M[k * 16 + i * 4 + j] * static_cast<double>(chv[j]);
+                term += sj * static_cast<double>(pv[i]) * fw[k * 4 + i];
+            }
+            site += term;
         }
     }
-    if (kPow2) {
-#pragma unroll
-        for (int off = 1; off < C; off <<= 1) term += __shfl_xor_sync(0xffffffffu, term, off);
-    } else {                                              // category 0's lane adds the C terms in category order
-        const double mine = term;
-        term = 0.0;
-#pragma unroll
-        for (int j = 0; j < C; ++j) term += __shfl_sync(0xffffffffu, mine, lane - k + j);
-    }
     double v = 0.0;
-    if (active && k == 0 && p < A.P) {
-        double ll = log(term);
+    if (p < A.P) {
+        double ll = log(site);
         if (A.cum) ll += A.cum[p];
         v = ll * A.patWeights[p];
     }
-    blockReduceAndFinish<256>(v, A.blockSums, A.ticket, A.out, A.doneFlag, A.doneSeq);
+    blockReduceAndFinish<THREADS>(v, A.blocks, A.blockSums, A.ticket, A.out, A.doneFlag, A.doneSeq);
 }
 
 }  // namespace sb200

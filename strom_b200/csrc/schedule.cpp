@@ -32,6 +32,16 @@ static void assignTipTipTables(Schedule& out, int tipCount) {
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
                   int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out,
                   bool keepSubtreeScalers, int groupsTipsLevel) {
+    if (groupsPerLevel < 1) groupsPerLevel = 1;
+    const LevelPolicy fixed = [=](int, bool tipsCandidate) {
+        return LevelChoice{0, (groupsTipsLevel > 0 && tipsCandidate) ? groupsTipsLevel : groupsPerLevel};
+    };
+    return buildSchedule(ops, count, tipCount, partialsBufferCount, matrixCount, scaleCount, accumulate, fixed, out, keepSubtreeScalers);
+}
+
+int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
+                  int matrixCount, int scaleCount, bool accumulate, const LevelPolicy& policy, Schedule& out,
+                  bool keepSubtreeScalers) {
     out = Schedule();
     const int nbuf = tipCount + partialsBufferCount;
     if (count < 0) return BEAGLE_ERROR_OUT_OF_RANGE;
@@ -96,7 +106,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             out.ops.push_back(makeOp(op.destinationPartials - tipCount, op.child1Partials, op.child1TransitionMatrix,
                                      op.child2Partials, op.child2TransitionMatrix, -1, -1, fl, -1));
             out.chains.push_back(DevChain{o, 1, -1, (accumulate && rescale) ? CHAIN_ADD_TO_CUM : 0});
-            out.levels.push_back(Level{o, 1, o, 1, 0});
+            out.levels.push_back(Level{o, 1, o, 1, 0, policy(1, false).variant});
             out.groups.push_back(Group{o, o + 1});
             out.opLevel[o] = o;
             out.opChain[o] = o;
@@ -185,7 +195,6 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
     int maxLevel = -1;
     for (int l : chainLevel) maxLevel = std::max(maxLevel, l);
     std::vector<int> chainNewId(nChains, -1);
-    if (groupsPerLevel < 1) groupsPerLevel = 1;
     // chains of every level, in chain order
     std::vector<int> levelBegin(maxLevel + 2, 0), byLevel(nChains);
     for (int c = 0; c < nChains; ++c) ++levelBegin[chainLevel[c] + 1];
@@ -202,8 +211,8 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
         int* ids = byLevel.data() + levelBegin[lvl];
         const int nIds = levelBegin[lvl + 1] - levelBegin[lvl];
         std::stable_sort(ids, ids + nIds, [&](int x, int y) { return chainLen[x] > chainLen[y]; });
-        const int wanted = (groupsTipsLevel > 0 && !levelHasPartialOperand[lvl]) ? groupsTipsLevel : groupsPerLevel;
-        const int nGroups = std::max(1, std::min<int>(wanted, nIds));
+        const LevelChoice choice = policy(nIds, !levelHasPartialOperand[lvl]);
+        const int nGroups = std::max(1, std::min<int>(choice.groups, nIds));
         heap.clear();
         for (int g = 0; g < nGroups; ++g) heap.emplace_back(size_t(0), g);
         const auto heavier = [](const std::pair<size_t, int>& x, const std::pair<size_t, int>& y) { return x > y; };
@@ -223,7 +232,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             std::vector<int> fill(groupBegin.begin(), groupBegin.end() - 1);
             for (int q = 0; q < nIds; ++q) order[fill[groupOf[q]]++] = ids[q];       // stable: dealing order inside a group
         }
-        Level L{static_cast<int>(out.chains.size()), nIds, static_cast<int>(out.groups.size()), nGroups, 0};
+        Level L{static_cast<int>(out.chains.size()), nIds, static_cast<int>(out.groups.size()), nGroups, 0, choice.variant};
         for (int g = 0; g < nGroups; ++g) {
             Group G{static_cast<int>(out.ops.size()), 0};
             for (int q = groupBegin[g]; q < groupBegin[g + 1]; ++q) {

@@ -14,6 +14,7 @@
 // still written, so the buffers hold exactly what the reference's would.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "../../include/strom_beagle.h"
@@ -64,7 +65,17 @@ struct Level {
     int groupCount;
     int tipsOnly;     // every operand read from memory is a tip and no operation reads a subtree scaler (level 0 of a
                       // full evaluation): the launch may use the kernel variant without partials-operand code
+    int variant;      // thread shape of the pruning kernel this launch runs (chosen by the LevelPolicy; kernels.cuh kVar*)
 };
+
+// How a launch is shaped: given the number of independent chains of a level, and whether every operand it reads from
+// memory is a tip, the engine picks the kernel's thread shape and how many thread-block groups the chains are dealt into
+// (it knows the pattern-tile counts and how many blocks are resident at once).
+struct LevelChoice {
+    int variant;
+    int groups;
+};
+typedef std::function<LevelChoice(int chainCount, bool tipsCandidate)> LevelPolicy;
 
 struct Group {
     int opStart;
@@ -100,5 +111,9 @@ struct Schedule {
 int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
                   int matrixCount, int scaleCount, bool accumulate, int groupsPerLevel, Schedule& out,
                   bool keepSubtreeScalers = false, int groupsTipsLevel = 0);
+// The same with the engine's per-level policy (thread shape and group count from the level's chain count).
+int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int partialsBufferCount,
+                  int matrixCount, int scaleCount, bool accumulate, const LevelPolicy& policy, Schedule& out,
+                  bool keepSubtreeScalers = false);
 
 }  // namespace sb200

@@ -23,7 +23,8 @@ class StromEvalArgs(C.Structure):
     _fields_ = [("stateFrequencies", _DP), ("eigenVectors", _DP), ("inverseEigenVectors", _DP), ("eigenValues", _DP),
                 ("categoryRates", _DP), ("categoryWeights", _DP), ("matrixIndices", _IP), ("edgeLengths", _DP),
                 ("edgeCount", C.c_int), ("operations", _IP), ("operationCount", C.c_int),
-                ("rootParentBuffer", C.c_int), ("rootChildBuffer", C.c_int), ("rootMatrix", C.c_int)]
+                ("rootParentBuffer", C.c_int), ("rootChildBuffer", C.c_int), ("rootMatrix", C.c_int),
+                ("categoryCount", C.c_int)]
 
 
 class EngineAPI:
@@ -37,6 +38,9 @@ class EngineAPI:
             "sb200SetDevice": (C.c_int, [C.c_int]),
             "sb200SetStream": (C.c_int, [C.c_int, C.c_void_p]),
             "sb200SetTipStatesU8": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+            "sb200SetAllTipStatesU8": (C.c_int, [C.c_int, C.c_void_p]),
+            "sb200EvalBatchAsync": (C.c_int, [C.c_int, _IP, C.POINTER(StromEvalArgs)]),
+            "sb200ReplayBatchAsync": (C.c_int, [C.c_int, _IP]),
             "sb200Eval": (C.c_int, [C.c_int, C.POINTER(StromEvalArgs), _DP]),
             "sb200EvalAsync": (C.c_int, [C.c_int, C.POINTER(StromEvalArgs), C.c_void_p]),
             "sb200ReplayAsync": (C.c_int, [C.c_int, C.c_void_p]),
@@ -130,7 +134,8 @@ class EvalArgs:
         self.c = StromEvalArgs(a["freqs"].ctypes.data_as(_DP), a["evec"].ctypes.data_as(_DP), a["ivec"].ctypes.data_as(_DP),
                                a["evals"].ctypes.data_as(_DP), a["rates"].ctypes.data_as(_DP), a["probs"].ctypes.data_as(_DP),
                                a["pidx"].ctypes.data_as(_IP), a["elen"].ctypes.data_as(_DP), int(a["pidx"].size),
-                               a["ops"].ctypes.data_as(_IP), int(a["ops"].size // 7), int(parent), int(child), int(child))
+                               a["ops"].ctypes.data_as(_IP), int(a["ops"].size // 7), int(parent), int(child), int(child),
+                               int(a["rates"].size))
 
     @property
     def h2d_bytes(self) -> int:

@@ -31,6 +31,33 @@
 
 namespace strom {
 
+#ifdef STROM_B200_ENGINE
+// Collects the evaluations several Likelihood objects begin (the heated chains of an MC3 run that share a GPU; the
+// reference steps them one after the other, src/strom.hpp:316-324) and hands them to the engine as ONE set of launches
+// (sb200EvalBatchAsync) when the first of them is finished.  Single-threaded use, like the lockstep driver.
+class EvalBatcher {
+  public:
+    typedef std::shared_ptr<EvalBatcher> SharedPtr;
+    void add(int instance, const StromEvalArgs& args) {
+        _instances.push_back(instance);
+        _args.push_back(args);
+    }
+    // enqueues what has been added since the last flush; returns that call's code to every evaluation of the set
+    int flush() {
+        if (_instances.empty()) return _code;
+        _code = sb200EvalBatchAsync(static_cast<int>(_instances.size()), &_instances[0], &_args[0]);
+        _instances.clear();
+        _args.clear();
+        return _code;
+    }
+
+  private:
+    std::vector<int> _instances;
+    std::vector<StromEvalArgs> _args;
+    int _code = 0;
+};
+#endif
+
 class Likelihood {
     friend struct LikelihoodInspector;   // test hook: reads the operation list (capi.cpp)
 
@@ -64,6 +91,11 @@ class Likelihood {
     // matrices that changed.  A new model or a different Tree object falls back to the full list.  No updater has to
     // cooperate: a rejected move is simply the next difference.  Has no effect on the CPU call path.
     void setIncremental(bool on);
+#ifdef STROM_B200_ENGINE
+    // Evaluations begun on this object are enqueued together with those of the other Likelihoods that share `b`
+    // (one set of kernel launches for all of them) when the first one is finished.  One pattern shard only.
+    void setBatcher(EvalBatcher::SharedPtr b) { _batcher = b; }
+#endif
     unsigned lastOperationCount() const { return static_cast<unsigned>(_operations.size() / 7); }
 
     typedef std::shared_ptr<Likelihood> SharedPtr;
@@ -77,7 +109,8 @@ class Likelihood {
     void setModelRateMatrix();
     void defineOperations(Tree::SharedPtr t);
     bool defineChangedOperations(Tree::SharedPtr t);
-    void rememberState(Tree::SharedPtr t, double log_likelihood);
+    void snapshotState(Tree::SharedPtr t);
+    void commitState(double log_likelihood);
     void modelNumbers(std::vector<double>& v) const;
     void updateTransitionMatrices();
     void calculatePartials();
@@ -102,23 +135,33 @@ class Likelihood {
     bool _using_data;
     bool _pending = false, _pending_on_device = false;   // an evaluation was begun / its scalar is still on the device
     double _pending_value = 0.0;
-    Tree::SharedPtr _pending_tree;
+    unsigned _instance_categ = 0;        // category count the instances were created with
+#ifdef STROM_B200_ENGINE
+    StromEvalArgs _args;                 // of the evaluation in flight (its arrays are members of this object and the model)
+    EvalBatcher::SharedPtr _batcher;
+    bool _pending_in_batch = false;
+#endif
 
     // what the engine holds from the previous call (incremental evaluation)
     bool _incremental;
     bool _remembered;
-    const Tree* _held_tree;
+    unsigned long long _held_tree_uid;   // Tree::uid() of the tree the device state belongs to (0: none)
     std::vector<int> _buffer_of;         // by node slot (index in Tree::_nodes): buffer = matrix index, frozen at the first call
     std::vector<int> _held_left, _held_right;   // by buffer: buffers of the two children the partials were computed from
     std::vector<double> _held_length;    // by matrix index: edge length its transition matrices were computed from
     std::vector<double> _held_model;
     double _held_log_likelihood;
     std::vector<char> _changed;          // scratch, by buffer
+    // the same four as the evaluation in flight will leave them: taken when it is begun (the caller may edit the tree or
+    // the model before finishing), committed when it has succeeded
+    std::vector<int> _next_left, _next_right;
+    std::vector<double> _next_length, _next_model;
+    unsigned long long _next_tree_uid = 0;
 };
 
 inline Likelihood::Likelihood()
     : _ntaxa(0), _nstates(0), _npatterns(0), _rooted(false), _prefer_gpu(true), _single(false), _quiet(false), _using_data(true),
-      _incremental(false), _remembered(false), _held_tree(nullptr), _held_log_likelihood(0.0) {
+      _incremental(false), _remembered(false), _held_tree_uid(0), _held_log_likelihood(0.0) {
     _model = Model::SharedPtr(new Model());
     _devices.assign(1, 0);
     // BeagleLib error codes, so that useful messages reach the user (reference src/likelihood.hpp:79-87)
@@ -218,6 +261,7 @@ inline void Likelihood::initBeagleLib() {
     long requirementFlags = (_single ? BEAGLE_FLAG_PRECISION_SINGLE : BEAGLE_FLAG_PRECISION_DOUBLE) | BEAGLE_FLAG_SCALING_MANUAL;
     long preferenceFlags = _prefer_gpu ? BEAGLE_FLAG_PROCESSOR_GPU : BEAGLE_FLAG_PROCESSOR_CPU;
 
+    _instance_categ = static_cast<unsigned>(_model->_relative_rates.size());
     const unsigned nshards = std::min<unsigned>(static_cast<unsigned>(_devices.size()), std::max(1u, _npatterns));
     for (unsigned r = 0; r < nshards; ++r) {
         unsigned lo, hi;
@@ -231,7 +275,7 @@ inline void Likelihood::initBeagleLib() {
                                               hi - lo,                // patterns (this shard's slice)
                                               1,                      // models
                                               num_transition_probs,   // transition matrices
-                                              _model->_num_categ,     // rate categories
+                                              static_cast<int>(_instance_categ),   // rate categories (+1 with invariable sites)
                                               num_internals + 1,      // scale buffers
                                               &resource, 1,           // device of this shard
                                               preferenceFlags, requirementFlags, &details);
@@ -258,18 +302,26 @@ inline void Likelihood::setTipStates() {
     for (unsigned r = 0; r < nshards; ++r) {
         unsigned lo, hi;
         Data::sliceBounds(_npatterns, r, nshards, lo, hi);
-        for (unsigned t = 0; t < _ntaxa; ++t) {
 #ifdef STROM_B200_ENGINE
+        // every taxon's 1-byte codes of this shard's slice in one strided upload (the reference uploads 4-byte ints
+        // taxon by taxon, src/likelihood.hpp:228-247)
+        std::vector<unsigned char> all;
+        all.reserve(static_cast<size_t>(_ntaxa) * (hi - lo));
+        for (unsigned t = 0; t < _ntaxa; ++t) {
             const std::vector<unsigned char> codes = _data->packTipCodes(t, lo, hi);
-            const int code = sb200SetTipStatesU8(_instances[r], static_cast<int>(t), codes.data());
+            all.insert(all.end(), codes.begin(), codes.end());
+        }
+        const int code = sb200SetAllTipStatesU8(_instances[r], all.data());
+        if (code != 0) throw XStrom("failed to set tip states (" + errorText(code) + ")");
 #else
+        for (unsigned t = 0; t < _ntaxa; ++t) {
             const Data::pattern_t& row = _data->getDataMatrix()[t];
             const int code = beagleSetTipStates(_instances[r], static_cast<int>(t), &row[lo]);
-#endif
             if (code != 0)
                 throw XStrom("failed to set tip state for taxon " + std::to_string(t + 1) + " (\"" + _data->getTaxonNames()[t] + "\"; " +
                              errorText(code) + ")");
         }
+#endif
     }
 }
 
@@ -379,10 +431,17 @@ inline bool Likelihood::defineChangedOperations(Tree::SharedPtr t) {
     const Node* base = &t->_nodes[0];
     std::vector<double> model;
     modelNumbers(model);
-    const bool fresh = !_remembered || _held_tree != t.get() || model != _held_model || _buffer_of.size() != t->_nodes.size();
+    const bool fresh = !_remembered || _held_tree_uid != t->uid() || model != _held_model || _buffer_of.size() != t->_nodes.size();
     if (fresh) {
         _buffer_of.assign(t->_nodes.size(), -1);
-        for (Node* nd : t->_levelorder) _buffer_of[nd - base] = nd->_number;
+        for (Node* nd : t->_levelorder) {
+            // tips keep their taxon number, internal nodes get the partials buffers ntaxa .. 2 ntaxa - 3
+            const bool tip = nd->_left_child == nullptr;
+            if (nd->_number < 0 || (tip ? nd->_number >= static_cast<int>(_ntaxa)
+                                        : (nd->_number < static_cast<int>(_ntaxa) || nd->_number > 2 * static_cast<int>(_ntaxa) - 3)))
+                throw XStrom("tree node numbers do not match the data (tips 0..n-1, internal nodes n..2n-3)");
+            _buffer_of[nd - base] = nd->_number;
+        }
         const size_t nbuf = 2 * static_cast<size_t>(_ntaxa);
         _held_left.assign(nbuf, -1);
         _held_right.assign(nbuf, -1);
@@ -427,19 +486,31 @@ inline bool Likelihood::defineChangedOperations(Tree::SharedPtr t) {
     return true;
 }
 
-inline void Likelihood::rememberState(Tree::SharedPtr t, double log_likelihood) {
+// The state the evaluation being begun will leave on the device (read from the tree and model as they are NOW).
+inline void Likelihood::snapshotState(Tree::SharedPtr t) {
     const Node* base = &t->_nodes[0];
     Node* top = t->_preorder[0];
+    _next_left = _held_left;
+    _next_right = _held_right;
+    _next_length = _held_length;
     for (Node* nd : t->_levelorder) {
         const int buf = _buffer_of[nd - base];
-        _held_length[(nd == top) ? t->_root->_number : buf] = nd->_edge_length;
+        _next_length[(nd == top) ? t->_root->_number : buf] = nd->_edge_length;
         if (nd->_left_child) {
-            _held_left[buf] = _buffer_of[nd->_left_child - base];
-            _held_right[buf] = _buffer_of[nd->_left_child->_right_sib - base];
+            _next_left[buf] = _buffer_of[nd->_left_child - base];
+            _next_right[buf] = _buffer_of[nd->_left_child->_right_sib - base];
         }
     }
-    modelNumbers(_held_model);
-    _held_tree = t.get();
+    modelNumbers(_next_model);
+    _next_tree_uid = t->uid();
+}
+
+inline void Likelihood::commitState(double log_likelihood) {
+    _held_left.swap(_next_left);
+    _held_right.swap(_next_right);
+    _held_length.swap(_next_length);
+    _held_model.swap(_next_model);
+    _held_tree_uid = _next_tree_uid;
     _held_log_likelihood = log_likelihood;
     _remembered = true;
 }
@@ -479,6 +550,9 @@ inline void Likelihood::beginLogLikelihood(Tree::SharedPtr t) {
     if (t->_is_rooted) throw XStrom("can only compute likelihoods for unrooted trees currently");
     if (!_data) throw XStrom("must call setData before calcLogLikelihood");
 
+    if (!_instances.empty() && _instance_categ != _model->_relative_rates.size()) {
+        finalizeInstances();   // the (shared) model's category count changed since the instances were created
+    }
     initBeagleLib();   // no-op if valid instances already exist
 
     // "root" is leaf 0 and has exactly one child
@@ -491,6 +565,7 @@ inline void Likelihood::beginLogLikelihood(Tree::SharedPtr t) {
             return;
         }
         _remembered = false;                             // until this call has succeeded
+        snapshotState(t);
     } else {
         defineOperations(t);
     }
@@ -500,27 +575,33 @@ inline void Likelihood::beginLogLikelihood(Tree::SharedPtr t) {
 
 #ifdef STROM_B200_ENGINE
     // one fused call per shard (asynchronous); finishLogLikelihood adds the scalars in shard order
-    StromEvalArgs args;
+    StromEvalArgs& args = _args;
     args.stateFrequencies = &_model->_state_freqs[0];
     args.eigenVectors = _model->_eigenvectors;
     args.inverseEigenVectors = _model->_inverse_eigenvectors;
     args.eigenValues = _model->_eigenvalues;
     args.categoryRates = &_model->_relative_rates[0];
     args.categoryWeights = &_model->_rate_probs[0];
-    args.matrixIndices = &_pmatrix_index[0];
-    args.edgeLengths = &_edge_lengths[0];
+    args.categoryCount = static_cast<int>(_model->_relative_rates.size());
+    args.matrixIndices = _pmatrix_index.empty() ? nullptr : &_pmatrix_index[0];
+    args.edgeLengths = _edge_lengths.empty() ? nullptr : &_edge_lengths[0];
     args.edgeCount = static_cast<int>(_pmatrix_index.size());
-    args.operations = reinterpret_cast<const BeagleOperation*>(&_operations[0]);
+    args.operations = _operations.empty() ? nullptr : reinterpret_cast<const BeagleOperation*>(&_operations[0]);
     args.operationCount = static_cast<int>(_operations.size() / 7);
     args.rootParentBuffer = index_focal_parent;
     args.rootChildBuffer = index_focal_child;
     args.rootMatrix = index_focal_child;
-    for (int inst : _instances) {
-        const int code = sb200EvalAsync(inst, &args, NULL);
-        if (code != 0) throw XStrom("failed to evaluate the likelihood on the engine. " + errorText(code));
+    _pending_in_batch = false;
+    if (_batcher && _instances.size() == 1) {
+        _batcher->add(_instances[0], args);              // enqueued with the other chains' when the first one is finished
+        _pending_in_batch = true;
+    } else {
+        for (int inst : _instances) {
+            const int code = sb200EvalAsync(inst, &args, NULL);
+            if (code != 0) throw XStrom("failed to evaluate the likelihood on the engine. " + errorText(code));
+        }
     }
     _pending_on_device = true;
-    _pending_tree = t;
     _pending = true;
 #else
     // the reference's sequence of BeagleLib calls; the last one is synchronous, so the value is known here
@@ -549,6 +630,11 @@ inline double Likelihood::finishLogLikelihood() {
 #ifdef STROM_B200_ENGINE
     if (_pending_on_device) {
         _pending_on_device = false;
+        if (_pending_in_batch) {
+            _pending_in_batch = false;
+            const int code = _batcher->flush();
+            if (code != 0) throw XStrom("failed to evaluate the likelihood on the engine. " + errorText(code));
+        }
         double log_likelihood = 0.0;
         int failed = 0;
         for (int inst : _instances) {                    // (every shard is drained even if one reports an error)
@@ -557,10 +643,8 @@ inline double Likelihood::finishLogLikelihood() {
             if (code != 0 && failed == 0) failed = code;
             log_likelihood += part;
         }
-        Tree::SharedPtr t = _pending_tree;
-        _pending_tree.reset();
         if (failed != 0) throw XStrom("failed to calculate edge logLikelihoods in CalcLogLikelihood. " + errorText(failed));
-        if (_incremental) rememberState(t, log_likelihood);
+        if (_incremental) commitState(log_likelihood);
         _pending_value = log_likelihood;
     }
 #endif

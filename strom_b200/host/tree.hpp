@@ -1,6 +1,7 @@
 // tree.hpp -- tree container (mirrors reference src/tree.hpp:14-80): unrooted trees are "rooted" at
 // a tip whose only child is preorder[0]; Likelihood reads the traversal vectors directly.
 #pragma once
+#include <atomic>
 #include <memory>
 
 #include "node.hpp"
@@ -14,7 +15,12 @@ class Tree {
     friend class TreeUpdater;
 
   public:
-    Tree() { clear(); }
+    Tree() : _uid(nextUid()) { clear(); }
+    Tree(const Tree& other) = delete;             // (node pointers refer into _nodes)
+    Tree& operator=(const Tree& other) = delete;
+    // Process-wide unique identity of this Tree object (never reused, unlike its address): what a Likelihood that keeps
+    // device state between calls remembers about "the tree the state was computed from".
+    unsigned long long uid() const { return _uid; }
     bool isRooted() const { return _is_rooted; }
     unsigned numLeaves() const { return _nleaves; }
     unsigned numNodes() const { return static_cast<unsigned>(_nodes.size()); }
@@ -31,6 +37,12 @@ class Tree {
         _levelorder.clear();
     }
 
+    static unsigned long long nextUid() {
+        static std::atomic<unsigned long long> counter(0);
+        return ++counter;
+    }
+
+    const unsigned long long _uid;
     bool _is_rooted;
     Node* _root;
     unsigned _nleaves;
