@@ -132,7 +132,7 @@ struct Engine {
     bool schedValid = false;
     int schedHint = 1;                    // batchHint the active plan's launches were shaped for
     std::vector<BeagleOperation> schedOps;
-    DevOp* dOps = nullptr;
+    DevRec* dOps = nullptr;
     Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
     bool keepSubtreeScalers = false;      // incremental evaluation: permanent per-buffer subtree scaler slots (sb200SetSubtreeScalers)
@@ -151,7 +151,7 @@ struct Engine {
         bool accumulate = false, valid = false;
         int hint = 1;
         std::vector<BeagleOperation> key;
-        DevOp* dOps = nullptr;
+        DevRec* dOps = nullptr;
         Group* dGroups = nullptr;
         int* dRootSlots = nullptr;
         int* dTTOps = nullptr;
@@ -190,7 +190,8 @@ struct Engine {
     bool usePdl = true;
     bool useTipsKernel = true;            // SB200_TIPS_KERNEL=0 (tuning aid): tips-only launches run the general kernel
     int forceVariant = -1;                // SB200_VARIANT (tuning aid): every launch of a small instance runs this thread shape
-    int wideMinWarps = 0;                 // small instances: a level runs the wide thread shape from this many warps up
+    int wideMinWarps = 0;                 // small instances: a level runs the wide thread shape from this many warps up,
+    int narrowMinWarps = 0;               // ... the narrow one from this many up, the quad shape below
 
     size_t realSize() const { return fp32 ? 4 : 8; }
     ParamBlockHeader* hHeader() { return reinterpret_cast<ParamBlockHeader*>(hBlock); }
@@ -285,7 +286,8 @@ struct Engine {
         usePdl = envInt("SB200_PDL", 1) != 0;                 // tuning aid: plain stream order
         useTipsKernel = envInt("SB200_TIPS_KERNEL", 1) != 0;
         forceVariant = envInt("SB200_VARIANT", -1);
-        wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 8 * smCount);
+        wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 16 * smCount);
+        narrowMinWarps = envInt("SB200_NARROW_MIN_WARPS", 4 * smCount);
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -395,8 +397,13 @@ struct Engine {
         }
         const int K = std::max(1, batchHint);
         const long wideWarps = static_cast<long>(K) * chainCount * (Ppad / varPatterns(C, kVarWide, static_cast<int>(realSize()))) * varWarps(C, kVarWide, static_cast<int>(realSize()));
-        c.variant = wideWarps >= wideMinWarps ? kVarWide : kVarNarrow;
-        if (forceVariant == kVarWide || forceVariant == kVarNarrow) c.variant = forceVariant;
+        const long narrowWarps = static_cast<long>(K) * chainCount * (Ppad / 32) * C;
+        c.variant = wideWarps >= wideMinWarps ? kVarWide : narrowWarps >= narrowMinWarps ? kVarNarrow : kVarQuad;
+        if (forceVariant >= kVarWide && forceVariant <= kVarQuad) c.variant = forceVariant;
+        if (c.variant == kVarQuad) {                   // every chain its own group: the launch has blocks to spare
+            c.groups = std::max(1, chainCount);
+            return c;
+        }
         const int tiles = Ppad / varPatterns(C, c.variant, static_cast<int>(realSize()));
         const int waves = tipsCandidate && useTipsKernel ? 1 : 2;
         int slots = smCount * blocksPerSm(c.variant, tipsCandidate) * waves;
@@ -483,7 +490,7 @@ struct Engine {
         schedAccumulate = accumulate;
         schedHint = hint;
         // stage + upload
-        const size_t opsB = sizeof(DevOp) * sched.ops.size();
+        const size_t opsB = sizeof(DevRec) * sched.ops.size();
         const size_t chB = sizeof(Group) * sched.groups.size();
         const size_t rtB = sizeof(int) * sched.rootSlots.size();
         std::vector<int> ttOps(sched.tipTipCount, 0);
@@ -511,8 +518,8 @@ struct Engine {
             planCap = total + total / 2 + 256;
             CK(cudaMalloc(&dPlan, planCap));
         }
-        // (48-byte operation records first: every array stays aligned to its element size)
-        dOps = reinterpret_cast<DevOp*>(dPlan);
+        // (64-byte operation records first: every array stays aligned to its element size)
+        dOps = reinterpret_cast<DevRec*>(dPlan);
         dGroups = reinterpret_cast<Group*>(dPlan + opsB);
         dRootSlots = reinterpret_cast<int*>(dPlan + opsB + chB);
         dTTOps = reinterpret_cast<int*>(dPlan + opsB + chB + rtB);
@@ -523,7 +530,21 @@ struct Engine {
             CK(cudaMalloc(&dTT, ttCap));
         }
         unsigned char* st = static_cast<unsigned char*>(hSchedStage);
-        if (opsB) std::memcpy(st, sched.ops.data(), opsB);
+        {
+            // the planner's operations with every operand resolved to a byte offset (kernels.cuh: DevRec)
+            DevRec* rec = reinterpret_cast<DevRec*>(st);
+            const long long bufBytes = static_cast<long long>(Ppad) * C * 4 * static_cast<long long>(realSize());
+            for (size_t i = 0; i < sched.ops.size(); ++i) {
+                const DevOp& d = sched.ops[i];
+                DevRec& r = rec[i];
+                r.flags = d.flags; r.ma = d.ma; r.mb = d.mb; r.tt = d.tt;
+                r.destOff = d.dest * bufBytes;
+                r.bOff = (d.flags & OP_B_TIP) ? d.b * tipStride : (d.b - nTips) * bufBytes;
+                r.aOff = !(d.flags & OP_CHAIN_START) ? 0 : (d.flags & OP_A_TIP) ? d.a * tipStride : (d.a - nTips) * bufBytes;
+                r.sa = d.sa; r.sb = d.sb; r.sOut = d.sOut;
+                r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            }
+        }
         if (chB) std::memcpy(st + opsB, sched.groups.data(), chB);
         if (rtB) std::memcpy(st + opsB + chB, sched.rootSlots.data(), rtB);
         if (ttB) std::memcpy(st + opsB + chB + rtB, ttOps.data(), ttB);
@@ -711,9 +732,10 @@ static void launchLevelV(Engine& L, const PruneBatch<real>& pb, dim3 grid, bool 
     else launchK(L.stream, L.usePdl, prune_chains_kernel<real, CC, V, false>, grid, dim3(varThreads(CC, V, sizeof(real))), pb);
 }
 template <typename real, int CC>
-static void launchLevelC(Engine& L, const PruneBatch<real>& pb, int tilesOf[3], int maxGroups, int K, int V, bool tips) {
+static void launchLevelC(Engine& L, const PruneBatch<real>& pb, int tilesOf[4], int maxGroups, int K, int V, bool tips) {
     const dim3 grid(tilesOf[V], maxGroups, K);
-    if (V == kVarStream) launchLevelV<real, CC, kVarStream>(L, pb, grid, tips);
+    if (V == kVarQuad) launchK(L.stream, L.usePdl, prune_quad_kernel<real, CC>, grid, dim3(32 * CC), pb);
+    else if (V == kVarStream) launchLevelV<real, CC, kVarStream>(L, pb, grid, tips);
     else if (V == kVarWide) launchLevelV<real, CC, kVarWide>(L, pb, grid, tips);
     else launchLevelV<real, CC, kVarNarrow>(L, pb, grid, tips);
 }
@@ -747,8 +769,9 @@ static void launchPartialsSetT(Engine* const* es, int K, const int* cumIdx) {
         CK(cudaGetLastError());
         ++L.launches;
     }
-    int tilesOf[3];
+    int tilesOf[4];
     for (int v = 0; v < 3; ++v) tilesOf[v] = L.Ppad / varPatterns(C, v, sizeof(real));
+    tilesOf[kVarQuad] = L.Ppad / kQuadPatterns;
     const int traceLevel = envInt("SB200_TRACE_LEVEL", -1);   // tuning aid (needs -DSB200_TRACE)
     for (size_t l = 0; l < maxLevels; ++l) {
         // the instances' launches number l, grouped by (thread shape, tips-only): normally ONE launch
@@ -765,7 +788,7 @@ static void launchPartialsSetT(Engine* const* es, int K, const int* cumIdx) {
                 if (done[z] || l >= es[z]->sched.levels.size()) continue;
                 const Level& Lz = es[z]->sched.levels[l];
                 if (Lz.groupCount == 0) { done[z] = true; continue; }
-                if (Lz.variant != V || (Lz.tipsOnly != 0 && L.useTipsKernel) != tips) continue;
+                if (Lz.variant != V || (V != kVarQuad && (Lz.tipsOnly != 0 && L.useTipsKernel) != tips)) continue;
                 pb.a[n] = args[z];
                 pb.a[n].trace = (traceLevel < 0 || traceLevel == static_cast<int>(l)) ? args[z].trace : nullptr;
                 pb.groupBase[n] = Lz.groupStart;

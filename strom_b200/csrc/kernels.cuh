@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "schedule.hpp"
 
 namespace sb200 {
@@ -49,10 +51,15 @@ __host__ __device__ constexpr int ttStride(int C, int realBytes) { return 25 * t
 //   kVarWide    the same thread shape in 4-warp blocks, for launches of small instances that have enough independent
 //               chains to fill the GPU (the lower levels of rbcl738, or several evaluations batched);
 //   kVarNarrow  one category per thread (a warp per category, maxima exchanged through shared memory): C times the
-//               warps and a C times shorter dependent instruction stream per step, for launches with few chains
-//               (the top of the tree), where a step is bound by the latency of one warp's instructions.
+//               warps and a C times shorter dependent instruction stream per step, for launches with few chains,
+//               where a step is bound by the latency of one warp's instructions;
+//   kVarQuad    one STATE of one category of one pattern per thread (prune_quad_kernel: a warp = 8 patterns x 4 states
+//               of a category, a block = C such warps): four times the warps again and a quarter of the arithmetic per
+//               thread, for the last launches of a small tree -- a handful of chains of dependent steps that leave all
+//               but a few warp schedulers of the GPU idle whatever the shape.
 // ------------------------------------------------------------------------------------------
-enum { kVarStream = 0, kVarWide = 1, kVarNarrow = 2 };
+enum { kVarStream = 0, kVarWide = 1, kVarNarrow = 2, kVarQuad = 3 };
+constexpr int kQuadPatterns = 8;    // patterns per block of the quad shape
 // categories per thread of the stream / wide shapes: what the register file carries without spilling (two FP64 or four
 // FP32 operand vectors per operand); a category count that does not divide leaves the last warp's spare slots repeating
 // the last category (5 = 2+2+1 in FP64, 3+2 in FP32)
@@ -87,6 +94,22 @@ __host__ __device__ constexpr int varBlocksPerSm(int C, int V, bool tips, int re
 }
 __host__ __device__ constexpr int rootPatternsPerBlock() { return 128; }
 
+// One operation as the pruning kernels read it: built by the engine from the planner's DevOp when a plan is uploaded.
+// Operands are byte offsets (from the start of the partials arena, or of the tip-state table), so a thread forms an
+// address with one 64-bit add; the first 16 bytes are all that staging an operation's matrix images needs.
+struct alignas(16) DevRec {
+    int flags;             // OP_* bits
+    int ma, mb;            // transition matrices of operand A's and B's edge
+    int tt;                // OP_TIPTIP: index of the precomputed (stateA, stateB) table
+    long long destOff;     // destination buffer
+    long long bOff;        // operand B (partials buffer, or tip row when OP_B_TIP)
+    long long aOff;        // operand A at a chain start (partials buffer, or tip row when OP_A_TIP)
+    int sa, sb;            // subtree log-scaler slots to add for A / B, or -1
+    int sOut;              // OP_CHAIN_END / OP_STORE_S: slot receiving the subtree log-scaler of dest, or -1
+    int pad[3];
+};
+static_assert(sizeof(DevRec) == 64, "DevRec is four 16-byte words");
+
 // Per-eigen-index model block, resident in HBM and refreshed once per evaluation.
 struct DevModel {
     double freqs[4];
@@ -105,7 +128,7 @@ struct PruneArgs {
     double* cum;                     // cumulative scale buffer or nullptr
     const real* ttTables;            // [tipTipCount][ttStride(C)]
     long long* trace;                // optional per-step clock samples of block (0,0) (tuning builds only)
-    const DevOp* ops;
+    const DevRec* ops;               // the plan's operations in the form the kernels read
     const Group* groups;
     long long tipStride;
     int Ppad;
@@ -135,7 +158,7 @@ struct MatBatch {
 
 template <typename real>
 struct TableJob {
-    const DevOp* ops;
+    const DevRec* ops;
     const int* ttOps;
     const real* mats;
     real* tables;
@@ -270,7 +293,7 @@ tiptip_tables_kernel(const __grid_constant__ TableBatch<real> B, const int C) {
     pdlLaunchDependents();
     const TableJob<real>& J = B.j[blockIdx.y];
     if (static_cast<int>(blockIdx.x) >= J.count) return;
-    const DevOp op = J.ops[J.ttOps[blockIdx.x]];      // (plan data: uploaded by a copy, not produced by a kernel)
+    const DevRec op = J.ops[J.ttOps[blockIdx.x]];     // (plan data: uploaded by a copy, not produced by a kernel)
     pdlWait();                                        // the matrices are
     const real* ma = J.mats + static_cast<size_t>(op.ma) * C * kMatStride;
     const real* mb = J.mats + static_cast<size_t>(op.mb) * C * kMatStride;
@@ -356,12 +379,18 @@ __device__ __forceinline__ float fastRcp(float m) {
 __device__ __noinline__ double foldedLog(double prod, double factor) { return log(prod) + log(factor); }
 __device__ __noinline__ double scalerTotal(double acc, double prod) { return acc + log(prod); }
 
-constexpr int kOpChunk = 256;                  // operations of a group held in shared memory at a time
+constexpr int kOpChunk = 128;                  // operations of a group held in shared memory at a time
 #ifndef SB200_PREFETCH_AHEAD
-#define SB200_PREFETCH_AHEAD 3
+#define SB200_PREFETCH_AHEAD 2
 #endif
-constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // steps between an operand tile's L2 prefetch and its register load
-constexpr int kOpWords = sizeof(DevOp) / 16;   // 16-byte words per operation
+constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // streaming shape: steps between an operand's L2 prefetch and its register load
+constexpr int kRecWords = sizeof(DevRec) / 16;
+
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <typename T>
+__device__ __forceinline__ T* byteOffset(T* base, long long bytes) {
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(base)) + bytes);
+}
 
 template <typename real, int C, int V, bool TIPS>
 __global__ void __launch_bounds__(varThreads(C, V, sizeof(real)), varBlocksPerSm(C, V, TIPS, sizeof(real)))
@@ -380,16 +409,13 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     constexpr int IMG = TTS > 2 * MSZ ? TTS : 2 * MSZ;   // shared image of one step: two matrices OR one table
     constexpr int NSTG = (IMG / CHUNK + THREADS - 1) / THREADS;   // staging chunks per thread
     constexpr bool kSingleWarp = THREADS == 32;
+    constexpr bool kPrefetch = V == kVarStream && kPrefetchAhead > 0 && !TIPS;   // (small instances live in L2 anyway)
     __shared__ __align__(16) real sm[2][IMG];
-    __shared__ int4 sops[kOpChunk * kOpWords];
+    __shared__ DevRec sops[kOpChunk];
     __shared__ double sAcc[THREADS];                     // log part of the running scaler (touched rarely)
     __shared__ real smax[2][NCW > 1 ? THREADS : 1];      // narrow shape: per-warp maxima of a step, double-buffered
 
-#ifdef SB200_Z0
-    const int z = 0;
-#else
     const int z = blockIdx.z;
-#endif
     pdlLaunchDependents();
     if (static_cast<int>(blockIdx.y) >= B.groupCount[z]) return;
     const PruneArgs<real>& A = B.a[z];
@@ -403,18 +429,14 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     const Group grp = A.groups[B.groupBase[z] + blockIdx.y];
     const int nOps = grp.opEnd - grp.opStart;
     const int Ppad = A.Ppad;
-    const int nTips = A.nTips;
-    const size_t tile0 = static_cast<size_t>(blockIdx.x) * G;       // first pattern of this block's tile
-    const size_t pat = tile0 + sp * 32 + lane;                      // this thread's pattern
+    const size_t pat = static_cast<size_t>(blockIdx.x) * G + sp * 32 + lane;   // this thread's pattern
     const size_t catStride = static_cast<size_t>(Ppad) * 4;         // reals between categories
-    const size_t bufStride = catStride * C;
     auto kcat = [&](int c) { return kEven ? kb + c : min(kb + c, C - 1); };               // category of slot c
     auto catOff = [&](int c) { return static_cast<size_t>(kcat(c) - kb) * catStride; };     // ... relative to pmine
-    real* const pmine = A.partials + (static_cast<size_t>(kb) * Ppad + pat) * 4;   // category c of this thread: + c*catStride
+    real* const pmine = A.partials + (static_cast<size_t>(kb) * Ppad + pat) * 4;   // category slot c of this thread: + catOff(c)
     const uint8_t* const tmine = A.tips + pat;
     double* const accMine = A.slotAcc + pat;
     double* const prodMine = A.slotProd + pat;
-    const long long tipStride = A.tipStride;
     const real* const mats = A.mats;
 
     auto blockSync = [&]() {
@@ -423,9 +445,10 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     };
     // ---- helpers ---------------------------------------------------------------------------
     // matrix images (or the tip x tip table) of one operation -> sm[buf], 16 bytes per cp.async
-    auto stage = [&](int buf, const int4& w0, const int4& w1, int tt) {
-        if (w1.w & OP_TIPTIP) {
-            const real* src = A.ttTables + static_cast<size_t>(tt) * TTS;
+    auto stage = [&](int buf, const DevRec& r) {
+        const int4 w = *reinterpret_cast<const int4*>(&r);           // flags, ma, mb, tt
+        if (w.x & OP_TIPTIP) {
+            const real* src = A.ttTables + static_cast<size_t>(w.w) * TTS;
 #pragma unroll
             for (int s = 0; s < NSTG; ++s) {
                 const int c = tid + s * THREADS;
@@ -437,41 +460,30 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                 const int c = tid + s * THREADS;
                 if (c < 2 * NCH) {
                     const int o = c >= NCH ? 1 : 0;
-                    cpAsync16(&sm[buf][c * CHUNK], mats + static_cast<size_t>(o ? w1.x : w0.z) * MSZ + (c - o * NCH) * CHUNK);
+                    cpAsync16(&sm[buf][c * CHUNK], mats + static_cast<size_t>(o ? w.z : w.y) * MSZ + (c - o * NCH) * CHUNK);
                 }
             }
         }
         cpAsyncCommit();
     };
-    auto fetchPartial = [&](int src, real (&v)[CPT][4]) {
-        const real* base = pmine + static_cast<size_t>(src - nTips) * bufStride;
+    auto fetchPartial = [&](long long off, real (&v)[CPT][4]) {
+        const real* base = byteOffset(pmine, off);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) ld4(base + catOff(c), v[c]);
     };
-    // L2 prefetch of everything an operation will read from HBM (bulk requests per tile, issued by a few threads
-    // kPrefetchAhead steps early): the register loads one step ahead then hit L2.  Requests are 16-byte granular
-    // (a tile of 32*TP one-byte tip codes or 8-byte scalers always is).
-    auto prefetchOperands = [&](const int4& w0, const int4& w1) {
-        // thread q < C asks for category q of the partials operand(s); thread C for the tips and scalers
-        if (tid < C) {
-            const real* ptile = A.partials + (static_cast<size_t>(tid) * Ppad + tile0) * 4;
-            constexpr unsigned kTileBytes = G * 4 * sizeof(real);
-            if (!TIPS && !(w1.w & OP_B_TIP)) bulkPrefetchL2(ptile + static_cast<size_t>(w0.w - nTips) * bufStride, kTileBytes);
-            if (!TIPS && (w1.w & OP_CHAIN_START) && !(w1.w & OP_A_TIP))
-                bulkPrefetchL2(ptile + static_cast<size_t>(w0.y - nTips) * bufStride, kTileBytes);
-        } else if (tid == C) {
-            if (TIPS || (w1.w & OP_B_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.w) * tipStride + tile0, G);
-            if (!TIPS && w1.z >= 0) {
-                bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.z) * Ppad + tile0, G * 8);
-                bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.z) * Ppad + tile0, G * 8);
-            }
-            if (w1.w & OP_CHAIN_START) {
-                if (TIPS || (w1.w & OP_A_TIP)) bulkPrefetchL2(A.tips + static_cast<size_t>(w0.y) * tipStride + tile0, G);
-                if (!TIPS && w1.y >= 0) {
-                    bulkPrefetchL2(A.slotAcc + static_cast<size_t>(w1.y) * Ppad + tile0, G * 8);
-                    bulkPrefetchL2(A.slotProd + static_cast<size_t>(w1.y) * Ppad + tile0, G * 8);
-                }
-            }
+    // Streaming sizes: every thread asks L2 for the sectors of operand B (and A, at a chain start) it will load
+    // kPrefetchAhead steps later, so that the register loads, issued one step ahead, hit L2.
+    auto prefetchOperands = [&](const DevRec& r) {
+        const int fl = r.flags;
+        if (!(fl & OP_B_TIP)) {
+            const real* base = byteOffset(pmine, r.bOff);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) prefetchL2(base + catOff(c));
+        }
+        if ((fl & (OP_CHAIN_START | OP_A_TIP)) == OP_CHAIN_START) {
+            const real* base = byteOffset(pmine, r.aOff);
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) prefetchL2(base + catOff(c));
         }
     };
 
@@ -493,22 +505,28 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         }
     };
     // operand A of a chain start, and the scaler of the chain that produced it
-    auto startChain = [&](const int4& w0, const int4& w1) {
-        if (TIPS || (w1.w & OP_A_TIP)) sX = tmine[static_cast<size_t>(w0.y) * tipStride];
-        else fetchPartial(w0.y, X);
-        if (!TIPS && w1.y >= 0 && scalerWarp) {
-            const double a = accMine[static_cast<size_t>(w1.y) * Ppad];
-            const double pr = prodMine[static_cast<size_t>(w1.y) * Ppad];
-            accumulate(a, pr);
+    auto startChain = [&](const DevRec& r) {
+        if (TIPS || (r.flags & OP_A_TIP)) sX = *byteOffset(tmine, r.aOff);
+        else fetchPartial(r.aOff, X);
+        if (!TIPS && scalerWarp) {
+            const int sa = r.sa;
+            if (sa >= 0) {
+                const double a = accMine[static_cast<size_t>(sa) * Ppad];
+                const double pr = prodMine[static_cast<size_t>(sa) * Ppad];
+                accumulate(a, pr);
+            }
         }
     };
     // operand B (and its chain's scaler) of an operation, one step ahead of its use
-    auto fetchB = [&](const int4& w0, const int4& w1) {
-        if (TIPS || (w1.w & OP_B_TIP)) sY = tmine[static_cast<size_t>(w0.w) * tipStride];
-        else fetchPartial(w0.w, Y);
-        if (!TIPS && w1.z >= 0 && scalerWarp) {
-            pendAcc = accMine[static_cast<size_t>(w1.z) * Ppad];
-            pendProd = prodMine[static_cast<size_t>(w1.z) * Ppad];
+    auto fetchB = [&](const DevRec& r) {
+        if (TIPS || (r.flags & OP_B_TIP)) sY = *byteOffset(tmine, r.bOff);
+        else fetchPartial(r.bOff, Y);
+        if (!TIPS && scalerWarp) {
+            const int sb = r.sb;
+            if (sb >= 0) {
+                pendAcc = accMine[static_cast<size_t>(sb) * Ppad];
+                pendProd = prodMine[static_cast<size_t>(sb) * Ppad];
+            }
         }
     };
 
@@ -520,15 +538,14 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
 #else
 #define SB200_TICK(slot)
 #endif
-    // ---- one step: operation (w0,w1) at position j of the chunk; (n0,n1) is the next one (if more) -----
+    // ---- one step: operation j of the chunk ------------------------------------------------------------
     // On entry image j is visible to the whole block and image j+1 is on its way.
     auto step = [&](const int j, const int nc) {
         SB200_TICK(0)
         const bool more = j + 1 < nc;
-        const int4 w0 = sops[j * kOpWords], w1 = sops[j * kOpWords + 1];
-        const int flags = w1.w;
-        if (kPrefetchAhead > 0 && tid <= C && j + 1 + kPrefetchAhead < nc)
-            prefetchOperands(sops[(j + 1 + kPrefetchAhead) * kOpWords], sops[(j + 1 + kPrefetchAhead) * kOpWords + 1]);
+        const DevRec& rec = sops[j];
+        const int flags = rec.flags;
+        if (kPrefetch && j + 1 + kPrefetchAhead < nc) prefetchOperands(sops[j + 1 + kPrefetchAhead]);
         const real* sa = sm[j & 1];
         const real* sb = sa + MSZ;
         double mfac;                                         // this step's rescaling maximum (1 when not rescaled)
@@ -537,7 +554,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         if (flags & OP_TIPTIP) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
             const int combo = sX * 5 + sY;
-            if (more) fetchB(sops[(j + 1) * kOpWords], sops[(j + 1) * kOpWords + 1]);
+            if (more) fetchB(sops[j + 1]);
             const real* T = sa + combo * TTE;
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
@@ -580,10 +597,10 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                     for (int i = 0; i < 4; ++i) X[c][i] *= F[i];
                 }
             }
-            if (!TIPS && w1.z >= 0 && scalerWarp) accumulate(pendAcc, pendProd);
+            if (!TIPS && scalerWarp && rec.sb >= 0) accumulate(pendAcc, pendProd);
             SB200_TICK(2)
             // next step's operand B is requested now; the rescaling below hides its latency
-            if (more) fetchB(sops[(j + 1) * kOpWords], sops[(j + 1) * kOpWords + 1]);
+            if (more) fetchB(sops[j + 1]);
             if (flags & OP_RESCALE) {
                 m = rmax(rmax(X[0][0], X[0][1]), rmax(X[0][2], X[0][3]));
 #pragma unroll
@@ -596,10 +613,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         if (more) cpAsyncWaitAll();   // (my part of) image j+1 has landed
         blockSync();                  // image j+1 and this step's maxima visible; everyone is done with image j
         SB200_TICK(4)
-        if (j + 2 < nc) {
-            const int4 s0 = sops[(j + 2) * kOpWords], s1 = sops[(j + 2) * kOpWords + 1];
-            stage(j & 1, s0, s1, (s1.w & OP_TIPTIP) ? sops[(j + 2) * kOpWords + 2].y : -1);
-        }
+        if (j + 2 < nc) stage(j & 1, sops[j + 2]);
         if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) {
             if (NCW > 1) {
                 const real* q = &smax[j & 1][(sp * NCW) * 32 + lane];
@@ -619,7 +633,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             mfac = static_cast<double>(m);
         }
         SB200_TICK(5)
-        real* dest = pmine + static_cast<size_t>(w0.x) * bufStride;
+        real* dest = byteOffset(pmine, rec.destOff);
         if (flags & OP_CHAIN_END) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
@@ -643,7 +657,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             if (flags & (OP_STORE_S | OP_CHAIN_END)) {
                 // a chain end hands its subtree log-scaler to the parent chain (and resets); incremental plans keep
                 // every node's (OP_STORE_S: store and carry on)
-                const int sOut = sops[j * kOpWords + 2].x;
+                const int sOut = rec.sOut;
                 double a = sAcc[tid];
                 if (sOut >= 0) {
                     if (prod < 1e-100) {                     // keep a parent's product of two stored factors normal
@@ -666,10 +680,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                 }
             }
         }
-        if (more) {
-            const int4 n1 = sops[(j + 1) * kOpWords + 1];
-            if (n1.w & OP_CHAIN_START) startChain(sops[(j + 1) * kOpWords], n1);
-        }
+        if (more && (sops[j + 1].flags & OP_CHAIN_START)) startChain(sops[j + 1]);
         SB200_TICK(6)
     };
 
@@ -679,25 +690,260 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         if (chunk0 > 0) blockSync();
         {
             const int4* gops = reinterpret_cast<const int4*>(A.ops + grp.opStart + chunk0);
-            for (int w = tid; w < nc * kOpWords; w += THREADS) sops[w] = gops[w];
+            int4* dst = reinterpret_cast<int4*>(sops);
+            for (int w = tid; w < nc * kRecWords; w += THREADS) dst[w] = gops[w];
         }
         blockSync();
         if (chunk0 == 0) pdlWait();   // the plan is in shared memory; everything below reads what earlier kernels wrote
-        const int4 a0 = sops[0], a1 = sops[1];
-        stage(0, a0, a1, (a1.w & OP_TIPTIP) ? sops[2].y : -1);
-        if (nc > 1) {
-            const int4 s0 = sops[kOpWords], s1 = sops[kOpWords + 1];
-            stage(1, s0, s1, (s1.w & OP_TIPTIP) ? sops[kOpWords + 2].y : -1);
-        }
-        if (a1.w & OP_CHAIN_START) startChain(a0, a1);       // (a later chunk may begin in mid-chain: A is carried)
-        fetchB(a0, a1);
-        if (kPrefetchAhead > 0 && tid <= C) {
+        stage(0, sops[0]);
+        if (nc > 1) stage(1, sops[1]);
+        if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);       // (a later chunk may begin in mid-chain: A is carried)
+        fetchB(sops[0]);
+        if (kPrefetch) {
 #pragma unroll
             for (int a = 1; a <= kPrefetchAhead; ++a)
-                if (a < nc) prefetchOperands(sops[a * kOpWords], sops[a * kOpWords + 1]);
+                if (a < nc) prefetchOperands(sops[a]);
         }
         cpAsyncWaitAll();
         blockSync();                  // images 0 and 1 visible
+#pragma unroll 1
+        for (int j = 0; j < nc; ++j) step(j, nc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (b') the same step for launches that are bound by the latency of ONE warp's instruction stream (the top of a small
+//      tree: one to a few chains, a few dozen warps in the whole launch): thread = (pattern, category, STATE).
+//      A warp holds 8 patterns x 4 states of one category, a block the C categories of its 8 patterns.  A thread keeps
+//      the whole 4-vector of its (pattern, category) but computes ONE row of each matrix-vector product; the new vector is
+//      put together again by four shuffles inside the quad; the per-pattern maximum takes two shuffles inside the quad
+//      and one exchange between the category warps through shared memory.  Same arithmetic, same order of additions
+//      and the same reciprocal as prune_chains_kernel: the two produce the same bits.
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__device__ __forceinline__ real quadGather(real v, int lane, int j) { return __shfl_sync(0xffffffffu, v, (lane & ~3) + j); }
+
+template <typename real, int C>
+__global__ void __launch_bounds__(32 * C)
+prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
+    constexpr int THREADS = 32 * C;
+    constexpr int G = kQuadPatterns;
+    constexpr int MSZ = kMatStride * C;
+    constexpr int CHUNK = 16 / static_cast<int>(sizeof(real));
+    constexpr int NCH = MSZ / CHUNK;
+    constexpr int TTE = ttEntry(C, sizeof(real));
+    constexpr int TTS = ttStride(C, sizeof(real));
+    constexpr int NTT = TTS / CHUNK;
+    constexpr int IMG = TTS > 2 * MSZ ? TTS : 2 * MSZ;
+    constexpr int NSTG = (IMG / CHUNK + THREADS - 1) / THREADS;
+    constexpr bool kSingleWarp = C == 1;
+    __shared__ __align__(16) real sm[2][IMG];
+    __shared__ DevRec sops[kOpChunk];
+    __shared__ double sAcc[THREADS];
+    __shared__ real smax[2][C * G];
+
+    const int z = blockIdx.z;
+    pdlLaunchDependents();
+    if (static_cast<int>(blockIdx.y) >= B.groupCount[z]) return;
+    const PruneArgs<real>& A = B.a[z];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int k = tid >> 5;                              // category = warp
+    const int i = lane & 3;                              // state (row of the matrices) of this thread
+    const int q = lane >> 2;                             // pattern of the tile
+    const bool scalerThread = k == 0 && i == 0;          // keeps and stores the pattern's log-scalers
+    const Group grp = A.groups[B.groupBase[z] + blockIdx.y];
+    const int nOps = grp.opEnd - grp.opStart;
+    const int Ppad = A.Ppad;
+    const size_t pat = static_cast<size_t>(blockIdx.x) * G + q;
+    real* const pmine = A.partials + (static_cast<size_t>(k) * Ppad + pat) * 4;   // this thread's (pattern, category) vector
+    const uint8_t* const tmine = A.tips + pat;
+    double* const accMine = A.slotAcc + pat;
+    double* const prodMine = A.slotProd + pat;
+    const real* const mats = A.mats;
+
+    auto blockSync = [&]() {
+        if (kSingleWarp) __syncwarp();
+        else __syncthreads();
+    };
+    auto stage = [&](int buf, const DevRec& r) {
+        const int4 w = *reinterpret_cast<const int4*>(&r);           // flags, ma, mb, tt
+        if (w.x & OP_TIPTIP) {
+            const real* src = A.ttTables + static_cast<size_t>(w.w) * TTS;
+#pragma unroll
+            for (int s = 0; s < NSTG; ++s) {
+                const int c = tid + s * THREADS;
+                if (c < NTT) cpAsync16(&sm[buf][c * CHUNK], src + c * CHUNK);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NSTG; ++s) {
+                const int c = tid + s * THREADS;
+                if (c < 2 * NCH) {
+                    const int o = c >= NCH ? 1 : 0;
+                    cpAsync16(&sm[buf][c * CHUNK], mats + static_cast<size_t>(o ? w.z : w.y) * MSZ + (c - o * NCH) * CHUNK);
+                }
+            }
+        }
+        cpAsyncCommit();
+    };
+
+    real X[4], Y[4];
+    int sX = 0, sY = 0;
+    double prod = 1.0, pendAcc = 0.0, pendProd = 1.0;
+    sAcc[tid] = 0.0;
+    auto accumulate = [&](double addAcc, double factor) {
+        const double t = prod * factor;
+        if (addAcc != 0.0) sAcc[tid] += addAcc;
+        if (t < 1e-200) {
+            sAcc[tid] += foldedLog(prod, factor);
+            prod = 1.0;
+        } else {
+            prod = t;
+        }
+    };
+    auto startChain = [&](const DevRec& r) {
+        if (r.flags & OP_A_TIP) sX = *byteOffset(tmine, r.aOff);
+        else ld4(byteOffset(pmine, r.aOff), X);
+        if (scalerThread) {
+            const int sa = r.sa;
+            if (sa >= 0) {
+                const double a = accMine[static_cast<size_t>(sa) * Ppad];
+                const double pr = prodMine[static_cast<size_t>(sa) * Ppad];
+                accumulate(a, pr);
+            }
+        }
+    };
+    auto fetchB = [&](const DevRec& r) {
+        if (r.flags & OP_B_TIP) sY = *byteOffset(tmine, r.bOff);
+        else ld4(byteOffset(pmine, r.bOff), Y);
+        if (scalerThread) {
+            const int sb = r.sb;
+            if (sb >= 0) {
+                pendAcc = accMine[static_cast<size_t>(sb) * Ppad];
+                pendProd = prodMine[static_cast<size_t>(sb) * Ppad];
+            }
+        }
+    };
+
+    auto step = [&](const int j, const int nc) {
+        const bool more = j + 1 < nc;
+        const DevRec& rec = sops[j];
+        const int flags = rec.flags;
+        const real* sa = sm[j & 1];
+        const real* sb = sa + MSZ;
+        double mfac = 1.0;
+        real m = real(1);
+        real v;                                              // state i of the new vector
+        if (flags & OP_TIPTIP) {
+            const int combo = sX * 5 + sY;
+            if (more) fetchB(sops[j + 1]);
+            v = sa[combo * TTE + k * 4 + i];
+            mfac = static_cast<double>(sa[25 * TTE + combo]);
+        } else {
+            real fa, fb;
+            if (flags & OP_A_TIP) {
+                fa = sa[tipIndex(k, sX, i)];
+            } else {
+                const real* row = sa + pmIndex(k, i * 4);
+                fa = row[0] * X[0];
+                fa += row[1] * X[1];
+                fa += row[2] * X[2];
+                fa += row[3] * X[3];
+            }
+            if (flags & OP_B_TIP) {
+                fb = sb[tipIndex(k, sY, i)];
+            } else {
+                const real* row = sb + pmIndex(k, i * 4);
+                fb = row[0] * Y[0];
+                fb += row[1] * Y[1];
+                fb += row[2] * Y[2];
+                fb += row[3] * Y[3];
+            }
+            v = fa * fb;
+            if (scalerThread && rec.sb >= 0) accumulate(pendAcc, pendProd);
+            if (more) fetchB(sops[j + 1]);
+            if (flags & OP_RESCALE) {
+                m = rmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                m = rmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                if (C > 1 && i == 0) smax[j & 1][k * G + q] = m;
+            }
+        }
+        if (more) cpAsyncWaitAll();
+        blockSync();                  // image j+1 and this step's maxima visible; everyone is done with image j
+        if (j + 2 < nc) stage(j & 1, sops[j + 2]);
+        if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) {
+            if (C > 1) {
+                m = smax[j & 1][q];
+#pragma unroll
+                for (int w = 1; w < C; ++w) m = rmax(m, smax[j & 1][w * G + q]);
+            }
+            constexpr real kTiny = sizeof(real) == 4 ? real(1e-30) : real(1e-290);
+            m = (m == real(0)) ? real(1) : m;
+            const real inv = (m < kTiny) ? real(1) / m : fastRcp(m);
+            v *= inv;
+            mfac = static_cast<double>(m);
+        }
+        // one state per lane: 8 bytes x 32 lanes = 256 contiguous bytes per warp
+        real* dest = byteOffset(pmine, rec.destOff) + i;
+        if (flags & OP_CHAIN_END) *dest = v;
+        else __stcs(dest, v);
+        // the whole vector again in every lane of the quad: operand A of the next step
+#pragma unroll
+        for (int s = 0; s < 4; ++s) X[s] = quadGather(v, lane, s);
+        if (scalerThread) {
+            {
+                const double t = prod * mfac;
+                if (t < 1e-200) {
+                    sAcc[tid] += foldedLog(prod, mfac);
+                    prod = 1.0;
+                } else {
+                    prod = t;
+                }
+            }
+            if (flags & (OP_STORE_S | OP_CHAIN_END)) {
+                const int sOut = rec.sOut;
+                double a = sAcc[tid];
+                if (sOut >= 0) {
+                    if (prod < 1e-100) {
+                        a += foldedLog(prod, 1.0);
+                        prod = 1.0;
+                        if (!(flags & OP_CHAIN_END)) sAcc[tid] = a;
+                    }
+                    accMine[static_cast<size_t>(sOut) * Ppad] = a;
+                    prodMine[static_cast<size_t>(sOut) * Ppad] = prod;
+                }
+                if (flags & OP_CHAIN_END) {
+                    if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr) {
+                        const double total = scalerTotal(a, prod);
+                        double* c = A.cum + pat;
+                        if (A.cumMode) *c = total;
+                        else *c += total;
+                    }
+                    sAcc[tid] = 0.0;
+                    prod = 1.0;
+                }
+            }
+        }
+        if (more && (sops[j + 1].flags & OP_CHAIN_START)) startChain(sops[j + 1]);
+    };
+
+    for (int chunk0 = 0; chunk0 < nOps; chunk0 += kOpChunk) {
+        const int nc = min(kOpChunk, nOps - chunk0);
+        if (chunk0 > 0) blockSync();
+        {
+            const int4* gops = reinterpret_cast<const int4*>(A.ops + grp.opStart + chunk0);
+            int4* dst = reinterpret_cast<int4*>(sops);
+            for (int w = tid; w < nc * kRecWords; w += THREADS) dst[w] = gops[w];
+        }
+        blockSync();
+        if (chunk0 == 0) pdlWait();
+        stage(0, sops[0]);
+        if (nc > 1) stage(1, sops[1]);
+        if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);
+        fetchB(sops[0]);
+        cpAsyncWaitAll();
+        blockSync();
 #pragma unroll 1
         for (int j = 0; j < nc; ++j) step(j, nc);
     }

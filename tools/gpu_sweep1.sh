@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+r738() { python tools/rbcl738_run.py 500 2>&1 | grep "device us" ; }
+b250() { python bench.py --taxa 1000 --patterns 250000 --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('250k ms', d['ms_per_step'], 'sched_frac', d['roofline'].get('scheduled_frac'))"; }
+{
+echo "== default"; r738; PINVAR=0.2 r738; b250
+for v in cpt4r128 cpt1 r96 pf2; do echo "== lib $v"; export STROM_B200_LIB=$PWD/tools/_var/$v/libstrom_b200.so; r738; b250; unset STROM_B200_LIB; done
+echo "== all wide"; SB200_VARIANT=1 r738
+echo "== all narrow"; SB200_VARIANT=2 r738
+for w in 300 600 2400 4800; do echo "== wide min warps $w"; SB200_WIDE_MIN_WARPS=$w r738; done
+for s in 444 888 1776 3552; do echo "== slots $s"; SB200_SLOTS=$s r738; done
+echo "== no tips kernel"; SB200_TIPS_KERNEL=0 r738
+} > gpurun_out/sweep1.log 2>&1
+cat gpurun_out/sweep1.log
+python tools/rbcl738_run.py 3 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -s 60 -c 12 --csv --log-file gpurun_out/r2_rbcl738_levels.csv python tools/rbcl738_run.py 3 > gpurun_out/ncu1.log 2>&1
+python bench.py --taxa 1000 --patterns 250000 --steps 1 --warmup 1 --no-cpu > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum -k regex:prune --clock-control none -c 10 --csv --log-file gpurun_out/r2_levels_1000x250k.csv python bench.py --taxa 1000 --patterns 250000 --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu2.log 2>&1
+echo done
