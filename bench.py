@@ -157,30 +157,89 @@ def synthetic_inputs(args, rank, world, device):
     return tree, model, tips_h, lo, hi
 
 
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 8 << 30
+
+
+def oracle_full_pass(args, tree, model, threads, slice_patterns, budget_s, max_passes):
+    """The CPU path over the WHOLE alignment, `slice_patterns` at a time (the oracle keeps all n-2 partials buffers of a
+    slice in host memory: 128 KB per pattern at 1000 taxa).  Returns (seconds per full evaluation, passes, summed logL)."""
+    import torch
+    from strom_b200 import synth
+    api = oracle_api(threads)
+    P = args.patterns
+    bounds = [(lo, min(P, lo + slice_patterns)) for lo in range(0, P, slice_patterns)]
+    # the SAME alignment as the GPU arm: its sites come from torch's CUDA generator (chunks of 125000 seeded by chunk
+    # index), so the GPU of the box simulates the input here too; only the likelihood is the CPU's work
+    gen_dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    inst, inst_P = None, -1
+    total, passes, logl = 0.0, 0, None
+    t_start = time.perf_counter()
+    while passes < max_passes:
+        ll_sum, secs = 0.0, 0.0
+        for lo, hi in bounds:
+            tips = synth.simulate_alignment(tree, model, lo, hi, seed=3, device=gen_dev).cpu().numpy()
+            if inst is None or inst_P != hi - lo:
+                if inst is not None:
+                    api.finalize(inst)
+                inst, inst_P = api.create(args.taxa, hi - lo, 4), hi - lo
+            api.set_data(inst, tips.astype(np.int32), np.ones(hi - lo))
+            del tips
+            if passes == 0 and lo == 0:      # untimed first touch of the partials arena
+                api.calc_log_likelihood(inst, model, tree.ops, tree.pmatrix_index, tree.edge_lengths, tree.parent_buffer, 0)
+            t0 = time.perf_counter()
+            ll_sum += api.calc_log_likelihood(inst, model, tree.ops, tree.pmatrix_index, tree.edge_lengths, tree.parent_buffer, 0)
+            secs += time.perf_counter() - t0
+        total += secs
+        passes += 1
+        logl = ll_sum
+        if time.perf_counter() - t_start + 1.3 * (time.perf_counter() - t_start) / passes > budget_s:
+            break
+    if inst is not None:
+        api.finalize(inst)
+    return total / passes, passes, logl, gen_dev
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (restated in oracle/; BeagleLib itself is not buildable
-    here) on the host cores, bounded sample of the same workload."""
+    here) on the host cores.  One step = one full evaluation of the SAME configuration as the GPU arm
+    (all patterns, processed in slices that fit the host's memory); as many such steps as fit the time budget."""
     if rank != 0:
         return None
     threads = host_threads()
     from strom_b200 import synth
     tree = synth.RandomTree(args.taxa, seed=1, mean_edge=0.05)
     model = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA, 4)
-    Ps = min(args.patterns, args.cpu_sample)
-    tips = synth.simulate_alignment(tree, model, 0, Ps, seed=3, device="cpu", chunk=Ps).numpy()
-    w = np.ones(Ps)
-    evals_s, done, ll = time_oracle(tips, w, model, tree.ops, tree.pmatrix_index, tree.edge_lengths, tree.parent_buffer,
-                                    threads, args.steps, args.warmup, budget_s=120.0)
-    upd = (args.taxa - 2) * Ps * 4 * evals_s
+    per_pattern = (args.taxa - 2) * 4 * 4 * 8 + 64
+    slice_patterns = int(max(1024, min(args.patterns, 125000, 0.4 * mem_available_bytes() / per_pattern)))
+    sec, passes, ll, gen_dev = oracle_full_pass(args, tree, model, threads, slice_patterns, budget_s=args.cpu_budget,
+                                                max_passes=max(1, args.steps))
+    evals_s = 1.0 / sec
+    upd = (args.taxa - 2) * args.patterns * 4 * evals_s
+    nslices = (args.patterns + slice_patterns - 1) // slice_patterns
     line = {
-        "impl": "reference", "metric": METRIC, "value": upd, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / evals_s, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": upd, "unit": UNIT, "n_gpus": args.gpus, "steps": passes,
+        "warmup": 1, "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, sample=Ps),
+        "config": workload_config(args),
+        "same_config": True,
         "cpu_baseline": {"value": upd, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "first %d of %d patterns, same tree and model; one step = one full evaluation" % (Ps, args.patterns)},
+                         "sample": "the whole alignment: %d patterns in %d slices of <= %d (host memory), same tree and model; "
+                                   "one step = one full evaluation of all slices; %d step(s) within the %.0f s budget "
+                                   "(alignment simulation and tip upload per slice not timed)"
+                                   % (args.patterns, nslices, slice_patterns, passes, args.cpu_budget)},
         "e2e": {"value": upd, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "evals_per_sec_on_sample": evals_s, "logL_sample": ll,
+        "evals_per_sec": evals_s, "logL": ll,
+        "data_generator": gen_dev + (" (same alignment as the GPU arm)" if gen_dev != "cpu" else
+                                     " (no GPU: torch's CPU generator gives another alignment of the same distribution; logL not comparable)"),
+        "note": "CPU restatement of the reference's BeagleLib path (oracle/beagle_cpu.c, plain C, %d threads); compare `logL` "
+                "with the GPU arm's `logL`" % threads,
     }
     return line
 
@@ -242,31 +301,48 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
     alg, sch = C.c_double(), C.c_double()
     E.sb200LastTraffic(L.inst, C.byref(alg), C.byref(sch))
     L.close()
-    # several independent evaluations at once on ONE GPU (each its own engine instance and stream), as the heated
-    # chains of an MC3 run are: one rbcl738 evaluation leaves most SMs idle, so they overlap
-    K = 4
-    Ls = [ShardedLikelihood(data, fx["counts"], NC, device=device) for _ in range(K)]
-    for Lk in Ls:
-        Lk.calc_log_likelihood(ea)
-    done = [torch.cuda.Event() for _ in range(K)]
-    def rounds(count):
-        for _ in range(count):
-            for Lk in Ls:
-                Lk.replay_async()
-    rounds(warmup)
-    torch.cuda.synchronize(device)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    main = torch.cuda.current_stream(device)
-    c0.record(main)
-    for Lk in Ls:
-        Lk.stream.wait_event(c0)
-    rounds(steps)
-    for Lk, ev in zip(Ls, done):
-        ev.record(Lk.stream)
-        main.wait_event(ev)
-    c1.record(main)
-    torch.cuda.synchronize(device)
-    conc_ms = c0.elapsed_time(c1) / (steps * K)
+    # K independent evaluations (own tree / model each, as the heated chains of an MC3 run) as ONE set of kernel
+    # launches on ONE GPU (sb200EvalBatchAsync): a single rbcl738 evaluation leaves most of the GPU idle
+    K = 8
+    from strom_b200.engine import StromEvalArgs
+    rng = np.random.default_rng(5)
+    Ls, eas = [], []
+    for c in range(K):
+        mk = gtr_gamma_model(PAUP_PI, PAUP_R, PAUP_ALPHA * (1.0 + 0.1 * c), 4)
+        if pinvar > 0.0:
+            mk["rates"], mk["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA * (1.0 + 0.1 * c), 4, pinvar)
+        elen = fx["edge_lengths"] * np.exp(0.2 * rng.standard_normal(fx["edge_lengths"].shape)) if c else fx["edge_lengths"]
+        Ls.append(ShardedLikelihood(data, fx["counts"], NC, device=device))
+        eas.append(EvalArgs(mk, fx["ops"], fx["pmatrix_index"], elen, int(fx["parent"]), 0))
+    single_vals = [Lk.calc_log_likelihood(ek) for Lk, ek in zip(Ls, eas)]
+    insts = (C.c_int * K)(*[Lk.inst for Lk in Ls])
+    bargs = (StromEvalArgs * K)(*[ek.c for ek in eas])
+    res = C.c_double()
+
+    def batch_eval():
+        E.check(E.sb200EvalBatchAsync(K, insts, bargs), "batched evaluation")
+        vals = []
+        for Lk in Ls:
+            E.check(E.sb200Finish(Lk.inst, C.byref(res)), "finish")
+            vals.append(res.value)
+        return vals
+    batch_vals = batch_eval()
+    batch_rel = max(abs(a - b) / abs(b) for a, b in zip(batch_vals, single_vals))
+    for _ in range(warmup):
+        E.check(E.sb200ReplayBatchAsync(K, insts), "replay")
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(Ls[0].stream):
+        Ls[0].stream.synchronize()
+        b0.record()
+        for _ in range(steps):
+            E.check(E.sb200ReplayBatchAsync(K, insts), "replay")
+        b1.record()
+        Ls[0].stream.synchronize()
+    batch_dev_ms = b0.elapsed_time(b1) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        batch_eval()
+    batch_e2e_ms = (time.perf_counter() - t0) * 1000.0 / steps
     for Lk in Ls:
         Lk.close()
     # the C++ Likelihood facade (strom_b200/host/likelihood.hpp): what strom's Chain / Updaters call
@@ -304,13 +380,53 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
         "evals_per_sec_e2e_fused_call": 1000.0 / fused_ms,
         "evals_per_sec_e2e_cpp_facade": 1.0 / sec, "logL_cpp_facade": llf,
         "evals_per_sec_e2e_cpp_facade_13_calls": (1.0 / sec13) if sec13 else None, "logL_cpp_facade_13_calls": llf13,
-        "evals_per_sec_device_4_concurrent_chains": 1000.0 / conc_ms,
+        "batched_chains": {"chains": K, "call": "sb200EvalBatchAsync: one set of kernel launches for all chains (own tree and model each)",
+                           "evals_per_sec_device": K * 1000.0 / batch_dev_ms, "evals_per_sec_e2e": K * 1000.0 / batch_e2e_ms,
+                           "us_per_batch_device": batch_dev_ms * 1000.0, "max_rel_diff_vs_single_evaluations": batch_rel,
+                           "speedup_e2e_vs_cpu_all_threads": (K * 1000.0 / batch_e2e_ms) / allc,
+                           "speedup_e2e_vs_cpu_1thread": (K * 1000.0 / batch_e2e_ms) / one},
         "partial_updates_per_sec_device": upd * 1000.0 / dev_ms,
+        "roofline": {"bound": "hbm", "achieved": alg.value / (dev_ms / 1000.0) / 1e9, "peak": peaks()[0], "unit": "GB/s",
+                     "frac": alg.value / (dev_ms / 1000.0) / 1e9 / peaks()[0],
+                     "scheduled_frac": sch.value / (dev_ms / 1000.0) / 1e9 / peaks()[0],
+                     "batched_frac": K * alg.value / (batch_dev_ms / 1000.0) / 1e9 / peaks()[0],
+                     "batched_scheduled_frac": K * sch.value / (batch_dev_ms / 1000.0) / 1e9 / peaks()[0],
+                     "traffic": None, "note": "whole evaluation (matrices, tables, pruning launches, root) per algorithmic / "
+                                              "scheduled byte of the pruning launches; the working set of ONE evaluation fits L2"},
         "cpu_evals_per_sec_1thread": one, "cpu_evals_per_sec_all_threads": allc, "cpu_threads": thr,
         "speedup_e2e_vs_cpu_1thread": (1.0 / sec) / one, "speedup_e2e_vs_cpu_all_threads": (1.0 / sec) / allc,
         "algorithmic_bytes_per_eval": alg.value, "scheduled_bytes_per_eval": sch.value,
         "l2": "warm: the 116 MB working set is re-used by every MCMC step, as in the reference's usage",
     }
+
+
+def mc3_block(devices, niter=200, burnin=100, nchains=8):
+    """BASELINE.json configs[4]: Metropolis-coupled MCMC, 8 heated chains on rbcl738 (reference loop src/strom.hpp:316-402),
+    through the C++ host driver: chains stepped in turn (the reference's order of work) against side by side -- one chain per
+    GPU on host threads when there are several GPUs, or, on ONE GPU, one host thread with the chains' evaluations batched
+    into one set of launches.  Same seed: the two traces must be identical."""
+    from strom_b200.host import host
+    H = host()
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "rbcl738.npz"))
+    data = np.minimum(fx["data"], 4).astype(np.int32)
+    cols = np.repeat(np.arange(data.shape[1]), fx["counts"].astype(int))
+    hd = H.data_from_codes(data[:, cols], compress=True)
+    kw = dict(seed=13579, niter=niter, burnin=burnin, samplefreq=1, nchains=nchains, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA,
+              freqs=PAUP_PI, rmat=[x / sum(PAUP_R) for x in PAUP_R], devices=tuple(devices))
+    H.mcmc(hd, str(fx["newick"]), **dict(kw, niter=4, burnin=2), per_chain_streams=True)                  # warm-up (instances, plans)
+    tr_turn, sec_turn = H.mcmc(hd, str(fx["newick"]), per_chain_streams=True, **kw)
+    if len(devices) > 1:
+        tr_side, sec_side = H.mcmc(hd, str(fx["newick"]), parallel_chains=True, **kw)
+        how = "one heated chain per GPU (%d GPUs), every chain on its own host thread" % len(devices)
+    else:
+        tr_side, sec_side = H.mcmc(hd, str(fx["newick"]), lockstep_chains=True, **kw)
+        how = "ONE GPU, one host thread: every update begun on all chains, their evaluations ONE set of kernel launches"
+    H.data_free(hd)
+    its = nchains * (niter + burnin)
+    same = tr_turn.shape == tr_side.shape and bool(np.array_equal(tr_turn, tr_side))
+    return {"workload": "rbcl738 GTR+G4, %d heated chains, %d iterations each (5 updates + a swap proposal per iteration)" % (nchains, niter + burnin),
+            "side_by_side": how, "chain_iterations_per_sec_in_turn": its / sec_turn, "chain_iterations_per_sec_side_by_side": its / sec_side,
+            "speedup": sec_turn / sec_side, "traces_identical": same, "gpus": len(devices)}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -341,17 +457,18 @@ def run_ours(args, rank, world, local_rank):
         L.replay_async()
     E.sb200SetProfiling(L.inst, 1)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]      # one event per step: p10 / p50 / p90
     barrier()
     launches0 = L.launches()
     with torch.cuda.stream(L.stream):
-        e0.record()
-        for _ in range(K):
+        evs[0].record()
+        for i in range(K):
             L.replay_async()
-        e1.record()
+            evs[i + 1].record()
     barrier()
     launches = L.launches() - launches0
-    dev_ms = e0.elapsed_time(e1)
+    dev_ms = evs[0].elapsed_time(evs[K])
+    step_ms = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(K)])
     clocks = sampler.stop() if sampler else None
     pms, pcalls = C.c_double(), C.c_long()
     E.sb200PartialsTime(L.inst, C.byref(pms), C.byref(pcalls))
@@ -374,13 +491,57 @@ def run_ours(args, rank, world, local_rank):
     e2e_wall_ms = (time.perf_counter() - t0) * 1000.0
     e2e_ms = e2.elapsed_time(e3)
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms, pms.value / max(pcalls.value, 1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms, pms.value / max(pcalls.value, 1)] + [float(x) for x in np.percentile(step_ms, [10, 50, 90])],
+                     dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_wall_ms, prune_ms = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, e2e_wall_ms, prune_ms, p10, p50, p90 = [float(x) for x in t.tolist()]
     L.close()
     del L
     torch.cuda.empty_cache()
+
+    # ---- self-check: the first cpu_sample patterns of THIS alignment on the GPU and on the CPU oracle ------------------
+    verify = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        Ps = min(Pl, args.cpu_sample)
+        Lv = ShardedLikelihood(np.ascontiguousarray(tips_h[:, :Ps]), np.ones(Ps), 4, device=local_rank, single=(args.dtype == "f32"))
+        gpu_sample = Lv.calc_log_likelihood(ea)
+        Lv.close()
+        verify = {"sample_patterns": Ps, "logL_sample_gpu": gpu_sample}
+
+    # ---- the stated FP32 variant on the same alignment (own roofline) --------------------------------------------------
+    f32 = None
+    if world == 1 and args.dtype == "f64" and not args.no_f32:
+        Lf = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, single=True)
+        lf = Lf.calc_log_likelihood(ea)
+        Kf = max(3, min(K, 5))
+        for _ in range(3):
+            Lf.replay_async()
+        E.sb200SetProfiling(Lf.inst, 1)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(Lf.stream):
+            Lf.stream.synchronize()
+            f0.record()
+            for _ in range(Kf):
+                Lf.replay_async()
+            f1.record()
+            Lf.stream.synchronize()
+        fms = f0.elapsed_time(f1) / Kf
+        fp, fc = C.c_double(), C.c_long()
+        E.sb200PartialsTime(Lf.inst, C.byref(fp), C.byref(fc))
+        fa, fs = C.c_double(), C.c_double()
+        E.sb200LastTraffic(Lf.inst, C.byref(fa), C.byref(fs))
+        Lf.close()
+        del Lf
+        torch.cuda.empty_cache()
+        fprune = fp.value / max(fc.value, 1)
+        pk = peaks()[0]
+        f32 = {"dtype": "f32 partials / matrices / tables, FP64 scalers and root accumulation (BEAGLE_FLAG_PRECISION_SINGLE)",
+               "value": float(n - 2) * args.patterns * 4 / (fms / 1000.0), "unit": UNIT, "ms_per_step": fms, "steps": Kf,
+               "logL": lf, "rel_diff_vs_f64": abs(lf - logl) / abs(logl), "stated_tolerance": 2e-5,
+               "roofline": {"bound": "hbm", "achieved": fa.value / (fprune / 1000.0) / 1e9, "peak": pk, "unit": "GB/s",
+                            "frac": fa.value / (fprune / 1000.0) / 1e9 / pk, "scheduled_frac": fs.value / (fprune / 1000.0) / 1e9 / pk,
+                            "algorithmic_bytes_per_eval": fa.value, "scheduled_bytes_per_eval": fs.value, "traffic": None}}
 
     if rank == 0:
         upd_per_eval = float(n - 2) * args.patterns * 4
@@ -388,18 +549,23 @@ def run_ours(args, rank, world, local_rank):
         e2e_val = upd_per_eval * K / (max(e2e_ms, e2e_wall_ms) / 1000.0)
         peak, peak_src = peaks()
         achieved = alg.value / (prune_ms / 1000.0) / 1e9            # this rank's slice / this rank's time
-        traffic = None
+        # DRAM bytes of the pruning launches from an ncu capture (profiles/traffic.json): a STORED figure, scaled by the
+        # pattern count, used only for the very shape it was captured on; otherwise null
+        traffic, traffic_source = None, "none: no ncu capture stored for this dtype / taxon count (profiles/traffic.json)"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("prune_chains_dram_bytes_per_eval")
-                if traffic is not None:
-                    traffic = traffic * (args.patterns / 1e6) / world      # captured at 1M patterns on one rank; linear in patterns
+                tj = json.load(open(tp))
+                if tj.get("dtype", "f64") == args.dtype and int(tj.get("taxa", 1000)) == args.taxa and tj.get("prune_chains_dram_bytes_per_eval"):
+                    traffic = tj["prune_chains_dram_bytes_per_eval"] * (args.patterns / float(tj.get("patterns", 1e6))) / world
+                    traffic_source = "stored: %s, scaled linearly to %d patterns / %d rank(s); not measured in this run" % (
+                        tj.get("source", "profiles/traffic.json"), args.patterns, world)
             except Exception:
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": dev_ms / K, "ms_per_step_p10": p10, "ms_per_step_p50": p50, "ms_per_step_p90": p90,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": workload_config(args),
             "evals_per_sec": K / (dev_ms / 1000.0), "logL": logl, "logL_e2e": logl2,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": ea.h2d_bytes, "d2h_bytes_per_step": 8,
@@ -409,24 +575,44 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "prune_chains_kernel (all level launches of one evaluation)",
+                         "traffic": traffic, "traffic_source": traffic_source,
+                         "kernel": "prune_chains_kernel (all level launches of one evaluation)",
                          "algorithmic_bytes_per_eval_per_rank": alg.value, "scheduled_bytes_per_eval_per_rank": sch.value,
                          "scheduled_frac": sch.value / (prune_ms / 1000.0) / 1e9 / peak,
                          "prune_ms_per_eval": prune_ms, "peak_source": peak_src},
         }
+        if f32 is not None:
+            line["f32"] = f32
         if world == 1 and not args.no_cpu:
             thr = host_threads()
             Ps = min(args.patterns, args.cpu_sample)
-            ev, done, _ = time_oracle(tips_h[:, :Ps], np.ones(Ps), model, tree.ops, tree.pmatrix_index, tree.edge_lengths,
-                                      tree.parent_buffer, thr, 50, 1, budget_s=12.0)
+            ev, done, llc = time_oracle(tips_h[:, :Ps], np.ones(Ps), model, tree.ops, tree.pmatrix_index, tree.edge_lengths,
+                                        tree.parent_buffer, thr, 50, 1, budget_s=12.0)
             ev1, done1, _ = time_oracle(tips_h[:, :Ps], np.ones(Ps), model, tree.ops, tree.pmatrix_index, tree.edge_lengths,
                                         tree.parent_buffer, 1, 50, 1, budget_s=12.0)
             line["cpu_baseline"] = {"value": (n - 2) * Ps * 4 * ev, "unit": UNIT, "cores": thr, "kind": "port",
                                     "sample": "first %d of %d patterns, same tree/model, %d evaluations" % (Ps, args.patterns, done),
                                     "single_thread_value": (n - 2) * Ps * 4 * ev1}
+            if verify is not None:
+                verify["logL_sample_cpu"] = llc
+                verify["rel_diff"] = abs(verify["logL_sample_gpu"] - llc) / abs(llc)
+                verify["ok"] = bool(verify["rel_diff"] < (2e-5 if args.dtype == "f32" else 1e-9))
+                verify["note"] = "the timed kernels on the first patterns of the benched alignment against the CPU oracle; the " \
+                                 "--impl reference arm prints the CPU logL of the WHOLE alignment to compare with `logL`"
+                line["verify"] = verify
             if not args.no_rbcl738:
                 line["rbcl738"] = rbcl738_block(E, local_rank)
                 line["rbcl738_i_g4"] = rbcl738_block(E, local_rank, pinvar=0.2)
+        if world == 1 and not args.no_mc3 and not args.no_rbcl738:
+            line["mc3"] = mc3_block([local_rank])
+    if distributed:
+        dist.barrier()                   # every rank has released its shard
+        if rank == 0 and world == 8 and not args.no_mc3:
+            # BASELINE.json configs[4]: 8 heated chains on rbcl738, one per GPU (the other ranks wait at the barrier below)
+            try:
+                line["mc3"] = mc3_block(list(range(world)))
+            except Exception as e:
+                line["mc3"] = {"error": repr(e)}
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -442,6 +628,9 @@ def main():
     ap.add_argument("--taxa", type=int, default=1000)
     ap.add_argument("--patterns", type=int, default=1000000)
     ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds the reference arm may spend on timed full evaluations")
+    ap.add_argument("--no-f32", action="store_true")
+    ap.add_argument("--no-mc3", action="store_true")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f32 = the stated FP32 variant (partials/matrices float)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rbcl738", action="store_true")

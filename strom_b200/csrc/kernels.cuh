@@ -827,6 +827,7 @@ prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
     };
 
     auto step = [&](const int j, const int nc) {
+        SB200_TICK(0)
         const bool more = j + 1 < nc;
         const DevRec& rec = sops[j];
         const int flags = rec.flags;
@@ -861,17 +862,22 @@ prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
                 fb += row[3] * Y[3];
             }
             v = fa * fb;
+            SB200_TICK(1)
             if (scalerThread && rec.sb >= 0) accumulate(pendAcc, pendProd);
             if (more) fetchB(sops[j + 1]);
+            SB200_TICK(2)
             if (flags & OP_RESCALE) {
                 m = rmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
                 m = rmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
                 if (C > 1 && i == 0) smax[j & 1][k * G + q] = m;
             }
         }
+        SB200_TICK(3)
         if (more) cpAsyncWaitAll();
         blockSync();                  // image j+1 and this step's maxima visible; everyone is done with image j
+        SB200_TICK(4)
         if (j + 2 < nc) stage(j & 1, sops[j + 2]);
+        SB200_TICK(5)
         if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) {
             if (C > 1) {
                 m = smax[j & 1][q];
@@ -884,6 +890,7 @@ prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
             v *= inv;
             mfac = static_cast<double>(m);
         }
+        SB200_TICK(6)
         // one state per lane: 8 bytes x 32 lanes = 256 contiguous bytes per warp
         real* dest = byteOffset(pmine, rec.destOff) + i;
         if (flags & OP_CHAIN_END) *dest = v;
@@ -926,6 +933,7 @@ prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
             }
         }
         if (more && (sops[j + 1].flags & OP_CHAIN_START)) startChain(sops[j + 1]);
+        SB200_TICK(7)
     };
 
     for (int chunk0 = 0; chunk0 < nOps; chunk0 += kOpChunk) {

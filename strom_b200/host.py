@@ -36,6 +36,8 @@ class HostAPI:
                                  _DP, _DP, C.c_int, _IP, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         L.strom_mcmc_ex.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint,
                                     C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
+        L.strom_mcmc_ex2.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint,
+                                     C.c_double, C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         L.strom_incremental_walk.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, _IP, C.c_uint,
                                              C.c_int, _DP, _DP, _IP, _DP, _DP, C.c_char_p, C.c_int]
         self._err = C.create_string_buffer(1024)
@@ -121,13 +123,15 @@ class HostAPI:
     def mcmc(self, data_handle: int, newick: str, seed: int = 13579, niter: int = 100, burnin: int = 100, samplefreq: int = 1,
              nchains: int = 1, heatfactor: float = 0.5, ncateg: int = 4, gammashape: float = 0.5, freqs=(0.25,) * 4,
              rmat=(1.0 / 6,) * 6, devices=(0,), per_chain_streams: bool = False, parallel_chains: bool = False,
-             incremental: bool = False, lockstep_chains: bool = False):
+             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True):
         """Returns (trace [rows][15] = iteration, lnL, lnPrior, TL, 6 r, 4 pi, alpha; seconds).
 
         ``parallel_chains``: the heated chains are stepped side by side on host threads (one chain per GPU of
         ``devices``), each with its own random stream; ``per_chain_streams`` alone keeps them in turn;
         ``lockstep_chains``: one host thread, every update begun on all chains before it is finished on any, so the
-        chains' likelihoods overlap on the GPU(s) they share -- same trace as ``per_chain_streams``."""
+        chains' likelihoods overlap on the GPU(s) they share -- same trace as ``per_chain_streams``; with
+        ``batch_evaluations`` (engine builds) the evaluations the chains of one GPU begin together are ONE set of kernel
+        launches.  ``pinvar`` > 0: GTR+I+G with that fixed proportion of invariable sites."""
         f = np.ascontiguousarray(freqs, dtype=np.float64)
         r = np.ascontiguousarray(rmat, dtype=np.float64)
         dev = np.ascontiguousarray(devices, dtype=np.int32)
@@ -135,11 +139,11 @@ class HostAPI:
         rows = np.zeros((max_rows, 15))
         sec = C.c_double()
         flags = (1 if per_chain_streams else 0) | (2 if parallel_chains else 0) | (4 if incremental else 0) | \
-            (8 if lockstep_chains else 0)
-        n = self._check(self.lib.strom_mcmc_ex(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor,
-                                               ncateg, gammashape, f.ctypes.data_as(_DP), r.ctypes.data_as(_DP), int(dev.size),
-                                               dev.ctypes.data_as(_IP), flags, rows.ctypes.data_as(_DP), max_rows, C.byref(sec),
-                                               self._err, 1024))
+            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16)
+        n = self._check(self.lib.strom_mcmc_ex2(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor,
+                                                ncateg, gammashape, float(pinvar), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
+                                                int(dev.size), dev.ctypes.data_as(_IP), flags, rows.ctypes.data_as(_DP), max_rows,
+                                                C.byref(sec), self._err, 1024))
         return rows[:n].copy(), sec.value
 
 

@@ -302,13 +302,30 @@ HOST_API int strom_local_move_check(const char* newick, unsigned seed, double la
 // `flags`: 1 = every chain draws from its own random stream, 2 = chains are stepped side by side on host threads
 // (one heated chain per GPU; implies 1), 4 = incremental likelihood (only the changed path is re-evaluated).
 // 8 = lockstep: one host thread begins every update on all chains before finishing it on any (implies 1).
+// 16 = lockstep WITHOUT handing the chains' evaluations to the engine as one set of launches (for comparison).
 // 0 = the reference's single shared stream, chains in turn, every node recomputed on every call.
+// pinvar > 0: GTR+I+G with that fixed proportion of invariable sites.
+HOST_API int strom_mcmc_ex2(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
+                            unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, double pinvar, const double* freqs,
+                            const double* rmat, int ndevices, const int* devices, unsigned flags, double* rows, int max_rows, double* seconds,
+                            char* err, int errlen);
+
 HOST_API int strom_mcmc_ex(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
                            unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, const double* freqs, const double* rmat,
                            int ndevices, const int* devices, unsigned flags, double* rows, int max_rows, double* seconds, char* err,
                            int errlen) {
+    return strom_mcmc_ex2(data_handle, newick, seed, niter, burnin, samplefreq, nchains, heatfactor, ncateg, gammashape, 0.0, freqs, rmat,
+                          ndevices, devices, flags, rows, max_rows, seconds, err, errlen);
+}
+
+HOST_API int strom_mcmc_ex2(int data_handle, const char* newick, unsigned seed, unsigned niter, unsigned burnin, unsigned samplefreq,
+                            unsigned nchains, double heatfactor, unsigned ncateg, double gammashape, double pinvar, const double* freqs,
+                            const double* rmat, int ndevices, const int* devices, unsigned flags, double* rows, int max_rows, double* seconds,
+                            char* err, int errlen) {
     try {
         McmcOptions opt;
+        opt.pinvar = pinvar;
+        opt.batchEvaluations = (flags & 16u) == 0;
         opt.seed = seed; opt.niter = niter; opt.burnin = burnin; opt.samplefreq = samplefreq ? samplefreq : 1; opt.nchains = nchains;
         opt.heatfactor = heatfactor; opt.ncateg = ncateg; opt.gammashape = gammashape;
         opt.statefreq.assign(freqs, freqs + 4);

@@ -478,6 +478,8 @@ struct TraceRow {
 struct McmcOptions {
     unsigned seed = 13579, niter = 100, burnin = 100, samplefreq = 1, nchains = 1, ncateg = 4;
     double heatfactor = 0.5, gammashape = 0.5;
+    double pinvar = 0.0;                     // GTR+I+G (north-star extension: the reference has no such parameter, src/model.hpp:60-76):
+                                             // a FIXED proportion of invariable sites, one more rate category; no updater moves it
     std::vector<double> statefreq = {0.25, 0.25, 0.25, 0.25};
     std::vector<double> rmatrix = {1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6, 1.0 / 6};   // on the simplex, like strom's default
     std::vector<int> devices = {0};          // chain c runs on devices[c % size]: one heated chain per GPU
@@ -489,6 +491,8 @@ struct McmcOptions {
     bool lockstepChains = false;             // ONE host thread: every update is begun (proposed, likelihood enqueued) on all
                                              // chains before it is finished on any, so the chains' evaluations overlap on the
                                              // GPU(s) they share (implies perChainStreams; same trace as perChainStreams alone)
+    bool batchEvaluations = true;            // lockstep, engine builds: the evaluations the chains of one GPU begin together go
+                                             // to the engine as ONE set of kernel launches (sb200EvalBatchAsync); same values
     bool parallelChains = false;             // every chain runs on its own host thread (implies perChainStreams); only the two
                                              // chains of a swap proposal wait for each other.  Same trace as perChainStreams
                                              // alone, whatever the thread timing
@@ -513,6 +517,9 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
     Lot::SharedPtr lot(new Lot(opt.seed));
     const bool ownStreams = opt.perChainStreams || opt.parallelChains || opt.lockstepChains;
     std::vector<Chain> chains(opt.nchains);
+#ifdef STROM_B200_ENGINE
+    std::map<int, EvalBatcher::SharedPtr> batchers;                // one per GPU
+#endif
     for (unsigned c = 0; c < opt.nchains; ++c) {
         Chain& ch = chains[c];
         ch.setTreeFromNewick(newick);
@@ -521,10 +528,18 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         model->setExchangeabilitiesAndStateFreqs(opt.rmatrix, opt.statefreq);
         model->setGammaShape(opt.gammashape);
         model->setGammaNCateg(opt.ncateg);
+        if (opt.pinvar > 0.0) model->setPinvar(opt.pinvar);
         Likelihood::SharedPtr lik(new Likelihood());
         lik->setQuiet(true);
         lik->setIncremental(opt.incremental);
         lik->setDevices(std::vector<int>(1, opt.devices[c % opt.devices.size()]));
+#ifdef STROM_B200_ENGINE
+        if (opt.lockstepChains && opt.batchEvaluations && !opt.parallelChains && opt.nchains > 1) {
+            EvalBatcher::SharedPtr& b = batchers[opt.devices[c % opt.devices.size()]];
+            if (!b) b.reset(new EvalBatcher());
+            lik->setBatcher(b);
+        }
+#endif
         lik->setData(data);
         lik->setModel(model);
         if (std::getenv("STROM_HOST_NODATA")) lik->useStoredData(false);   // tuning aid: host cost of an iteration without likelihoods
