@@ -38,6 +38,8 @@ class HostAPI:
                                     C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         L.strom_mcmc_ex2.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint,
                                      C.c_double, C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
+        L.strom_incremental_rebuild_check.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_int, C.c_uint, _DP, C.c_char_p,
+                                                      C.c_int]
         L.strom_incremental_walk.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, _IP, C.c_uint,
                                              C.c_int, _DP, _DP, _IP, _DP, _DP, C.c_char_p, C.c_int]
         self._err = C.create_string_buffer(1024)
@@ -147,6 +149,10 @@ class HostAPI:
         return rows[:n].copy(), sec.value
 
 
+    def rebuild_check(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, rounds: int = 10, seed: int = 1) -> float:
+        """Incremental against full evaluation over a sequence of trees rebuilt from newick strings (test hook)."""
+        return self._rebuild_check(data_handle, newick, freqs, rmat, shape, ncat, rounds, seed)
+
     def incremental_walk(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0,
                          devices=(0,), seed: int = 1, nsteps: int = 100):
         """Random tree moves evaluated incrementally and in full: (incremental logL[], full logL[], ops listed[],
@@ -163,6 +169,15 @@ class HostAPI:
                                                         b.ctypes.data_as(_DP), k.ctypes.data_as(_IP), C.byref(si), C.byref(sf),
                                                         self._err, 1024))
         return a[:n], b[:n], k[:n], si.value, sf.value
+
+
+    def _rebuild_check(self, data_handle, newick, freqs, rmat, shape, ncat, rounds, seed):
+        f = np.ascontiguousarray(freqs, dtype=np.float64)
+        r = np.ascontiguousarray(rmat, dtype=np.float64)
+        worst = C.c_double()
+        self._check(self.lib.strom_incremental_rebuild_check(data_handle, newick.encode(), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
+                                                             shape, ncat, rounds, seed, C.byref(worst), self._err, 1024))
+        return worst.value
 
 
 _host = None

@@ -260,6 +260,46 @@ HOST_API int strom_incremental_walk(int data_handle, const char* newick, const d
     } catch (const std::exception& e) { return fail(e, err, errlen); }
 }
 
+// TEST HOOK: an incremental Likelihood is shown a sequence of trees, each built anew by
+// TreeManip::buildFromNewick -- a new Tree object every round, usually at the address of the one just destroyed -- after an
+// NNI swap and a change of three edge lengths; a second Likelihood recomputes everything.  worst_out receives the largest
+// |incremental - full| / |full|.
+HOST_API int strom_incremental_rebuild_check(int data_handle, const char* newick, const double* freqs, const double* rmat, double shape,
+                                             int ncat, int rounds, unsigned seed, double* worst_out, char* err, int errlen) {
+    try {
+        Data::SharedPtr d = dataOf(data_handle);
+        Likelihood::SharedPtr inc(new Likelihood()), full(new Likelihood());
+        Model::SharedPtr model = makeModel(freqs, rmat, shape, ncat, 0.0);
+        for (Likelihood::SharedPtr L : {inc, full}) {
+            L->setQuiet(true);
+            L->setData(d);
+            L->setModel(model);
+        }
+        inc->setIncremental(true);
+        Lot lot(seed);
+        std::string current = newick;
+        double worst = 0.0;
+        TreeManip tm;
+        for (int r = 0; r < rounds; ++r) {
+            tm.buildFromNewick(current, false, false);           // the previous Tree dies here
+            const double a = inc->calcLogLikelihood(tm.getTree());
+            const double b = full->calcLogLikelihood(tm.getTree());
+            worst = std::max(worst, std::fabs(a - b) / std::fabs(b));
+            Node* x = tm.randomInternalEdge(lot.uniform());
+            Node* child = x->getLeftChild();
+            Node* y = x->getParent();
+            Node* sib = (x == y->getLeftChild()) ? x->getRightSib() : y->getLeftChild();
+            child->setEdgeLength(child->getEdgeLength() * std::exp(lot.uniform() - 0.5));
+            x->setEdgeLength(x->getEdgeLength() * std::exp(lot.uniform() - 0.5));
+            sib->setEdgeLength(sib->getEdgeLength() * std::exp(lot.uniform() - 0.5));
+            tm.nniNodeSwap(child, sib);
+            current = tm.makeNewick(12);
+        }
+        if (worst_out) *worst_out = worst;
+        return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
 // TEST HOOK for the LOCAL move (mcmc.hpp::TreeUpdater): `nsteps` proposals on the tree; each is first made and taken back
 // (the tree must then be exactly the one before: same shape, same 17-digit edge lengths) and then made again and kept.  Returns the number of take-backs that did
 // NOT restore the tree; counts topology-changing proposals, and the largest |focal path after / (m * before) - 1| and

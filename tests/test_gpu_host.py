@@ -143,6 +143,10 @@ def test_device_pattern_compression_matches_host(ntaxa, nsites, alphabet, seed):
     got, counts = api().compress_patterns(codes)
     assert got.shape == want.shape and np.array_equal(got, want) and np.array_equal(counts, wcounts)
     assert counts.sum() == nsites
+    # ... and directly against the oracle's restatement of Data::compressPatterns (sorted unique columns)
+    from oracle import strom_host_ref as HR
+    owant, ocounts = HR.compress_patterns(codes.astype(np.int32))
+    assert np.array_equal(got, owant) and np.array_equal(counts, ocounts)
     hd = H.data_from_codes(codes.astype(np.int32), compress=2)
     m, w, ns = H.data_arrays(hd)
     H.data_free(hd)
@@ -156,3 +160,17 @@ def test_device_pattern_compression_rejects_wide_codes():
     codes[1, 4] = 32
     with pytest.raises(BeagleError):
         api().compress_patterns(codes)
+
+
+def test_incremental_cache_is_tied_to_the_tree_object_not_its_address():
+    """the incremental facade used to recognise "the same tree" by its address.  A tree that is destroyed and
+    rebuilt (TreeManip::buildFromNewick makes a new Tree, usually at the address the old one had) must be evaluated afresh."""
+    from helpers import PAUP_ALPHA, PAUP_PI, PAUP_R
+    from strom_b200.host import host
+    H = host()
+    fx = load_golden("rbcl10")
+    cols = np.repeat(np.arange(fx["data"].shape[1]), fx["counts"].astype(int))
+    h = H.data_from_codes(fx["data"].astype(np.int32)[:, cols], compress=True)
+    bad = H.rebuild_check(h, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, rounds=12, seed=3)
+    H.data_free(h)
+    assert bad < 1e-12

@@ -87,3 +87,53 @@ def test_incremental_trace_matches_cpu_call_path(key, kw):
     cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), key, **kw)
     rel = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-300)
     assert gpu.shape == cpu.shape and rel.max() <= 1e-9
+
+
+def test_rbcl738_trace_matches_cpu_call_path():
+    """BASELINE.json configs[2]: the real 738-taxon data set, two heated chains with swaps, all five updaters (reference call
+    chain src/updater.hpp:184-225 -> src/likelihood.hpp:390-448): CUDA engine against the CPU call path, same seed."""
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    kw = dict(niter=24, burnin=16, nchains=2, samplefreq=4, seed=2024, gammashape=0.5)
+    gpu, _ = _run(host(), "rbcl738", **kw)
+    cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), "rbcl738", **kw)
+    assert gpu.shape == cpu.shape and gpu.shape[0] == 7
+    rel = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-300)
+    bad = np.argwhere(rel > 1e-9)
+    assert bad.size == 0, "first divergence at sample row %d column %d: gpu %r cpu %r" % (
+        bad[0][0], bad[0][1], gpu[bad[0][0], bad[0][1]], cpu[bad[0][0], bad[0][1]])
+
+
+@pytest.mark.parametrize("key,kw", [("rbcl10", dict(niter=200, burnin=100, nchains=2, samplefreq=10, seed=5)),
+                                    ("rbcl738", dict(niter=10, burnin=6, nchains=1, samplefreq=2, seed=11))])
+def test_invariable_sites_mcmc_trace_matches_cpu_call_path(key, kw):
+    """GTR+I+G4 (BASELINE.json configs[2]; +I is a north-star extension, the reference has no such parameter): an MCMC with a
+    fixed proportion of invariable sites -- five categories on the engine -- against the CPU call path."""
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    gpu, _ = _run(host(), key, pinvar=0.2, **kw)
+    cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), key, pinvar=0.2, **kw)
+    plain, _ = _run(host(), key, **kw)
+    assert gpu.shape == cpu.shape
+    rel = np.abs(gpu - cpu) / np.maximum(np.abs(cpu), 1e-300)
+    assert rel.max() <= 1e-9
+    assert not np.allclose(gpu[:, 1], plain[:, 1])                    # (+I really is another model)
+
+
+def test_eight_heated_chains_on_rbcl738_side_by_side_in_turn_and_cpu():
+    """BASELINE.json configs[4] (reference loop src/strom.hpp:316-402): 8 heated chains on rbcl738.  Stepped side by side on host
+    threads (one engine instance per chain, spread over the visible GPUs), in lockstep with their evaluations batched into one
+    set of launches, and in turn: bit for bit the same trace; and the CPU call path's to tolerance."""
+    import torch
+    from strom_b200.build import HOST_ORACLE_LIB
+    from strom_b200.host import HostAPI, host
+    devices = tuple(range(torch.cuda.device_count()))
+    kw = dict(niter=6, burnin=4, nchains=8, samplefreq=2, seed=31, gammashape=0.5)
+    side, _ = _run(host(), "rbcl738", parallel_chains=True, devices=devices, **kw)
+    turn, _ = _run(host(), "rbcl738", per_chain_streams=True, devices=devices, **kw)
+    lock, _ = _run(host(), "rbcl738", lockstep_chains=True, **kw)
+    lock_unbatched, _ = _run(host(), "rbcl738", lockstep_chains=True, batch_evaluations=False, **kw)
+    assert np.array_equal(side, turn) and np.array_equal(lock, turn) and np.array_equal(lock_unbatched, turn)
+    cpu, _ = _run(HostAPI(HOST_ORACLE_LIB), "rbcl738", per_chain_streams=True, **kw)
+    rel = np.abs(turn - cpu) / np.maximum(np.abs(cpu), 1e-300)
+    assert turn.shape == cpu.shape and rel.max() <= 1e-9

@@ -343,9 +343,160 @@ def test_incremental_lists_cover_only_the_changed_path(engine, oracle, source, m
         assert rel_err(a, b) < LOGL_RTOL, (it, len(sub))
     assert min(sizes) == 1 and max(sizes) < len(ops)
     # a new model invalidates everything: full list again, then incremental lists keep working
-    m2 = named_model("gtr_i_g4" if len(m["rates"]) == 4 else model)
+    # (same category count as the instance: 13-call uploads carry no count of their own)
+    from helpers import PAUP_PI, PAUP_R, make_model
+    from oracle import strom_host_ref as HR
+    ncat = len(m["rates"])
+    m2 = make_model(PAUP_PI, PAUP_R, *(HR.invariant_gamma_rates(0.9, ncat - 1, 0.3) if model == "gtr_i_g4" else HR.gamma_rates(0.9, ncat)))
+    assert len(m2["rates"]) == ncat
     a = engine.calc_log_likelihood(ie, m2, ops, pidx, el, parent, 0)
     b = oracle.calc_log_likelihood(io, m2, ops, pidx, el, parent, 0)
     assert rel_err(a, b) < LOGL_RTOL
     engine.finalize(ie)
     oracle.finalize(io)
+
+
+# ---- sets of evaluations as one set of launches (sb200EvalBatchAsync) ---------------------------------------------------
+def _batch_setup(engine, problems, models, single=False):
+    from strom_b200.engine import EvalArgs, StromEvalArgs, api
+    E = api()
+    insts, eas = [], []
+    for pr, m in zip(problems, models):
+        n, P = pr["data"].shape
+        inst = engine.create(n, P, len(m["rates"]), single=single)
+        engine.set_data(inst, pr["data"].astype(np.int32), pr["counts"])
+        insts.append(inst)
+        eas.append(EvalArgs(m, pr["ops"], pr["pmatrix_index"], pr["edge_lengths"], int(pr["parent"]), 0))
+    return E, insts, eas
+
+
+def _batch_eval(E, insts, eas):
+    from strom_b200.engine import StromEvalArgs
+    K = len(insts)
+    ci = (C.c_int * K)(*insts)
+    ca = (StromEvalArgs * K)(*[e.c for e in eas])
+    rc = E.sb200EvalBatchAsync(K, ci, ca)
+    if rc != 0:
+        return rc, None
+    out, vals = C.c_double(), []
+    for i in insts:
+        assert E.sb200Finish(i, C.byref(out)) == 0
+        vals.append(out.value)
+    return 0, vals
+
+
+@pytest.mark.parametrize("model,K,ntaxa,npat", [("gtr_g4", 8, 30, 700), ("gtr_i_g4", 3, 17, 95), ("jc", 11, 9, 33), ("gtr_g8", 2, 60, 1500)])
+def test_batched_evaluations_match_the_oracle_chain_by_chain(engine, oracle, model, K, ntaxa, npat):
+    """K chains -- the same alignment, a tree (own topology and edge lengths) and a model each -- as one set of launches:
+    every chain's value against the CPU oracle, every chain's root partials and cumulative scalers too; and bit for bit the
+    value of the same chain evaluated on its own."""
+    from helpers import PAUP_PI, PAUP_R, make_model
+    from oracle import strom_host_ref as HR
+    base = random_problem(ntaxa, npat, seed=100 + K)
+    problems, models = [], []
+    ncat = len(named_model(model)["rates"])
+    for c in range(K):
+        pr = random_problem(ntaxa, npat, seed=200 + 7 * c)          # another topology ...
+        pr["data"], pr["counts"] = base["data"], base["counts"]     # ... on the same alignment
+        problems.append(pr)
+        if model == "jc":
+            models.append(named_model("jc"))
+        elif model == "gtr_i_g4":
+            models.append(make_model(PAUP_PI, PAUP_R, *HR.invariant_gamma_rates(0.3 + 0.2 * c, 4, 0.1 + 0.05 * c)))
+        else:
+            models.append(make_model(PAUP_PI, PAUP_R, *HR.gamma_rates(0.3 + 0.2 * c, ncat)))
+    E, insts, eas = _batch_setup(engine, problems, models)
+    rc, vals = _batch_eval(E, insts, eas)
+    assert rc == 0
+    xe, xo = Extra(engine), Extra(oracle)
+    for c, (pr, m) in enumerate(zip(problems, models)):
+        want, io = full_eval(oracle, pr, m, keep=True)
+        assert rel_err(vals[c], want) < LOGL_RTOL, c
+        P, Cc = pr["data"].shape[1], len(m["rates"])
+        root = int(pr["parent"])
+        assert np.allclose(xe.partials(insts[c], root, P, Cc), xo.partials(io, root, P, Cc), rtol=1e-12, atol=0)
+        assert np.allclose(xe.scale(insts[c], 0, P), xo.scale(io, 0, P), rtol=1e-12, atol=1e-12)
+        oracle.finalize(io)
+    # the same chains one at a time: the same bits
+    for c, (inst, ea) in enumerate(zip(insts, eas)):
+        out = C.c_double()
+        assert E.sb200Eval(inst, C.byref(ea.c), C.byref(out)) == 0
+        assert out.value == vals[c], c
+    # a second batched call after single calls (plans for both launch shapes are kept)
+    rc, again = _batch_eval(E, insts, eas)
+    assert rc == 0 and again == vals
+    for i in insts:
+        engine.finalize(i)
+
+
+def test_batched_evaluation_rejects_bad_sets_without_enqueueing(engine):
+    pr = random_problem(12, 64, seed=5)
+    E, insts, eas = _batch_setup(engine, [pr, pr], [named_model("gtr_g4"), named_model("gtr_g4")])
+    rc, vals = _batch_eval(E, insts, eas)
+    assert rc == 0
+    # the same instance twice
+    rc, _ = _batch_eval(E, [insts[0], insts[0]], eas)
+    assert rc == -5
+    # a chain whose category count differs from the first one's
+    E2, other, eo = _batch_setup(engine, [pr], [named_model("gtr_g8")])
+    rc, _ = _batch_eval(E, [insts[0], other[0]], [eas[0], eo[0]])
+    assert rc == -5
+    # an out-of-range matrix index in the SECOND chain: nothing of the first one may have been touched
+    from strom_b200.engine import EvalArgs
+    bad = EvalArgs(named_model("gtr_g4"), pr["ops"], pr["pmatrix_index"] + 1000, pr["edge_lengths"], int(pr["parent"]), 0)
+    rc, _ = _batch_eval(E, insts, [eas[0], bad])
+    assert rc == -5
+    # a model with another category count than the instance was created with
+    wrong = EvalArgs(named_model("gtr_g8"), pr["ops"], pr["pmatrix_index"], pr["edge_lengths"], int(pr["parent"]), 0)
+    rc, _ = _batch_eval(E, insts, [eas[0], wrong])
+    assert rc == -5
+    rc, again = _batch_eval(E, insts, eas)
+    assert rc == 0 and again == vals
+    for i in insts + other:
+        engine.finalize(i)
+
+
+@pytest.mark.parametrize("model", ["gtr_g4", "gtr_i_g4", "jc", "gtr_g3"])
+def test_every_thread_shape_gives_the_same_bits(engine, oracle, model, monkeypatch):
+    """The launches of a small instance choose between three thread shapes (all categories of a pattern in a thread / a warp
+    per category / a thread per state); forcing each one on every launch gives bit-identical partials, scalers and logL."""
+    pr = random_problem(25, 300, seed=77)
+    m = named_model(model)
+    P, Cc = pr["data"].shape[1], len(m["rates"])
+    want = full_eval(oracle, pr, m)
+    xe = Extra(engine)
+    seen = []
+    for shape in ("", "1", "2", "3"):
+        if shape:
+            monkeypatch.setenv("SB200_VARIANT", shape)
+        else:
+            monkeypatch.delenv("SB200_VARIANT", raising=False)
+        ll, inst = full_eval(engine, pr, m, keep=True)                    # (the instance reads the variable when it is created)
+        bufs = [xe.partials(inst, 25 + b, P, Cc) for b in range(23)]
+        seen.append((ll, bufs, xe.scale(inst, 0, P)))
+        engine.finalize(inst)
+        assert rel_err(ll, want) < LOGL_RTOL
+    for ll, bufs, sc in seen[1:]:
+        assert ll == seen[0][0] and np.array_equal(sc, seen[0][2])
+        assert all(np.array_equal(a, b) for a, b in zip(bufs, seen[0][1]))
+
+
+def test_incremental_list_that_reads_a_slot_nobody_wrote_is_rejected(engine):
+    """sb200SetSubtreeScalers: the first list after enabling must cover every node; a partial first list would read
+    subtree scalers that no call has stored -- now BEAGLE_ERROR_OUT_OF_RANGE instead of a wrong value."""
+    pr = random_problem(16, 100, seed=9)
+    m = named_model("gtr_g4")
+    n, P = pr["data"].shape
+    inst = engine.create(n, P, 4)
+    engine.set_data(inst, pr["data"].astype(np.int32), pr["counts"])
+    engine.lib.sb200SetSubtreeScalers.argtypes = [C.c_int, C.c_int]
+    assert engine.lib.sb200SetSubtreeScalers(inst, 1) == 0
+    from strom_b200.beagle import BeagleError
+    root_only = pr["ops"][-1:]
+    with pytest.raises(BeagleError) as e:
+        engine.calc_log_likelihood(inst, m, root_only, pr["pmatrix_index"], pr["edge_lengths"], int(pr["parent"]), 0)
+    assert e.value.code == -5
+    full = engine.calc_log_likelihood(inst, m, pr["ops"], pr["pmatrix_index"], pr["edge_lengths"], int(pr["parent"]), 0)
+    again = engine.calc_log_likelihood(inst, m, root_only, pr["pmatrix_index"][-1:], pr["edge_lengths"][-1:], int(pr["parent"]), 0)
+    assert rel_err(again, full) < 1e-13
+    engine.finalize(inst)
