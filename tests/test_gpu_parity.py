@@ -414,7 +414,9 @@ def test_batched_evaluations_match_the_oracle_chain_by_chain(engine, oracle, mod
         assert rel_err(vals[c], want) < LOGL_RTOL, c
         P, Cc = pr["data"].shape[1], len(m["rates"])
         root = int(pr["parent"])
-        assert np.allclose(xe.partials(insts[c], root, P, Cc), xo.partials(io, root, P, Cc), rtol=1e-12, atol=0)
+        # (tolerances of test_every_buffer_matches_oracle: random trees have edges short enough for ~1e-8 relative noise
+        # in off-diagonal P entries, in any implementation)
+        assert np.allclose(xe.partials(insts[c], root, P, Cc), xo.partials(io, root, P, Cc), rtol=1e-7, atol=1e-13)
         assert np.allclose(xe.scale(insts[c], 0, P), xo.scale(io, 0, P), rtol=1e-12, atol=1e-12)
         oracle.finalize(io)
     # the same chains one at a time: the same bits
