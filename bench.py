@@ -343,6 +343,37 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
     for _ in range(steps):
         batch_eval()
     batch_e2e_ms = (time.perf_counter() - t0) * 1000.0 / steps
+    # ... the same with transient partials (only the last node of every chain is written)
+    for Lk in Ls:
+        E.check(E.sb200SetTransientPartials(Lk.inst, 1), "transient partials")
+    tr_vals = batch_eval()
+    tr_rel = max(abs(a - b) / abs(b) for a, b in zip(tr_vals, single_vals))
+    for _ in range(warmup):
+        E.check(E.sb200ReplayBatchAsync(K, insts), "replay")
+    with torch.cuda.stream(Ls[0].stream):
+        Ls[0].stream.synchronize()
+        b0.record()
+        for _ in range(steps):
+            E.check(E.sb200ReplayBatchAsync(K, insts), "replay")
+        b1.record()
+        Ls[0].stream.synchronize()
+    tr_batch_dev_ms = b0.elapsed_time(b1) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        batch_eval()
+    tr_batch_e2e_ms = (time.perf_counter() - t0) * 1000.0 / steps
+    L1 = Ls[0]
+    L1.calc_log_likelihood(eas[0])
+    for _ in range(warmup):
+        L1.replay_async()
+    with torch.cuda.stream(L1.stream):
+        L1.stream.synchronize()
+        b0.record()
+        for _ in range(steps):
+            L1.replay_async()
+        b1.record()
+        L1.stream.synchronize()
+    tr_dev_ms = b0.elapsed_time(b1) / steps
     for Lk in Ls:
         Lk.close()
     # the C++ Likelihood facade (strom_b200/host/likelihood.hpp): what strom's Chain / Updaters call
@@ -385,6 +416,11 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
                            "us_per_batch_device": batch_dev_ms * 1000.0, "max_rel_diff_vs_single_evaluations": batch_rel,
                            "speedup_e2e_vs_cpu_all_threads": (K * 1000.0 / batch_e2e_ms) / allc,
                            "speedup_e2e_vs_cpu_1thread": (K * 1000.0 / batch_e2e_ms) / one},
+        "transient_partials": {"evals_per_sec_device": 1000.0 / tr_dev_ms, "evals_per_sec_device_8_batched_chains": K * 1000.0 / tr_batch_dev_ms,
+                               "evals_per_sec_e2e_8_batched_chains": K * 1000.0 / tr_batch_e2e_ms,
+                               "speedup_e2e_8_batched_vs_cpu_all_threads": (K * 1000.0 / tr_batch_e2e_ms) / allc,
+                               "max_rel_diff_vs_materialised": tr_rel,
+                               "what": "sb200SetTransientPartials: partials inside a fused chain are not written to HBM; OFF everywhere else in this block"},
         "partial_updates_per_sec_device": upd * 1000.0 / dev_ms,
         "roofline": {"bound": "hbm", "achieved": alg.value / (dev_ms / 1000.0) / 1e9, "peak": peaks()[0], "unit": "GB/s",
                      "frac": alg.value / (dev_ms / 1000.0) / 1e9 / peaks()[0],
@@ -398,6 +434,41 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
         "algorithmic_bytes_per_eval": alg.value, "scheduled_bytes_per_eval": sch.value,
         "l2": "warm: the 116 MB working set is re-used by every MCMC step, as in the reference's usage",
     }
+
+
+def timed_variant(E, tips_h, Pl, ea, local_rank, n, patterns, logl_ref, steps, **kw):
+    """One more configuration of the engine on the benched alignment (FP32 storage, transient partials): device-timed
+    evaluations and the roofline of its pruning launches."""
+    import torch
+    from strom_b200.engine import ShardedLikelihood
+    Lf = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, **kw)
+    lf = Lf.calc_log_likelihood(ea)
+    for _ in range(3):
+        Lf.replay_async()
+    E.sb200SetProfiling(Lf.inst, 1)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(Lf.stream):
+        Lf.stream.synchronize()
+        f0.record()
+        for _ in range(steps):
+            Lf.replay_async()
+        f1.record()
+        Lf.stream.synchronize()
+    fms = f0.elapsed_time(f1) / steps
+    fp, fc = C.c_double(), C.c_long()
+    E.sb200PartialsTime(Lf.inst, C.byref(fp), C.byref(fc))
+    fa, fs = C.c_double(), C.c_double()
+    E.sb200LastTraffic(Lf.inst, C.byref(fa), C.byref(fs))
+    Lf.close()
+    del Lf
+    torch.cuda.empty_cache()
+    fprune = fp.value / max(fc.value, 1)
+    pk = peaks()[0]
+    return {"value": float(n - 2) * patterns * 4 / (fms / 1000.0), "unit": UNIT, "ms_per_step": fms, "steps": steps,
+            "logL": lf, "rel_diff_vs_f64": abs(lf - logl_ref) / abs(logl_ref),
+            "roofline": {"bound": "hbm", "achieved": fa.value / (fprune / 1000.0) / 1e9, "peak": pk, "unit": "GB/s",
+                         "frac": fa.value / (fprune / 1000.0) / 1e9 / pk, "scheduled_frac": fs.value / (fprune / 1000.0) / 1e9 / pk,
+                         "algorithmic_bytes_per_eval": fa.value, "scheduled_bytes_per_eval": fs.value, "traffic": None}}
 
 
 def mc3_block(devices, niter=200, burnin=100, nchains=8):
@@ -442,7 +513,8 @@ def run_ours(args, rank, world, local_rank):
     tree, model, tips_h, lo, hi = synthetic_inputs(args, rank, world, dev)
     torch.cuda.empty_cache()
     Pl = hi - lo
-    L = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, distributed=distributed, single=(args.dtype == "f32"))
+    L = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, distributed=distributed, single=(args.dtype == "f32"),
+                          transient_partials=args.transient)
     ea = EvalArgs(model, tree.ops, tree.pmatrix_index, tree.edge_lengths, tree.parent_buffer, 0)
     n, K, W = args.taxa, args.steps, args.warmup
 
@@ -510,38 +582,16 @@ def run_ours(args, rank, world, local_rank):
         verify = {"sample_patterns": Ps, "logL_sample_gpu": gpu_sample}
 
     # ---- the stated FP32 variant on the same alignment (own roofline) --------------------------------------------------
-    f32 = None
+    f32, transient = None, None
     if world == 1 and args.dtype == "f64" and not args.no_f32:
-        Lf = ShardedLikelihood(tips_h, np.ones(Pl), 4, device=local_rank, single=True)
-        lf = Lf.calc_log_likelihood(ea)
-        Kf = max(3, min(K, 5))
-        for _ in range(3):
-            Lf.replay_async()
-        E.sb200SetProfiling(Lf.inst, 1)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(Lf.stream):
-            Lf.stream.synchronize()
-            f0.record()
-            for _ in range(Kf):
-                Lf.replay_async()
-            f1.record()
-            Lf.stream.synchronize()
-        fms = f0.elapsed_time(f1) / Kf
-        fp, fc = C.c_double(), C.c_long()
-        E.sb200PartialsTime(Lf.inst, C.byref(fp), C.byref(fc))
-        fa, fs = C.c_double(), C.c_double()
-        E.sb200LastTraffic(Lf.inst, C.byref(fa), C.byref(fs))
-        Lf.close()
-        del Lf
-        torch.cuda.empty_cache()
-        fprune = fp.value / max(fc.value, 1)
-        pk = peaks()[0]
-        f32 = {"dtype": "f32 partials / matrices / tables, FP64 scalers and root accumulation (BEAGLE_FLAG_PRECISION_SINGLE)",
-               "value": float(n - 2) * args.patterns * 4 / (fms / 1000.0), "unit": UNIT, "ms_per_step": fms, "steps": Kf,
-               "logL": lf, "rel_diff_vs_f64": abs(lf - logl) / abs(logl), "stated_tolerance": 2e-5,
-               "roofline": {"bound": "hbm", "achieved": fa.value / (fprune / 1000.0) / 1e9, "peak": pk, "unit": "GB/s",
-                            "frac": fa.value / (fprune / 1000.0) / 1e9 / pk, "scheduled_frac": fs.value / (fprune / 1000.0) / 1e9 / pk,
-                            "algorithmic_bytes_per_eval": fa.value, "scheduled_bytes_per_eval": fs.value, "traffic": None}}
+        f32 = timed_variant(E, tips_h, Pl, ea, local_rank, n, args.patterns, logl, max(3, min(K, 5)), single=True)
+        f32["dtype"] = "f32 partials / matrices / tables, FP64 scalers and root accumulation (BEAGLE_FLAG_PRECISION_SINGLE)"
+        f32["stated_tolerance"] = 2e-5
+    if world == 1 and args.dtype == "f64" and not args.transient and not args.no_f32:
+        transient = timed_variant(E, tips_h, Pl, ea, local_rank, n, args.patterns, logl, max(3, min(K, 5)), transient_partials=True)
+        transient["what"] = "sb200SetTransientPartials / Likelihood::setTransientPartials: partials inside a fused chain of operations " \
+                            "stay in registers and are not written to HBM (only what a later launch reads is); same operations, same " \
+                            "bits; OFF in the headline numbers, where every node's buffer is written as BeagleLib does"
 
     if rank == 0:
         upd_per_eval = float(n - 2) * args.patterns * 4
@@ -583,6 +633,8 @@ def run_ours(args, rank, world, local_rank):
         }
         if f32 is not None:
             line["f32"] = f32
+        if transient is not None:
+            line["transient_partials"] = transient
         if world == 1 and not args.no_cpu:
             thr = host_threads()
             Ps = min(args.patterns, args.cpu_sample)
@@ -630,6 +682,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds the reference arm may spend on timed full evaluations")
     ap.add_argument("--no-f32", action="store_true")
+    ap.add_argument("--transient", action="store_true", help="sb200SetTransientPartials: chain-interior partials are not written")
     ap.add_argument("--no-mc3", action="store_true")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f32 = the stated FP32 variant (partials/matrices float)")
     ap.add_argument("--no-cpu", action="store_true")

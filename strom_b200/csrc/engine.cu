@@ -136,6 +136,7 @@ struct Engine {
     Group* dGroups = nullptr;
     int* dRootSlots = nullptr;
     bool keepSubtreeScalers = false;      // incremental evaluation: permanent per-buffer subtree scaler slots (sb200SetSubtreeScalers)
+    bool transientPartials = false;       // partials inside a chain are not written to HBM (sb200SetTransientPartials)
     std::vector<char> slotValid;          // ... and which of them hold the scaler of the partials now in the buffer
     long long* dTrace = nullptr;          // tuning builds: per-step clock samples (sb200DebugTrace)
     int* dTTOps = nullptr;                // op index of every tip x tip table
@@ -603,7 +604,9 @@ struct Engine {
         a.Ppad = Ppad;
         a.nTips = nTips;
         a.cumMode = cumMode;
-        a.pad = 0;
+        // (incremental lists read buffers of earlier calls, and lists that are not forests run one operation per launch:
+        // both need every buffer in memory)
+        a.storeAll = (transientPartials && !keepSubtreeScalers && !sched.sequential) ? 0 : 1;
         return a;
     }
 
@@ -1496,6 +1499,13 @@ extern "C" int sb200SetSubtreeScalers(int instance, int enable) {
     });
 }
 
+extern "C" int sb200SetTransientPartials(int instance, int enable) {
+    return withEngine(instance, [&](Engine& E) {
+        E.transientPartials = enable != 0;
+        return static_cast<int>(BEAGLE_SUCCESS);
+    });
+}
+
 extern "C" long sb200LaunchCount(int instance) {
     Engine* E = getEngine(instance);
     return E ? E->launches : -1;
@@ -1505,7 +1515,12 @@ extern "C" int sb200LastTraffic(int instance, double* algorithmicBytes, double* 
     Engine* E = getEngine(instance);
     if (!E) return BEAGLE_ERROR_UNINITIALIZED_INSTANCE;
     if (algorithmicBytes) *algorithmicBytes = E->algBytes;
-    if (scheduledBytes) *scheduledBytes = E->schedBytes;
+    if (scheduledBytes) {
+        *scheduledBytes = E->schedBytes;
+        if (E->transientPartials && !E->keepSubtreeScalers && !E->sched.sequential)      // only chain ends are written
+            *scheduledBytes -= static_cast<double>(E->sched.partialWrites - static_cast<long>(E->sched.chains.size())) * 4.0 *
+                               static_cast<double>(E->realSize()) * static_cast<double>(E->P) * E->C;
+    }
     return BEAGLE_SUCCESS;
 }
 

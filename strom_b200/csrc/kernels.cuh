@@ -75,10 +75,16 @@ __host__ __device__ constexpr int cptWide(int C, int realBytes) {
 }
 __host__ __device__ constexpr int varCPT(int C, int V, int realBytes) { return V == kVarNarrow ? 1 : cptWide(C, realBytes); }
 __host__ __device__ constexpr int varNCW(int C, int V, int realBytes) { return (C + varCPT(C, V, realBytes) - 1) / varCPT(C, V, realBytes); }
+#ifndef SB200_STREAM_WARPS
+#define SB200_STREAM_WARPS 4
+#endif
+#ifndef SB200_WIDE_WARPS
+#define SB200_WIDE_WARPS 4
+#endif
 __host__ __device__ constexpr int varTP(int C, int V, int realBytes) {
     return V == kVarNarrow ? 1
-         : V == kVarStream ? (8 / varNCW(C, V, realBytes) > 0 ? 8 / varNCW(C, V, realBytes) : 1)
-                           : (4 / varNCW(C, V, realBytes) > 0 ? 4 / varNCW(C, V, realBytes) : 1);
+         : V == kVarStream ? (SB200_STREAM_WARPS / varNCW(C, V, realBytes) > 0 ? SB200_STREAM_WARPS / varNCW(C, V, realBytes) : 1)
+                           : (SB200_WIDE_WARPS / varNCW(C, V, realBytes) > 0 ? SB200_WIDE_WARPS / varNCW(C, V, realBytes) : 1);
 }
 __host__ __device__ constexpr int varWarps(int C, int V, int realBytes) { return varNCW(C, V, realBytes) * varTP(C, V, realBytes); }
 __host__ __device__ constexpr int varThreads(int C, int V, int realBytes) { return 32 * varWarps(C, V, realBytes); }
@@ -134,7 +140,7 @@ struct PruneArgs {
     int Ppad;
     int nTips;
     int cumMode;                     // 1: the root chain overwrites the cumulative buffer (reset fused away), 0: adds
-    int pad;
+    int storeAll;                    // 0: partials that only travel in registers inside a chain are not written (sb200SetTransientPartials)
 };
 template <typename real>
 struct PruneBatch {
@@ -381,9 +387,11 @@ __device__ __noinline__ double scalerTotal(double acc, double prod) { return acc
 
 constexpr int kOpChunk = 128;                  // operations of a group held in shared memory at a time
 #ifndef SB200_PREFETCH_AHEAD
-#define SB200_PREFETCH_AHEAD 2
+#define SB200_PREFETCH_AHEAD 0
 #endif
-constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;   // streaming shape: steps between an operand's L2 prefetch and its register load
+// streaming shape: steps between an operand's L2 prefetch and its register load.  0 = none (the default: with the register loads one
+// step ahead and 24 warps per SM the prefetch only costs issue slots -- 7.72 ms against 7.91 per evaluation at 250k patterns)
+constexpr int kPrefetchAhead = SB200_PREFETCH_AHEAD;
 constexpr int kRecWords = sizeof(DevRec) / 16;
 
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -638,7 +646,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
                 if (kEven || kb + c < C) st4(dest + catOff(c), X[c]);
-        } else {
+        } else if (A.storeAll) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
                 if (kEven || kb + c < C) st4Stream(dest + catOff(c), X[c]);
@@ -894,7 +902,7 @@ prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
         // one state per lane: 8 bytes x 32 lanes = 256 contiguous bytes per warp
         real* dest = byteOffset(pmine, rec.destOff) + i;
         if (flags & OP_CHAIN_END) *dest = v;
-        else __stcs(dest, v);
+        else if (A.storeAll) __stcs(dest, v);
         // the whole vector again in every lane of the quad: operand A of the next step
 #pragma unroll
         for (int s = 0; s < 4; ++s) X[s] = quadGather(v, lane, s);

@@ -48,6 +48,7 @@ class EngineAPI:
             "sb200Synchronize": (C.c_int, [C.c_int]),
             "sb200SetProfiling": (C.c_int, [C.c_int, C.c_int]),
             "sb200SetSubtreeScalers": (C.c_int, [C.c_int, C.c_int]),
+            "sb200SetTransientPartials": (C.c_int, [C.c_int, C.c_int]),
             "sb200CompressPatterns": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, _DP, _IP]),
             "sb200PartialsTime": (C.c_int, [C.c_int, _DP, C.POINTER(C.c_long)]),
             "sb200LaunchCount": (C.c_long, [C.c_int]),
@@ -151,7 +152,7 @@ class ShardedLikelihood:
     (NCCL, one double) before returning; otherwise it is the single-GPU call."""
 
     def __init__(self, tips_u8: np.ndarray, weights: np.ndarray, ncateg: int, device: int = 0, single: bool = False,
-                 distributed: bool = False):
+                 distributed: bool = False, transient_partials: bool = False):
         import torch
         self.torch = torch
         self.E = api()
@@ -171,6 +172,8 @@ class ShardedLikelihood:
             raise beagle.BeagleError("failed to create instance", self.inst)
         self.stream = torch.cuda.Stream(device=device)
         self.E.check(self.E.sb200SetStream(self.inst, C.c_void_p(self.stream.cuda_stream)), "set stream")
+        if transient_partials:
+            self.E.check(self.E.sb200SetTransientPartials(self.inst, 1), "transient partials")
         self.out = torch.zeros(1, dtype=torch.float64, device="cuda:%d" % device)
         for t in range(n):
             row = np.ascontiguousarray(tips_u8[t])

@@ -91,6 +91,10 @@ class Likelihood {
     // matrices that changed.  A new model or a different Tree object falls back to the full list.  No updater has to
     // cooperate: a rejected move is simply the next difference.  Has no effect on the CPU call path.
     void setIncremental(bool on);
+    // Engine builds: partials that only travel in registers inside a fused chain of operations are not written to HBM
+    // (sb200SetTransientPartials; the reference recomputes every node on every call and never reads a buffer back).
+    // Same log-likelihood bit for bit.  No effect with incremental evaluation or on the CPU call path.
+    void setTransientPartials(bool on);
 #ifdef STROM_B200_ENGINE
     // Evaluations begun on this object are enqueued together with those of the other Likelihoods that share `b`
     // (one set of kernel launches for all of them) when the first one is finished.  One pattern shard only.
@@ -144,6 +148,7 @@ class Likelihood {
 
     // what the engine holds from the previous call (incremental evaluation)
     bool _incremental;
+    bool _transient = false;
     bool _remembered;
     unsigned long long _held_tree_uid;   // Tree::uid() of the tree the device state belongs to (0: none)
     std::vector<int> _buffer_of;         // by node slot (index in Tree::_nodes): buffer = matrix index, frozen at the first call
@@ -290,6 +295,7 @@ inline void Likelihood::initBeagleLib() {
             const int code = sb200SetSubtreeScalers(inst, 1);
             if (code != 0) throw XStrom("failed to switch incremental evaluation. " + errorText(code));
         }
+        if (_transient) sb200SetTransientPartials(inst, 1);
 #endif
     }
     setTipStates();
@@ -394,6 +400,16 @@ inline void Likelihood::defineOperations(Tree::SharedPtr t) {
     }
     _operations.resize(nn ? static_cast<size_t>(op - &_operations[0]) : 0);
     if (!t->_is_rooted && nn) _pmatrix_index[nn - 1] = t->_root->_number;
+}
+
+inline void Likelihood::setTransientPartials(bool on) {
+    _transient = on;
+#ifdef STROM_B200_ENGINE
+    for (int inst : _instances) {
+        const int code = sb200SetTransientPartials(inst, on ? 1 : 0);
+        if (code != 0) throw XStrom("failed to switch transient partials. " + errorText(code));
+    }
+#endif
 }
 
 inline void Likelihood::setIncremental(bool on) {

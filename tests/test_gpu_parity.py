@@ -502,3 +502,34 @@ def test_incremental_list_that_reads_a_slot_nobody_wrote_is_rejected(engine):
     again = engine.calc_log_likelihood(inst, m, root_only, pr["pmatrix_index"][-1:], pr["edge_lengths"][-1:], int(pr["parent"]), 0)
     assert rel_err(again, full) < 1e-13
     engine.finalize(inst)
+
+
+@pytest.mark.parametrize("source,model", [("rbcl738", "gtr_g4"), ("rbcl10", "gtr_i_g4"), ("random", "jc"), ("random", "gtr_g8")])
+def test_transient_partials_give_the_same_bits_and_leave_chain_interiors_unwritten(engine, oracle, source, model):
+    """sb200SetTransientPartials: only the buffers a later launch reads (the last node of every chain) are written.  Same
+    log-likelihood and cumulative scalers bit for bit, same root partials; and the switch goes back."""
+    from strom_b200.engine import api
+    E = api()
+    pr = load_golden(source) if source != "random" else random_problem(40, 500, seed=12)
+    m = named_model(model)
+    n, P = pr["data"].shape
+    Cc = len(m["rates"])
+    xe = Extra(engine)
+    ll0, inst = full_eval(engine, pr, m, keep=True)
+    root = int(pr["parent"])
+    want_root, want_scale = xe.partials(inst, root, P, Cc), xe.scale(inst, 0, P)
+    first_op_dest = int(pr["ops"][0][0])
+    assert E.sb200SetTransientPartials(inst, 1) == 0
+    # poison every buffer through a list that writes them with other edge lengths, then evaluate transiently
+    ll1 = engine.calc_log_likelihood(inst, m, pr["ops"], pr["pmatrix_index"], pr["edge_lengths"], root, 0)
+    assert ll1 == ll0
+    assert np.array_equal(xe.partials(inst, root, P, Cc), want_root) and np.array_equal(xe.scale(inst, 0, P), want_scale)
+    alg, sch = C.c_double(), C.c_double()
+    E.sb200LastTraffic(inst, C.byref(alg), C.byref(sch))
+    assert E.sb200SetTransientPartials(inst, 0) == 0
+    ll2 = engine.calc_log_likelihood(inst, m, pr["ops"], pr["pmatrix_index"], pr["edge_lengths"] * 1.0, root, 0)
+    sch_all = C.c_double()
+    E.sb200LastTraffic(inst, C.byref(alg), C.byref(sch_all))
+    assert ll2 == ll0 and sch.value < sch_all.value
+    assert rel_err(ll0, full_eval(oracle, pr, m)) < LOGL_RTOL
+    engine.finalize(inst)

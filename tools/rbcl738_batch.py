@@ -22,7 +22,7 @@ for c in range(K):
     if PINV > 0:
         model["rates"], model["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA * (1.0 + 0.1 * c), 4, PINV)
     elen = fx["edge_lengths"] * np.exp(0.2 * rng.standard_normal(fx["edge_lengths"].shape)) if c else fx["edge_lengths"]
-    L = ShardedLikelihood(tips, fx["counts"], len(model["rates"]), device=0)
+    L = ShardedLikelihood(tips, fx["counts"], len(model["rates"]), device=0, transient_partials=bool(os.environ.get("TRANSIENT")))
     Ls.append(L)
     eas.append(EvalArgs(model, fx["ops"], fx["pmatrix_index"], elen, int(fx["parent"]), 0))
 single = [L.calc_log_likelihood(ea) for L, ea in zip(Ls, eas)]

@@ -15,7 +15,7 @@ if PINV > 0:
     from strom_b200 import hostmodel
     model["rates"], model["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA, 4, PINV)
 NC = len(model["rates"])
-L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0)
+L = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0, transient_partials=bool(os.environ.get("TRANSIENT")))
 ea = EvalArgs(model, fx["ops"], fx["pmatrix_index"], fx["edge_lengths"], int(fx["parent"]), 0)
 print("logL", L.calc_log_likelihood(ea))
 for _ in range(10):
@@ -39,7 +39,7 @@ L.close()
 import ctypes as C
 from strom_b200.engine import api
 E = api()
-L2 = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0)
+L2 = ShardedLikelihood(np.minimum(fx["data"], 4).astype(np.uint8), fx["counts"], NC, device=0, transient_partials=bool(os.environ.get("TRANSIENT")))
 E.lib.sb200Finish.argtypes = [C.c_int, C.POINTER(C.c_double)]
 out = C.c_double()
 for _ in range(20):
