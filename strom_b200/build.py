@@ -18,6 +18,8 @@ ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle_beagle.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--shared", "-cudart", "static",
+    "-DSB200_NVTX",           # NVTX ranges around kernels (a), (b), (c) of an evaluation (header-only nvtx3; needs libdl)
+    "-ldl",
 ]
 
 

@@ -92,9 +92,13 @@ __host__ __device__ constexpr int varPatterns(int C, int V, int realBytes) { ret
 #ifndef SB200_REG_BUDGET
 #define SB200_REG_BUDGET 80
 #endif
+#ifndef SB200_REG_BUDGET_STREAM
+#define SB200_REG_BUDGET_STREAM 72
+#endif
 __host__ __device__ constexpr int varBlocksPerSm(int C, int V, bool tips, int realBytes) {
-    // registers per thread the kernel is compiled for: 64 for the tips-only variants, 80 otherwise
-    const int regs = tips ? 64 : SB200_REG_BUDGET;
+    // registers per thread the kernel is compiled for: 64 for the tips-only variants, otherwise 80, or 72 for the streaming
+    // shape (7 resident blocks of 4 warps instead of 6: 32.2 ms against 32.7 per 1M-pattern evaluation)
+    const int regs = tips ? 64 : V == kVarStream ? SB200_REG_BUDGET_STREAM : SB200_REG_BUDGET;
     const int byRegs = 65536 / (regs * varThreads(C, V, realBytes));
     return byRegs < 1 ? 1 : byRegs > 16 ? 16 : byRegs;
 }
@@ -551,11 +555,9 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     auto step = [&](const int j, const int nc) {
         SB200_TICK(0)
         const bool more = j + 1 < nc;
-        const DevRec& rec = sops[j];
-        const int flags = rec.flags;
+        const int flags = sops[j].flags;
         if (kPrefetch && j + 1 + kPrefetchAhead < nc) prefetchOperands(sops[j + 1 + kPrefetchAhead]);
-        const real* sa = sm[j & 1];
-        const real* sb = sa + MSZ;
+        const int ib = j & 1;                              // image buffer of this step: A's matrices at 0, B's at MSZ (or the table)
         double mfac;                                         // this step's rescaling maximum (1 when not rescaled)
         real m = real(1);
 
@@ -563,27 +565,33 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
             const int combo = sX * 5 + sY;
             if (more) fetchB(sops[j + 1]);
-            const real* T = sa + combo * TTE;
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) X[c][i] = T[kcat(c) * 4 + i];
+                for (int i = 0; i < 4; ++i) X[c][i] = sm[ib][combo * TTE + kcat(c) * 4 + i];
             }
-            mfac = static_cast<double>(sa[25 * TTE + combo]);
+            mfac = static_cast<double>(sm[ib][25 * TTE + combo]);
         } else {
             // factor of operand A (from registers, or a column of P at a chain start with a tip), then operand B
             if (!TIPS && (flags & OP_A_TIP)) {       // (TIPS: a chain start with a tip for A is a tip x tip operation)
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
-                    const real* T = sa + tipIndex(kcat(c), sX, 0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[c][i] = T[i];
+                    for (int i = 0; i < 4; ++i) X[c][i] = sm[ib][tipIndex(kcat(c), sX, i)];
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
                     real F[4];
-                    matVec<real>(sa + pmIndex(kcat(c), 0), X[c], F);
+                    const int o = pmIndex(kcat(c), 0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        real a = sm[ib][o + i * 4] * X[c][0];
+                        a += sm[ib][o + i * 4 + 1] * X[c][1];
+                        a += sm[ib][o + i * 4 + 2] * X[c][2];
+                        a += sm[ib][o + i * 4 + 3] * X[c][3];
+                        F[i] = a;
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) X[c][i] = F[i];
                 }
@@ -592,20 +600,24 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             if (TIPS || (flags & OP_B_TIP)) {
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
-                    const real* T = sb + tipIndex(kcat(c), sY, 0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[c][i] *= T[i];
+                    for (int i = 0; i < 4; ++i) X[c][i] *= sm[ib][MSZ + tipIndex(kcat(c), sY, i)];
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
-                    real F[4];
-                    matVec<real>(sb + pmIndex(kcat(c), 0), Y[c], F);
+                    const int o = MSZ + pmIndex(kcat(c), 0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) X[c][i] *= F[i];
+                    for (int i = 0; i < 4; ++i) {
+                        real a = sm[ib][o + i * 4] * Y[c][0];
+                        a += sm[ib][o + i * 4 + 1] * Y[c][1];
+                        a += sm[ib][o + i * 4 + 2] * Y[c][2];
+                        a += sm[ib][o + i * 4 + 3] * Y[c][3];
+                        X[c][i] *= a;
+                    }
                 }
             }
-            if (!TIPS && scalerWarp && rec.sb >= 0) accumulate(pendAcc, pendProd);
+            if (!TIPS && scalerWarp && sops[j].sb >= 0) accumulate(pendAcc, pendProd);
             SB200_TICK(2)
             // next step's operand B is requested now; the rescaling below hides its latency
             if (more) fetchB(sops[j + 1]);
@@ -613,7 +625,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                 m = rmax(rmax(X[0][0], X[0][1]), rmax(X[0][2], X[0][3]));
 #pragma unroll
                 for (int c = 1; c < CPT; ++c) m = rmax(m, rmax(rmax(X[c][0], X[c][1]), rmax(X[c][2], X[c][3])));
-                if (NCW > 1) smax[j & 1][tid] = m;
+                if (NCW > 1) smax[ib][tid] = m;
             }
             mfac = 1.0;
         }
@@ -624,10 +636,9 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         if (j + 2 < nc) stage(j & 1, sops[j + 2]);
         if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) {
             if (NCW > 1) {
-                const real* q = &smax[j & 1][(sp * NCW) * 32 + lane];
-                m = q[0];
+                m = smax[ib][(sp * NCW) * 32 + lane];
 #pragma unroll
-                for (int w = 1; w < NCW; ++w) m = rmax(m, q[w * 32]);
+                for (int w = 1; w < NCW; ++w) m = rmax(m, smax[ib][(sp * NCW + w) * 32 + lane]);
             }
             // below kTiny the hardware reciprocal seed (flush-to-zero) is not usable: exact division instead
             constexpr real kTiny = sizeof(real) == 4 ? real(1e-30) : real(1e-290);
@@ -641,7 +652,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             mfac = static_cast<double>(m);
         }
         SB200_TICK(5)
-        real* dest = byteOffset(pmine, rec.destOff);
+        real* dest = byteOffset(pmine, sops[j].destOff);
         if (flags & OP_CHAIN_END) {
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
@@ -665,7 +676,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             if (flags & (OP_STORE_S | OP_CHAIN_END)) {
                 // a chain end hands its subtree log-scaler to the parent chain (and resets); incremental plans keep
                 // every node's (OP_STORE_S: store and carry on)
-                const int sOut = rec.sOut;
+                const int sOut = sops[j].sOut;
                 double a = sAcc[tid];
                 if (sOut >= 0) {
                     if (prod < 1e-100) {                     // keep a parent's product of two stored factors normal
