@@ -607,6 +607,12 @@ struct Engine {
         // (incremental lists read buffers of earlier calls, and lists that are not forests run one operation per launch:
         // both need every buffer in memory)
         a.storeAll = (transientPartials && !keepSubtreeScalers && !sched.sequential) ? 0 : 1;
+        a.arenaBytes = static_cast<long long>(Ppad) * C * 4 * static_cast<long long>(realSize()) * nPartials;
+        a.tipBytes = static_cast<long long>(nTips) * tipStride;
+        a.nMat = nMat;
+        a.nTables = sched.tipTipCount;
+        a.nSlots = sched.slotCount;
+        a.nOps = static_cast<int>(sched.ops.size());
         return a;
     }
 

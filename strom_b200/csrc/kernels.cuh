@@ -145,6 +145,10 @@ struct PruneArgs {
     int nTips;
     int cumMode;                     // 1: the root chain overwrites the cumulative buffer (reset fused away), 0: adds
     int storeAll;                    // 0: partials that only travel in registers inside a chain are not written (sb200SetTransientPartials)
+    // extents, read only by builds with -DSB200_CHECK (every operand of every operation is checked against them; a
+    // violation traps): compute-sanitizer is not available on the measurement pool
+    long long arenaBytes, tipBytes;
+    int nMat, nTables, nSlots, nOps;
 };
 template <typename real>
 struct PruneBatch {
@@ -403,6 +407,27 @@ template <typename T>
 __device__ __forceinline__ T* byteOffset(T* base, long long bytes) {
     return reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(base)) + bytes);
 }
+
+#ifdef SB200_CHECK
+#define SB200_CHECK_REC(r, idx)                                                                                                      \
+    do {                                                                                                                             \
+        const long long _vec = 4 * static_cast<long long>(sizeof(real));                                                           \
+        const long long _span = (static_cast<long long>(C - 1) * A.Ppad + A.Ppad) * _vec;          /* one buffer, all categories */ \
+        bool _bad = (idx) < 0 || (idx) >= A.nOps || (r).ma < 0 || (r).ma >= A.nMat || (r).mb < 0 || (r).mb >= A.nMat;            \
+        _bad = _bad || (r).destOff < 0 || (r).destOff + _span > A.arenaBytes;                                                     \
+        if ((r).flags & OP_B_TIP) _bad = _bad || (r).bOff < 0 || (r).bOff + A.Ppad > A.tipBytes;                                  \
+        else _bad = _bad || (r).bOff < 0 || (r).bOff + _span > A.arenaBytes;                                                      \
+        if ((r).flags & OP_CHAIN_START) {                                                                                         \
+            if ((r).flags & OP_A_TIP) _bad = _bad || (r).aOff < 0 || (r).aOff + A.Ppad > A.tipBytes;                              \
+            else _bad = _bad || (r).aOff < 0 || (r).aOff + _span > A.arenaBytes;                                                  \
+        }                                                                                                                         \
+        if ((r).flags & OP_TIPTIP) _bad = _bad || (r).tt < 0 || (r).tt >= A.nTables;                                              \
+        _bad = _bad || (r).sa >= A.nSlots || (r).sb >= A.nSlots || (r).sOut >= A.nSlots;                                          \
+        if (_bad) __trap();                                                                                                       \
+    } while (0)
+#else
+#define SB200_CHECK_REC(r, idx) ((void)0)
+#endif
 
 template <typename real, int C, int V, bool TIPS>
 __global__ void __launch_bounds__(varThreads(C, V, sizeof(real)), varBlocksPerSm(C, V, TIPS, sizeof(real)))
@@ -714,6 +739,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         }
         blockSync();
         if (chunk0 == 0) pdlWait();   // the plan is in shared memory; everything below reads what earlier kernels wrote
+        for (int w = tid; w < nc; w += THREADS) SB200_CHECK_REC(sops[w], grp.opStart + chunk0 + w);
         stage(0, sops[0]);
         if (nc > 1) stage(1, sops[1]);
         if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);       // (a later chunk may begin in mid-chain: A is carried)
@@ -965,6 +991,7 @@ prune_quad_kernel(const __grid_constant__ PruneBatch<real> B) {
         }
         blockSync();
         if (chunk0 == 0) pdlWait();
+        for (int w = tid; w < nc; w += THREADS) SB200_CHECK_REC(sops[w], grp.opStart + chunk0 + w);
         stage(0, sops[0]);
         if (nc > 1) stage(1, sops[1]);
         if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);
