@@ -482,7 +482,7 @@ def mc3_block(devices, niter=200, burnin=100, nchains=8):
     data = np.minimum(fx["data"], 4).astype(np.int32)
     cols = np.repeat(np.arange(data.shape[1]), fx["counts"].astype(int))
     hd = H.data_from_codes(data[:, cols], compress=True)
-    kw = dict(seed=13579, niter=niter, burnin=burnin, samplefreq=1, nchains=nchains, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA,
+    kw = dict(seed=13579, niter=niter, burnin=burnin, samplefreq=10, nchains=nchains, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA,
               freqs=PAUP_PI, rmat=[x / sum(PAUP_R) for x in PAUP_R], devices=tuple(devices))
     H.mcmc(hd, str(fx["newick"]), **dict(kw, niter=4, burnin=2), per_chain_streams=True)                  # warm-up (instances, plans)
     tr_turn, sec_turn = H.mcmc(hd, str(fx["newick"]), per_chain_streams=True, **kw)
@@ -495,7 +495,7 @@ def mc3_block(devices, niter=200, burnin=100, nchains=8):
     H.data_free(hd)
     its = nchains * (niter + burnin)
     same = tr_turn.shape == tr_side.shape and bool(np.array_equal(tr_turn, tr_side))
-    return {"workload": "rbcl738 GTR+G4, %d heated chains, %d iterations each (5 updates + a swap proposal per iteration)" % (nchains, niter + burnin),
+    return {"workload": "rbcl738 GTR+G4, %d heated chains, %d iterations each (5 updates + a swap proposal per iteration, a sample every 10)" % (nchains, niter + burnin),
             "side_by_side": how, "chain_iterations_per_sec_in_turn": its / sec_turn, "chain_iterations_per_sec_side_by_side": its / sec_side,
             "speedup": sec_turn / sec_side, "traces_identical": same, "gpus": len(devices)}
 
@@ -659,13 +659,20 @@ def run_ours(args, rank, world, local_rank):
             line["mc3"] = mc3_block([local_rank])
     if distributed:
         dist.barrier()                   # every rank has released its shard
-        if rank == 0 and world == 8 and not args.no_mc3:
-            # BASELINE.json configs[4]: 8 heated chains on rbcl738, one per GPU (the other ranks wait at the barrier below)
-            try:
-                line["mc3"] = mc3_block(list(range(world)))
-            except Exception as e:
-                line["mc3"] = {"error": repr(e)}
-    if distributed:
+        torch.cuda.synchronize()
+        if world == 8 and not args.no_mc3:
+            # BASELINE.json configs[4]: 8 heated chains on rbcl738, one per GPU, driven by rank 0.  The other ranks wait on
+            # the rendezvous store (a socket), NOT in an NCCL barrier, whose kernels would spin on the very GPUs the chains use
+            import datetime
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                try:
+                    line["mc3"] = mc3_block(list(range(world)))
+                except Exception as e:
+                    line["mc3"] = {"error": repr(e)}
+                store.set("sb200_mc3_done", "1")
+            else:
+                store.wait(["sb200_mc3_done"], datetime.timedelta(minutes=30))
         dist.barrier()
         dist.destroy_process_group()
     return line if rank == 0 else None

@@ -38,6 +38,7 @@ class HostAPI:
                                     C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
         L.strom_mcmc_ex2.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_uint,
                                      C.c_double, C.c_double, _DP, _DP, C.c_int, _IP, C.c_uint, _DP, C.c_int, _DP, C.c_char_p, C.c_int]
+        L.strom_lot_draws.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _DP]
         L.strom_incremental_rebuild_check.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_int, C.c_uint, _DP, C.c_char_p,
                                                       C.c_int]
         L.strom_incremental_walk.argtypes = [C.c_int, C.c_char_p, _DP, _DP, C.c_double, C.c_int, C.c_double, C.c_int, _IP, C.c_uint,
@@ -126,7 +127,7 @@ class HostAPI:
     def mcmc(self, data_handle: int, newick: str, seed: int = 13579, niter: int = 100, burnin: int = 100, samplefreq: int = 1,
              nchains: int = 1, heatfactor: float = 0.5, ncateg: int = 4, gammashape: float = 0.5, freqs=(0.25,) * 4,
              rmat=(1.0 / 6,) * 6, devices=(0,), per_chain_streams: bool = False, parallel_chains: bool = False,
-             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True, transient_partials: bool = False):
+             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True, transient_partials: bool = False, boost_lot: bool = True):
         """Returns (trace [rows][15] = iteration, lnL, lnPrior, TL, 6 r, 4 pi, alpha; seconds).
 
         ``parallel_chains``: the heated chains are stepped side by side on host threads (one chain per GPU of
@@ -142,13 +143,19 @@ class HostAPI:
         rows = np.zeros((max_rows, 15))
         sec = C.c_double()
         flags = (1 if per_chain_streams else 0) | (2 if parallel_chains else 0) | (4 if incremental else 0) | \
-            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16) | (32 if transient_partials else 0)
+            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16) | (32 if transient_partials else 0) | (0 if boost_lot else 64)
         n = self._check(self.lib.strom_mcmc_ex2(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor,
                                                 ncateg, gammashape, float(pinvar), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
                                                 int(dev.size), dev.ctypes.data_as(_IP), flags, rows.ctypes.data_as(_DP), max_rows,
                                                 C.byref(sec), self._err, 1024))
         return rows[:n].copy(), sec.value
 
+
+    def lot_draws(self, seed: int, kind: str, n: int, a: float = 0.0, b: float = 0.0, boost: bool = True) -> np.ndarray:
+        """n variates of the host's random-number class (test hook): kind = uniform | randint | gamma | loguniform."""
+        out = np.zeros(n)
+        self.lib.strom_lot_draws(seed, int(boost), {"uniform": 0, "randint": 1, "gamma": 2, "loguniform": 3}[kind], a, b, n, out.ctypes.data_as(_DP))
+        return out
 
     def rebuild_check(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, rounds: int = 10, seed: int = 1) -> float:
         """Incremental against full evaluation over a sequence of trees rebuilt from newick strings (test hook)."""

@@ -261,6 +261,16 @@ HOST_API int strom_incremental_walk(int data_handle, const char* newick, const d
     } catch (const std::exception& e) { return fail(e, err, errlen); }
 }
 
+// TEST HOOK: n variates of the host's Lot from `seed`.  kind 0 = uniform, 1 = randint(lo = a, hi = b), 2 = gamma(shape a, scale b),
+// 3 = logUniform; boost != 0: the Boost 1.66 restatement (mcmc.hpp), else the std stand-in.
+HOST_API int strom_lot_draws(unsigned seed, int boost, int kind, double a, double b, int n, double* out) {
+    Lot lot(seed);
+    lot.setBoostCompatible(boost != 0);
+    for (int i = 0; i < n; ++i)
+        out[i] = kind == 0 ? lot.uniform() : kind == 1 ? lot.randint(static_cast<int>(a), static_cast<int>(b)) : kind == 2 ? lot.gamma(a, b) : lot.logUniform();
+    return n;
+}
+
 // TEST HOOK: an incremental Likelihood is shown a sequence of trees, each built anew by
 // TreeManip::buildFromNewick -- a new Tree object every round, usually at the address of the one just destroyed -- after an
 // NNI swap and a change of three edge lengths; a second Likelihood recomputes everything.  worst_out receives the largest
@@ -369,6 +379,7 @@ HOST_API int strom_mcmc_ex2(int data_handle, const char* newick, unsigned seed, 
         opt.pinvar = pinvar;
         opt.batchEvaluations = (flags & 16u) == 0;
         opt.transientPartials = (flags & 32u) != 0;
+        Lot::defaultBoostCompatible() = (flags & 64u) == 0;         // 64 = the std:: stand-in instead of the Boost 1.66 restatement
         opt.seed = seed; opt.niter = niter; opt.burnin = burnin; opt.samplefreq = samplefreq ? samplefreq : 1; opt.nchains = nchains;
         opt.heatfactor = heatfactor; opt.ncateg = ncateg; opt.gammashape = gammashape;
         opt.statefreq.assign(freqs, freqs + 4);

@@ -38,26 +38,94 @@
 
 namespace strom {
 
+// The reference's Lot (src/lot.hpp) is boost::mt19937 behind Boost.Random 1.66 distributions.  boost::mt19937 and
+// std::mt19937 are the same generator (MT19937, same seeding), so what has to be restated is how Boost turns its
+// 32-bit words into variates.  As published in Boost 1.66:
+//   * uniform_real<>(0,1) / uniform_01: ONE word, x / 2^32 (may be exactly 0; never 1);
+//   * randint (src/lot.hpp:79-106): the reference's own loop over cumulative 1/n sums -- restated with the same
+//     floating-point accumulation;
+//   * gamma_distribution<>(alpha, beta), alpha > 1 (the only case the Dirichlet updaters produce: alpha = 1 + x/lambda,
+//     src/dirichlet_updater.hpp:92): rejection from a Cauchy envelope, y = tan(pi u1), x = sqrt(2 alpha - 1) y + alpha - 1,
+//     accepted when u2 <= (1 + y^2) exp((alpha - 1) log(x / (alpha - 1)) - sqrt(2 alpha - 1) y), two words per attempt;
+//     alpha <= 1 needs Boost's exponential_distribution, a table-driven ziggurat since 1.56 whose tables are not available
+//     here: those cases draw the exponential by inversion (same distribution, other variates).
+// UNPINNED: there is no Boost in this environment to check a single variate against; setBoostCompatible(false) gives the
+// round-1 stand-in ((x + 0.5) / 2^32 and std::gamma_distribution).  Both consume the stream in a fixed order, so traces
+// are reproducible from the seed either way, and engine-vs-CPU trace parity does not depend on the choice.
 class Lot {
   public:
     explicit Lot(unsigned seed = 1) : _gen(seed) {}
     void setSeed(unsigned seed) { _gen.seed(seed); }
-    double uniform() {                      // (0,1): one 32-bit draw, never exactly 0
-        return (static_cast<double>(_gen()) + 0.5) / 4294967296.0;
+    void setBoostCompatible(bool on) { _boost = on; }
+    bool boostCompatible() const { return _boost; }
+    static bool& defaultBoostCompatible() {
+        static bool on = true;
+        return on;
     }
-    double logUniform() { return std::log(uniform()); }
-    double gamma(double shape, double scale) { return std::gamma_distribution<double>(shape, scale)(_gen); }
-    int randint(int low, int high) {        // inclusive, from one uniform like the reference (src/lot.hpp:79-106)
+    double uniform() {
+        if (_boost) return static_cast<double>(_gen()) / 4294967296.0;      // [0,1): one 32-bit word
+        return (static_cast<double>(_gen()) + 0.5) / 4294967296.0;           // (0,1)
+    }
+    double logUniform() {
+        double u = uniform();
+        while (u <= 0.0) u = uniform();         // (the reference asserts u > 0: probability 2^-32 per draw)
+        return std::log(u);
+    }
+    double gamma(double shape, double scale) {
+        if (!_boost) return std::gamma_distribution<double>(shape, scale)(_gen);
+        if (shape == 1.0) return exponential() * scale;
+        if (shape > 1.0) {
+            const double pi = 3.14159265358979323846;
+            for (;;) {
+                const double y = std::tan(pi * uniform());
+                const double x = std::sqrt(2.0 * shape - 1.0) * y + shape - 1.0;
+                if (x <= 0.0) continue;
+                if (uniform() > (1.0 + y * y) * std::exp((shape - 1.0) * std::log(x / (shape - 1.0)) - std::sqrt(2.0 * shape - 1.0) * y)) continue;
+                return x * scale;
+            }
+        }
+        const double p = std::exp(1.0) / (shape + std::exp(1.0));
+        for (;;) {
+            const double u = uniform();
+            const double y = exponential();
+            double x, q;
+            if (u < p) {
+                x = std::exp(-y / shape);
+                q = p * std::exp(-x);
+            } else {
+                x = 1.0 + y;
+                q = p + (1.0 - p) * std::pow(x, shape - 1.0);
+            }
+            if (u >= q) continue;
+            return x * scale;
+        }
+    }
+    int randint(int low, int high) {        // inclusive, from one uniform (src/lot.hpp:79-106)
         const double u = uniform();
-        const int n = high - low + 1;
-        int k = static_cast<int>(u * n);
-        if (k >= n) k = n - 1;
-        return low + k;
+        if (!_boost) {
+            const int n = high - low + 1;
+            int k = static_cast<int>(u * n);
+            if (k >= n) k = n - 1;
+            return low + k;
+        }
+        const double n = static_cast<double>(high - low + 1);
+        int retval = static_cast<int>(n);
+        double cumprob = 0.0;
+        for (unsigned i = 0; i < n; ++i) {
+            cumprob += 1.0 / n;
+            if (u < cumprob) {
+                retval = static_cast<int>(i);
+                break;
+            }
+        }
+        return retval + low;
     }
     typedef std::shared_ptr<Lot> SharedPtr;
 
   private:
+    double exponential() { return -std::log(1.0 - uniform()); }     // (Boost: ziggurat; see the note above)
     std::mt19937 _gen;
+    bool _boost = defaultBoostCompatible();
 };
 
 class Updater {

@@ -106,3 +106,53 @@ def test_incremental_walk_driver_on_cpu_call_path(hostlib):
     assert len(inc) == 40 and np.array_equal(inc, full) and np.all(nops == 8)
     assert len(set(np.round(full, 6))) > 12
     hostlib.data_free(h)
+
+
+def test_lot_restates_boost_uniform_randint_and_gamma(hostlib):
+    """SURVEY.md 8(f) rank 4: the reference's Lot (src/lot.hpp:79-106) is boost::mt19937 behind Boost 1.66 distributions.
+    MT19937 itself is pinned by its published first output for the default seed 5489 (3499211612); the mapping to variates is
+    the published Boost algorithm restated (unpinned: no Boost here): one word / 2^32 per uniform, the reference's own
+    cumulative-sum loop for randint, the Cauchy-envelope rejection sampler for gamma(alpha > 1)."""
+    u = hostlib.lot_draws(5489, "uniform", 3)
+    assert u[0] == 3499211612 / 2.0 ** 32 and u[1] == 581869302 / 2.0 ** 32 and u[2] == 3890346734 / 2.0 ** 32
+    # the stand-in of round 1 is another mapping of the same words
+    v = hostlib.lot_draws(5489, "uniform", 3, boost=False)
+    assert np.allclose(v, u + 0.5 / 2.0 ** 32, rtol=0, atol=1e-15) and not np.array_equal(u, v)
+    # randint: same words, the reference's loop
+    for lo, hi in ((0, 7), (-2, 3), (0, 0), (5, 6)):
+        us = hostlib.lot_draws(77, "uniform", 500)
+        ks = hostlib.lot_draws(77, "randint", 500, lo, hi)
+        n = float(hi - lo + 1)
+        want = []
+        for x in us:
+            ret, cum = int(n), 0.0
+            for i in range(int(n)):
+                cum += 1.0 / n
+                if x < cum:
+                    ret = i
+                    break
+            want.append(ret + lo)
+        assert np.array_equal(ks, np.array(want, dtype=float))
+        assert ks.min() >= lo and ks.max() <= hi
+    # gamma(alpha > 1): replay of the published algorithm on the same words
+    import math
+    us = list(hostlib.lot_draws(123, "uniform", 4000))
+    got = hostlib.lot_draws(123, "gamma", 200, 7.5, 2.0)
+    it = iter(us)
+    want = []
+    for _ in range(200):
+        while True:
+            y = math.tan(math.pi * next(it))
+            x = math.sqrt(2 * 7.5 - 1) * y + 7.5 - 1
+            if x <= 0:
+                continue
+            if next(it) > (1 + y * y) * math.exp((7.5 - 1) * math.log(x / (7.5 - 1)) - math.sqrt(2 * 7.5 - 1) * y):
+                continue
+            want.append(x * 2.0)
+            break
+    assert np.allclose(got, want, rtol=1e-14)
+    big = hostlib.lot_draws(9, "gamma", 40000, 3.0, 1.5)
+    assert abs(big.mean() - 4.5) < 0.05 and abs(big.var() - 6.75) < 0.25
+    small = hostlib.lot_draws(9, "gamma", 40000, 0.4, 1.0)           # alpha < 1 (never asked for by the updaters): right distribution
+    assert abs(small.mean() - 0.4) < 0.02 and abs(small.var() - 0.4) < 0.05
+    assert np.all(hostlib.lot_draws(3, "loguniform", 1000) < 0.0)
