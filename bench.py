@@ -382,6 +382,7 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
     cols = np.repeat(np.arange(P), fx["counts"].astype(int))
     hd = H.data_from_codes(data.astype(np.int32)[:, cols], compress=True)
     llf, sec = H.loglik(hd, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1)
+    llfm, secm = H.loglik(hd, str(fx["newick"]), PAUP_PI, PAUP_R, PAUP_ALPHA, 4, pinvar=pinvar, repeats=steps + 1, transient_partials=False)
     H.data_free(hd)
     # ... and the same facade compiled as the reference has it: 13 BeagleLib calls per evaluation, library = this engine
     llf13, sec13 = None, None
@@ -410,6 +411,9 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
         "evals_per_sec_device": 1000.0 / dev_ms, "evals_per_sec_e2e_13call_python_ctypes": 1000.0 / e2e_ms,
         "evals_per_sec_e2e_fused_call": 1000.0 / fused_ms,
         "evals_per_sec_e2e_cpp_facade": 1.0 / sec, "logL_cpp_facade": llf,
+        "evals_per_sec_e2e_cpp_facade_every_buffer_written": 1.0 / secm, "logL_cpp_facade_every_buffer_written": llfm,
+        "cpp_facade_note": "Likelihood::calcLogLikelihood (C++), transient partials as the facade has them by default; the second figure "
+                           "with Likelihood::setTransientPartials(false)",
         "evals_per_sec_e2e_cpp_facade_13_calls": (1.0 / sec13) if sec13 else None, "logL_cpp_facade_13_calls": llf13,
         "batched_chains": {"chains": K, "call": "sb200EvalBatchAsync: one set of kernel launches for all chains (own tree and model each)",
                            "evals_per_sec_device": K * 1000.0 / batch_dev_ms, "evals_per_sec_e2e": K * 1000.0 / batch_e2e_ms,

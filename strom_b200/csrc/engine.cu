@@ -288,7 +288,7 @@ struct Engine {
         useTipsKernel = envInt("SB200_TIPS_KERNEL", 1) != 0;
         forceVariant = envInt("SB200_VARIANT", -1);
         wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 16 * smCount);
-        narrowMinWarps = envInt("SB200_NARROW_MIN_WARPS", 4 * smCount);
+        narrowMinWarps = envInt("SB200_NARROW_MIN_WARPS", smCount);
         CK(cudaStreamSynchronize(stream));
     }
 

@@ -110,14 +110,14 @@ class HostAPI:
 
     # ---- Likelihood --------------------------------------------------------------------------
     def loglik(self, data_handle: int, newick: str, freqs, rmat, shape: float, ncat: int, pinvar: float = 0.0, devices=(0,),
-               single: bool = False, repeats: int = 1, transient_partials: bool = False):
+               single: bool = False, repeats: int = 1, transient_partials: bool = True):
         """Likelihood::calcLogLikelihood through the C++ facade; returns (logL, seconds per evaluation)."""
         f = np.ascontiguousarray(freqs, dtype=np.float64)
         r = np.ascontiguousarray(rmat, dtype=np.float64)
         dev = np.ascontiguousarray(devices, dtype=np.int32)
         out, sec = C.c_double(), C.c_double()
         self._check(self.lib.strom_loglik(data_handle, newick.encode(), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP), shape, ncat, pinvar,
-                                          int(dev.size), dev.ctypes.data_as(_IP), int(bool(single)) | (2 if transient_partials else 0), repeats,
+                                          int(dev.size), dev.ctypes.data_as(_IP), int(bool(single)) | (0 if transient_partials else 4), repeats,
                                           C.byref(out), C.byref(sec),
                                           self._err, 1024))
         return out.value, sec.value
@@ -127,7 +127,7 @@ class HostAPI:
     def mcmc(self, data_handle: int, newick: str, seed: int = 13579, niter: int = 100, burnin: int = 100, samplefreq: int = 1,
              nchains: int = 1, heatfactor: float = 0.5, ncateg: int = 4, gammashape: float = 0.5, freqs=(0.25,) * 4,
              rmat=(1.0 / 6,) * 6, devices=(0,), per_chain_streams: bool = False, parallel_chains: bool = False,
-             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True, transient_partials: bool = False, boost_lot: bool = True):
+             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True, transient_partials: bool = True, boost_lot: bool = True):
         """Returns (trace [rows][15] = iteration, lnL, lnPrior, TL, 6 r, 4 pi, alpha; seconds).
 
         ``parallel_chains``: the heated chains are stepped side by side on host threads (one chain per GPU of
@@ -143,7 +143,7 @@ class HostAPI:
         rows = np.zeros((max_rows, 15))
         sec = C.c_double()
         flags = (1 if per_chain_streams else 0) | (2 if parallel_chains else 0) | (4 if incremental else 0) | \
-            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16) | (32 if transient_partials else 0) | (0 if boost_lot else 64)
+            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16) | (0 if transient_partials else 32) | (0 if boost_lot else 64)
         n = self._check(self.lib.strom_mcmc_ex2(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor,
                                                 ncateg, gammashape, float(pinvar), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
                                                 int(dev.size), dev.ctypes.data_as(_IP), flags, rows.ctypes.data_as(_DP), max_rows,

@@ -173,7 +173,7 @@ HOST_API int strom_loglik(int data_handle, const char* newick, const double* fre
         L->setModel(makeModel(freqs, rmat, shape, ncat, pinvar));
         if (ndevices > 0) L->setDevices(std::vector<int>(devices, devices + ndevices));
         if (single & 1) L->setSinglePrecision(true);
-        if (single & 2) L->setTransientPartials(true);
+        L->setTransientPartials((single & 4) == 0);              // 4 = every node's buffer written, as the engine-level default
         double v = L->calcLogLikelihood(tm.getTree());
         if (repeats > 1) {
             const auto t0 = std::chrono::steady_clock::now();
@@ -353,7 +353,7 @@ HOST_API int strom_local_move_check(const char* newick, unsigned seed, double la
 // `flags`: 1 = every chain draws from its own random stream, 2 = chains are stepped side by side on host threads
 // (one heated chain per GPU; implies 1), 4 = incremental likelihood (only the changed path is re-evaluated).
 // 8 = lockstep: one host thread begins every update on all chains before finishing it on any (implies 1).
-// 32 = transient partials (Likelihood::setTransientPartials).
+// 32 = transient partials OFF (Likelihood::setTransientPartials(false): every node's buffer is written).
 // 16 = lockstep WITHOUT handing the chains' evaluations to the engine as one set of launches (for comparison).
 // 0 = the reference's single shared stream, chains in turn, every node recomputed on every call.
 // pinvar > 0: GTR+I+G with that fixed proportion of invariable sites.
@@ -378,7 +378,7 @@ HOST_API int strom_mcmc_ex2(int data_handle, const char* newick, unsigned seed, 
         McmcOptions opt;
         opt.pinvar = pinvar;
         opt.batchEvaluations = (flags & 16u) == 0;
-        opt.transientPartials = (flags & 32u) != 0;
+        opt.transientPartials = (flags & 32u) == 0;                   // 32 = every node's buffer written
         Lot::defaultBoostCompatible() = (flags & 64u) == 0;         // 64 = the std:: stand-in instead of the Boost 1.66 restatement
         opt.seed = seed; opt.niter = niter; opt.burnin = burnin; opt.samplefreq = samplefreq ? samplefreq : 1; opt.nchains = nchains;
         opt.heatfactor = heatfactor; opt.ncateg = ncateg; opt.gammashape = gammashape;

@@ -92,8 +92,11 @@ class Likelihood {
     // cooperate: a rejected move is simply the next difference.  Has no effect on the CPU call path.
     void setIncremental(bool on);
     // Engine builds: partials that only travel in registers inside a fused chain of operations are not written to HBM
-    // (sb200SetTransientPartials; the reference recomputes every node on every call and never reads a buffer back).
-    // Same log-likelihood bit for bit.  No effect with incremental evaluation or on the CPU call path.
+    // (sb200SetTransientPartials).  ON by default behind this facade: calcLogLikelihood recomputes every node on every call
+    // (as the reference does, src/likelihood.hpp:409-413) and nothing behind the facade ever reads a node's buffer back, so
+    // the copies would be written for nobody.  Same log-likelihood bit for bit.  The engine itself (13 BeagleLib calls,
+    // sb200Eval) keeps BeagleLib's behaviour -- every destination buffer written -- unless asked.  No effect with incremental
+    // evaluation (which reads earlier calls' buffers) or on the CPU call path.
     void setTransientPartials(bool on);
 #ifdef STROM_B200_ENGINE
     // Evaluations begun on this object are enqueued together with those of the other Likelihoods that share `b`
@@ -148,7 +151,7 @@ class Likelihood {
 
     // what the engine holds from the previous call (incremental evaluation)
     bool _incremental;
-    bool _transient = false;
+    bool _transient = true;
     bool _remembered;
     unsigned long long _held_tree_uid;   // Tree::uid() of the tree the device state belongs to (0: none)
     std::vector<int> _buffer_of;         // by node slot (index in Tree::_nodes): buffer = matrix index, frozen at the first call

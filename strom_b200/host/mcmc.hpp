@@ -559,7 +559,7 @@ struct McmcOptions {
     bool lockstepChains = false;             // ONE host thread: every update is begun (proposed, likelihood enqueued) on all
                                              // chains before it is finished on any, so the chains' evaluations overlap on the
                                              // GPU(s) they share (implies perChainStreams; same trace as perChainStreams alone)
-    bool transientPartials = false;          // engine builds: Likelihood::setTransientPartials (no effect with `incremental`)
+    bool transientPartials = true;           // engine builds: Likelihood::setTransientPartials (the facade's default; no effect with `incremental`)
     bool batchEvaluations = true;            // lockstep, engine builds: the evaluations the chains of one GPU begin together go
                                              // to the engine as ONE set of kernel launches (sb200EvalBatchAsync); same values
     bool parallelChains = false;             // every chain runs on its own host thread (implies perChainStreams); only the two
