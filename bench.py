@@ -495,7 +495,7 @@ def mc3_block(devices, niter=200, burnin=100, nchains=8):
         how = "one heated chain per GPU (%d GPUs), every chain on its own host thread" % len(devices)
     else:
         tr_side, sec_side = H.mcmc(hd, str(fx["newick"]), lockstep_chains=True, **kw)
-        how = "ONE GPU, one host thread: every update begun on all chains, their evaluations ONE set of kernel launches"
+        how = "ONE GPU, one host thread: the chains as two half-sets, each update of a half begun on all its chains and evaluated as ONE set of kernel launches while the host prepares the other half"
     H.data_free(hd)
     its = nchains * (niter + burnin)
     same = tr_turn.shape == tr_side.shape and bool(np.array_equal(tr_turn, tr_side))

@@ -587,8 +587,11 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
     const bool ownStreams = opt.perChainStreams || opt.parallelChains || opt.lockstepChains;
     std::vector<Chain> chains(opt.nchains);
 #ifdef STROM_B200_ENGINE
-    std::map<int, EvalBatcher::SharedPtr> batchers;                // one per GPU
+    // one per GPU and half: the chains are stepped as two half-sets, so that the host prepares one half's proposals while
+    // the GPU evaluates the other half's (see stepAll)
+    std::map<std::pair<int, int>, EvalBatcher::SharedPtr> batchers;
 #endif
+    const unsigned halfSize = (opt.nchains + 1) / 2;
     for (unsigned c = 0; c < opt.nchains; ++c) {
         Chain& ch = chains[c];
         ch.setTreeFromNewick(newick);
@@ -605,7 +608,7 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         lik->setDevices(std::vector<int>(1, opt.devices[c % opt.devices.size()]));
 #ifdef STROM_B200_ENGINE
         if (opt.lockstepChains && opt.batchEvaluations && !opt.parallelChains && opt.nchains > 1) {
-            EvalBatcher::SharedPtr& b = batchers[opt.devices[c % opt.devices.size()]];
+            EvalBatcher::SharedPtr& b = batchers[std::make_pair(opt.devices[c % opt.devices.size()], c < halfSize ? 0 : 1)];
             if (!b) b.reset(new EvalBatcher());
             lik->setBatcher(b);
         }
@@ -750,9 +753,25 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
             return;
         }
         const size_t nu = chains[0].numUpdates();          // (same model dimensions in every chain)
+        // Two half-sets A and B, software-pipelined: while the GPU evaluates one half's proposals the host finishes and
+        // proposes the other half's.  Every chain still sees its own updates in order and draws from its own stream, so
+        // the trace is that of the chains stepped in turn.
+        auto beginHalf = [&](int half, size_t k) {
+            for (unsigned c = half ? halfSize : 0; c < (half ? opt.nchains : halfSize); ++c) chains[c].beginUpdate(k);
+#ifdef STROM_B200_ENGINE
+            for (auto& b : batchers)
+                if (b.first.second == half) b.second->flush();       // this half's evaluations: one set of launches per GPU
+#endif
+        };
+        auto finishHalf = [&](int half, size_t k) {
+            for (unsigned c = half ? halfSize : 0; c < (half ? opt.nchains : halfSize); ++c) chains[c].finishUpdate(k);
+        };
+        beginHalf(0, 0);
         for (size_t k = 0; k < nu; ++k) {
-            for (Chain& ch : chains) ch.beginUpdate(k);
-            for (Chain& ch : chains) ch.finishUpdate(k);
+            beginHalf(1, k);
+            finishHalf(0, k);
+            if (k + 1 < nu) beginHalf(0, k + 1);
+            finishHalf(1, k);
         }
     };
     for (unsigned it = 1; it <= opt.burnin; ++it) {
