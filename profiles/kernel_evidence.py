@@ -27,7 +27,7 @@ def pretty(name):
     m = re.search(r"(transition_matrices|tiptip_tables)_kernelI([df])", name)
     if m:
         return "%s<%s>" % (m.group(1), "f64" if m.group(2) == "d" else "f32")
-    m = re.search(r"N5sb200\d+(\w+?)E", name)
+    m = re.search(r"\d+([a-z_]+_kernel)", name)
     return m.group(1) if m else name[:50]
 
 
