@@ -11,7 +11,7 @@ CSRC = os.path.join(ROOT, "strom_b200", "csrc")
 LIB = os.path.join(CSRC, "libstrom_b200.so")
 WANT = re.compile(r"prune_chains_kernelI([df])Li([145])ELi(\d)ELb(\d)|prune_quad_kernelI([df])Li([145])|root_loglik_kernelI([df])Li([45])|"
                   r"transition_matrices_kernelI([df])|tiptip_tables_kernelI([df])|fold_roots|pattern")
-SHAPES = {"0": "stream", "1": "wide", "2": "narrow"}
+SHAPES = {"0": "stream", "1": "wide", "2": "narrow", "4": "wide2"}
 
 
 def pretty(name):

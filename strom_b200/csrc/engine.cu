@@ -191,7 +191,8 @@ struct Engine {
     bool usePdl = true;
     bool useTipsKernel = true;            // SB200_TIPS_KERNEL=0 (tuning aid): tips-only launches run the general kernel
     int forceVariant = -1;                // SB200_VARIANT (tuning aid): every launch of a small instance runs this thread shape
-    int wideMinWarps = 0;                 // small instances: a level runs the wide thread shape from this many warps up,
+    int wideMinWarps = 0;                 // small instances: a level runs a wide thread shape from this many warps (of that shape) up,
+    int wide2MinWarps = 0;                // ... the two-categories-per-thread shape from this many (of ITS warps) up,
     int narrowMinWarps = 0;               // ... the narrow one from this many up, the quad shape below
 
     size_t realSize() const { return fp32 ? 4 : 8; }
@@ -287,7 +288,8 @@ struct Engine {
         usePdl = envInt("SB200_PDL", 1) != 0;                 // tuning aid: plain stream order
         useTipsKernel = envInt("SB200_TIPS_KERNEL", 1) != 0;
         forceVariant = envInt("SB200_VARIANT", -1);
-        wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 16 * smCount);
+        wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 64 * smCount);
+        wide2MinWarps = envInt("SB200_WIDE2_MIN_WARPS", 16 * smCount);
         narrowMinWarps = envInt("SB200_NARROW_MIN_WARPS", smCount);
         CK(cudaStreamSynchronize(stream));
     }
@@ -397,10 +399,13 @@ struct Engine {
             return c;
         }
         const int K = std::max(1, batchHint);
-        const long wideWarps = static_cast<long>(K) * chainCount * (Ppad / varPatterns(C, kVarWide, static_cast<int>(realSize()))) * varWarps(C, kVarWide, static_cast<int>(realSize()));
-        const long narrowWarps = static_cast<long>(K) * chainCount * (Ppad / 32) * C;
-        c.variant = wideWarps >= wideMinWarps ? kVarWide : narrowWarps >= narrowMinWarps ? kVarNarrow : kVarQuad;
-        if (forceVariant >= kVarWide && forceVariant <= kVarQuad) c.variant = forceVariant;
+        const int rb = static_cast<int>(realSize());
+        const long perChain = static_cast<long>(K) * chainCount * (Ppad / 32);                  // pattern sub-tiles x chains
+        const long wideWarps = perChain * varNCW(C, kVarWide, rb), wide2Warps = perChain * varNCW(C, kVarWide2, rb);
+        const long narrowWarps = perChain * C;
+        c.variant = wideWarps >= wideMinWarps ? kVarWide : wide2Warps >= wide2MinWarps ? kVarWide2
+                  : narrowWarps >= narrowMinWarps ? kVarNarrow : kVarQuad;
+        if (forceVariant >= kVarWide && forceVariant < kVarCount) c.variant = forceVariant;
         if (c.variant == kVarQuad) {                   // every chain its own group: the launch has blocks to spare
             c.groups = std::max(1, chainCount);
             return c;
@@ -741,9 +746,10 @@ static void launchLevelV(Engine& L, const PruneBatch<real>& pb, dim3 grid, bool 
     else launchK(L.stream, L.usePdl, prune_chains_kernel<real, CC, V, false>, grid, dim3(varThreads(CC, V, sizeof(real))), pb);
 }
 template <typename real, int CC>
-static void launchLevelC(Engine& L, const PruneBatch<real>& pb, int tilesOf[4], int maxGroups, int K, int V, bool tips) {
+static void launchLevelC(Engine& L, const PruneBatch<real>& pb, int tilesOf[kVarCount], int maxGroups, int K, int V, bool tips) {
     const dim3 grid(tilesOf[V], maxGroups, K);
-    if (V == kVarQuad) launchK(L.stream, L.usePdl, prune_quad_kernel<real, CC>, grid, dim3(32 * CC), pb);
+    if (V == kVarWide2) launchLevelV<real, CC, kVarWide2>(L, pb, grid, tips);
+    else if (V == kVarQuad) launchK(L.stream, L.usePdl, prune_quad_kernel<real, CC>, grid, dim3(32 * CC), pb);
     else if (V == kVarStream) launchLevelV<real, CC, kVarStream>(L, pb, grid, tips);
     else if (V == kVarWide) launchLevelV<real, CC, kVarWide>(L, pb, grid, tips);
     else launchLevelV<real, CC, kVarNarrow>(L, pb, grid, tips);
@@ -778,8 +784,8 @@ static void launchPartialsSetT(Engine* const* es, int K, const int* cumIdx) {
         CK(cudaGetLastError());
         ++L.launches;
     }
-    int tilesOf[4];
-    for (int v = 0; v < 3; ++v) tilesOf[v] = L.Ppad / varPatterns(C, v, sizeof(real));
+    int tilesOf[kVarCount];
+    for (int v = 0; v < kVarCount; ++v) tilesOf[v] = L.Ppad / varPatterns(C, v, sizeof(real));
     tilesOf[kVarQuad] = L.Ppad / kQuadPatterns;
     const int traceLevel = envInt("SB200_TRACE_LEVEL", -1);   // tuning aid (needs -DSB200_TRACE)
     for (size_t l = 0; l < maxLevels; ++l) {

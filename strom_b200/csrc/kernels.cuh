@@ -44,36 +44,41 @@ __host__ __device__ constexpr int ttStride(int C, int realBytes) { return 25 * t
 
 // ------------------------------------------------------------------------------------------
 // Shapes of the pruning kernel (template parameter V).  A thread owns ONE pattern and CPT of the C categories; a
-// warp = 32 consecutive patterns x CPT categories; NCW = C / CPT warps cover a pattern sub-tile; a block holds TP
-// sub-tiles.
-//   kVarStream  streaming sizes: all categories in the thread (matrix reads are warp-wide broadcasts, the per-pattern
-//               maximum over categories never leaves the registers, the reciprocal is taken once per pattern), 8 warps;
-//   kVarWide    the same thread shape in 4-warp blocks, for launches of small instances that have enough independent
-//               chains to fill the GPU (the lower levels of rbcl738, or several evaluations batched);
-//   kVarNarrow  one category per thread (a warp per category, maxima exchanged through shared memory): C times the
-//               warps and a C times shorter dependent instruction stream per step, for launches with few chains,
-//               where a step is bound by the latency of one warp's instructions;
+// warp = 32 consecutive patterns x CPT categories; NCW = ceil(C / CPT) warps cover a pattern sub-tile (a category count
+// that does not divide leaves the last warp's spare slots repeating the last category, without storing); a block holds
+// TP sub-tiles.
+//   kVarStream  streaming sizes: as many categories per thread as 96 registers carry without spilling -- all four of
+//               GTR+G4 in FP64 (matrix reads are warp-wide broadcasts, the per-pattern maximum over categories never
+//               leaves the registers, ONE reciprocal per pattern), 3+2 for five; 4-warp blocks, 5 per SM;
+//   kVarWide    the same thread shape for launches of small instances with so many independent chains that even this
+//               shape fills the GPU (the first launches of several evaluations batched);
+//   kVarWide2   two categories per thread (two category warps exchange their maxima through shared memory): twice the
+//               warps, 80 registers -- launches of small instances with enough chains for THIS shape to fill the GPU
+//               (the lower levels of one rbcl738 evaluation);
+//   kVarNarrow  one category per thread (a warp per category): C times the warps and a C times shorter dependent
+//               instruction stream per step, for launches with few chains, where a step is bound by the latency of
+//               one warp's instructions;
 //   kVarQuad    one STATE of one category of one pattern per thread (prune_quad_kernel: a warp = 8 patterns x 4 states
-//               of a category, a block = C such warps): four times the warps again and a quarter of the arithmetic per
-//               thread, for the last launches of a small tree -- a handful of chains of dependent steps that leave all
-//               but a few warp schedulers of the GPU idle whatever the shape.
+//               of a category, a block = C such warps): below one warp per SM (tiny data sets).
 // ------------------------------------------------------------------------------------------
-enum { kVarStream = 0, kVarWide = 1, kVarNarrow = 2, kVarQuad = 3 };
+enum { kVarStream = 0, kVarWide = 1, kVarNarrow = 2, kVarQuad = 3, kVarWide2 = 4, kVarCount = 5 };
 constexpr int kQuadPatterns = 8;    // patterns per block of the quad shape
-// categories per thread of the stream / wide shapes: what the register file carries without spilling (two FP64 or four
-// FP32 operand vectors per operand); a category count that does not divide leaves the last warp's spare slots repeating
-// the last category (5 = 2+2+1 in FP64, 3+2 in FP32)
 #ifndef SB200_CPT64
-#define SB200_CPT64 2
+#define SB200_CPT64 4              // (2: the round's first layout; 32.6 against 30.6 ms per 1M-pattern evaluation)
 #endif
 #ifndef SB200_CPT32
 #define SB200_CPT32 4
 #endif
-__host__ __device__ constexpr int cptWide(int C, int realBytes) {
-    return realBytes == 8 ? (C < SB200_CPT64 ? C : SB200_CPT64)
+__host__ __device__ constexpr int cptMost(int C, int realBytes) {       // stream / wide
+    return realBytes == 8 ? (C <= SB200_CPT64 ? C : (C == 5 || C == 6) ? 3 : SB200_CPT64)
                           : (C <= SB200_CPT32 ? C : (C == 5 || C == 6) ? 3 : SB200_CPT32);
 }
-__host__ __device__ constexpr int varCPT(int C, int V, int realBytes) { return V == kVarNarrow ? 1 : cptWide(C, realBytes); }
+__host__ __device__ constexpr int cptTwo(int C, int realBytes) {        // wide2: 2, or 3+2 for five categories
+    return C <= 2 ? C : (C == 5 && cptMost(C, realBytes) >= 3) ? 3 : 2;
+}
+__host__ __device__ constexpr int varCPT(int C, int V, int realBytes) {
+    return V == kVarNarrow ? 1 : V == kVarWide2 ? cptTwo(C, realBytes) : cptMost(C, realBytes);
+}
 __host__ __device__ constexpr int varNCW(int C, int V, int realBytes) { return (C + varCPT(C, V, realBytes) - 1) / varCPT(C, V, realBytes); }
 #ifndef SB200_STREAM_WARPS
 #define SB200_STREAM_WARPS 4
@@ -92,13 +97,13 @@ __host__ __device__ constexpr int varPatterns(int C, int V, int realBytes) { ret
 #ifndef SB200_REG_BUDGET
 #define SB200_REG_BUDGET 80
 #endif
-#ifndef SB200_REG_BUDGET_STREAM
-#define SB200_REG_BUDGET_STREAM 72
+#ifndef SB200_REG_BUDGET_MOST
+#define SB200_REG_BUDGET_MOST 96
 #endif
 __host__ __device__ constexpr int varBlocksPerSm(int C, int V, bool tips, int realBytes) {
-    // registers per thread the kernel is compiled for: 64 for the tips-only variants, otherwise 80, or 72 for the streaming
-    // shape (7 resident blocks of 4 warps instead of 6: 32.2 ms against 32.7 per 1M-pattern evaluation)
-    const int regs = tips ? 64 : V == kVarStream ? SB200_REG_BUDGET_STREAM : SB200_REG_BUDGET;
+    // registers per thread the kernel is compiled for: 64 for the tips-only variants; otherwise 96 where a thread carries
+    // three or four FP64 categories (stream / wide: no spills, 5 resident blocks of 4 warps), 80 for the others
+    const int regs = tips ? 64 : (realBytes == 8 && varCPT(C, V, realBytes) >= 3) ? SB200_REG_BUDGET_MOST : SB200_REG_BUDGET;
     const int byRegs = 65536 / (regs * varThreads(C, V, realBytes));
     return byRegs < 1 ? 1 : byRegs > 16 ? 16 : byRegs;
 }
