@@ -475,33 +475,55 @@ def timed_variant(E, tips_h, Pl, ea, local_rank, n, patterns, logl_ref, steps, *
                          "algorithmic_bytes_per_eval": fa.value, "scheduled_bytes_per_eval": fs.value, "traffic": None}}
 
 
-def mc3_block(devices, niter=200, burnin=100, nchains=8):
-    """BASELINE.json configs[4]: Metropolis-coupled MCMC, 8 heated chains on rbcl738 (reference loop src/strom.hpp:316-402),
-    through the C++ host driver: chains stepped in turn (the reference's order of work) against side by side -- one chain per
-    GPU on host threads when there are several GPUs, or, on ONE GPU, one host thread with the chains' evaluations batched
-    into one set of launches.  Same seed: the two traces must be identical."""
-    from strom_b200.host import host
-    H = host()
+MC3_KW = dict(seed=13579, niter=200, burnin=100, samplefreq=10, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA, freqs=PAUP_PI,
+              rmat=[x / sum(PAUP_R) for x in PAUP_R])
+
+
+def mc3_data(H):
     fx = np.load(os.path.join(ROOT, "tests", "golden", "rbcl738.npz"))
     data = np.minimum(fx["data"], 4).astype(np.int32)
     cols = np.repeat(np.arange(data.shape[1]), fx["counts"].astype(int))
-    hd = H.data_from_codes(data[:, cols], compress=True)
-    kw = dict(seed=13579, niter=niter, burnin=burnin, samplefreq=10, nchains=nchains, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA,
-              freqs=PAUP_PI, rmat=[x / sum(PAUP_R) for x in PAUP_R], devices=tuple(devices))
-    H.mcmc(hd, str(fx["newick"]), **dict(kw, niter=4, burnin=2), per_chain_streams=True)                  # warm-up (instances, plans)
-    tr_turn, sec_turn = H.mcmc(hd, str(fx["newick"]), per_chain_streams=True, **kw)
+    return H.data_from_codes(data[:, cols], compress=True), str(fx["newick"])
+
+
+def mc3_block(devices, nchains=8):
+    """BASELINE.json configs[4]: Metropolis-coupled MCMC, 8 heated chains on rbcl738 (reference loop src/strom.hpp:316-402),
+    through the C++ host driver in ONE process: chains stepped in turn (the reference's order of work) against side by side -- one
+    chain per GPU on host threads when there are several GPUs, or, on ONE GPU, one host thread with the chains' evaluations batched
+    into sets of launches.  Same seed: the two traces must be identical."""
+    from strom_b200.host import host
+    H = host()
+    hd, newick = mc3_data(H)
+    kw = dict(MC3_KW, nchains=nchains, devices=tuple(devices))
+    H.mcmc(hd, newick, **dict(kw, niter=4, burnin=2), per_chain_streams=True)                  # warm-up (instances, plans)
+    tr_turn, sec_turn = H.mcmc(hd, newick, per_chain_streams=True, **kw)
     if len(devices) > 1:
-        tr_side, sec_side = H.mcmc(hd, str(fx["newick"]), parallel_chains=True, **kw)
-        how = "one heated chain per GPU (%d GPUs), every chain on its own host thread" % len(devices)
+        tr_side, sec_side = H.mcmc(hd, newick, parallel_chains=True, **kw)
+        how = "one heated chain per GPU (%d GPUs), every chain on its own host thread of ONE process" % len(devices)
     else:
-        tr_side, sec_side = H.mcmc(hd, str(fx["newick"]), lockstep_chains=True, **kw)
+        tr_side, sec_side = H.mcmc(hd, newick, lockstep_chains=True, **kw)
         how = "ONE GPU, one host thread: the chains as two half-sets, each update of a half begun on all its chains and evaluated as ONE set of kernel launches while the host prepares the other half"
     H.data_free(hd)
-    its = nchains * (niter + burnin)
+    its = nchains * (kw["niter"] + kw["burnin"])
     same = tr_turn.shape == tr_side.shape and bool(np.array_equal(tr_turn, tr_side))
-    return {"workload": "rbcl738 GTR+G4, %d heated chains, %d iterations each (5 updates + a swap proposal per iteration, a sample every 10)" % (nchains, niter + burnin),
+    return {"workload": "rbcl738 GTR+G4, %d heated chains, %d iterations each (5 updates + a swap proposal per iteration, a sample every 10)" % (nchains, kw["niter"] + kw["burnin"]),
             "side_by_side": how, "chain_iterations_per_sec_in_turn": its / sec_turn, "chain_iterations_per_sec_side_by_side": its / sec_side,
-            "speedup": sec_turn / sec_side, "traces_identical": same, "gpus": len(devices)}
+            "speedup": sec_turn / sec_side, "traces_identical": same, "gpus": len(devices)}, tr_turn
+
+
+def mc3_one_chain_per_rank(local_rank, dev):
+    """The same run with one chain per PROCESS (rank r = chain r on GPU r), swap offers exchanged by an NCCL all-gather over
+    NVLink after every iteration (strom_b200/mc3.py).  Every rank calls this; returns (trace on every rank, seconds, chain-iterations)."""
+    from strom_b200 import mc3
+    from strom_b200.host import host
+    H = host()
+    hd, newick = mc3_data(H)
+    kw = dict(MC3_KW, device=local_rank, tensor_device=dev)
+    mc3.run_one_chain_per_rank(H, hd, newick, **dict(kw, niter=4, burnin=2))                   # warm-up (instances, plans, NCCL)
+    rows, sec, its = mc3.run_one_chain_per_rank(H, hd, newick, **kw)
+    trace = mc3.gather_trace(rows, tensor_device=dev)
+    H.data_free(hd)
+    return trace, sec, its
 
 
 def run_ours(args, rank, world, local_rank):
@@ -660,23 +682,39 @@ def run_ours(args, rank, world, local_rank):
                 line["rbcl738"] = rbcl738_block(E, local_rank)
                 line["rbcl738_i_g4"] = rbcl738_block(E, local_rank, pinvar=0.2)
         if world == 1 and not args.no_mc3 and not args.no_rbcl738:
-            line["mc3"] = mc3_block([local_rank])
+            line["mc3"] = mc3_block([local_rank])[0]
     if distributed:
         dist.barrier()                   # every rank has released its shard
         torch.cuda.synchronize()
         if world == 8 and not args.no_mc3:
-            # BASELINE.json configs[4]: 8 heated chains on rbcl738, one per GPU, driven by rank 0.  The other ranks wait on
-            # the rendezvous store (a socket), NOT in an NCCL barrier, whose kernels would spin on the very GPUs the chains use
+            # BASELINE.json configs[4]: 8 heated chains on rbcl738, one per GPU.  First rank 0 alone drives all eight in ONE
+            # process (in turn, then on host threads) while the other ranks wait on the rendezvous store (a socket, NOT an NCCL
+            # barrier, whose kernels would spin on the very GPUs the chains use); then every rank runs ITS chain and the swap
+            # offers travel by NCCL.
             import datetime
             store = dist.distributed_c10d._get_default_store()
+            turn_trace = None
             if rank == 0:
                 try:
-                    line["mc3"] = mc3_block(list(range(world)))
+                    line["mc3"], turn_trace = mc3_block(list(range(world)))
                 except Exception as e:
                     line["mc3"] = {"error": repr(e)}
                 store.set("sb200_mc3_done", "1")
             else:
                 store.wait(["sb200_mc3_done"], datetime.timedelta(minutes=30))
+            try:
+                trace, sec, its = mc3_one_chain_per_rank(local_rank, dev)
+                if rank == 0 and "error" not in line["mc3"]:
+                    m = line["mc3"]
+                    m["one_process_per_gpu"] = {
+                        "how": "rank r = heated chain r on GPU r; after every iteration the ranks all-gather 16 doubles over NCCL "
+                               "(NVLink): the two chains of the swap proposal exchange log kernel, heat and tuning parameters",
+                        "chain_iterations_per_sec": its / sec, "speedup_vs_in_turn": (its / sec) / m["chain_iterations_per_sec_in_turn"],
+                        "trace_identical_to_in_turn": bool(turn_trace is not None and trace.shape == turn_trace.shape and np.array_equal(trace, turn_trace))}
+                    m["speedup_one_process_per_gpu"] = m["one_process_per_gpu"]["speedup_vs_in_turn"]
+            except Exception as e:
+                if rank == 0:
+                    line.setdefault("mc3", {})["one_process_per_gpu"] = {"error": repr(e)}
         dist.barrier()
         dist.destroy_process_group()
     return line if rank == 0 else None

@@ -3,6 +3,7 @@
 // for the test-suite only, a variant linked to the CPU checker (same code, 13-call path).
 #include <chrono>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 #include "likelihood.hpp"
@@ -409,3 +410,117 @@ HOST_API int strom_mcmc(int data_handle, const char* newick, unsigned seed, unsi
                          ndevices, devices, 0u, rows, max_rows, seconds, err, errlen);
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One heated chain of a Metropolis-coupled run per PROCESS (BASELINE.json configs[4]: one chain per GPU, swap proposals
+// between processes; reference loop src/strom.hpp:316-402).  The process steps its chain and, at a swap proposal it takes
+// part in, exchanges one small vector with the partner (strom_b200/mc3.py does that with torch.distributed: NCCL over
+// NVLink, or gloo).  Same chain set-up, random streams, swap schedule and decisions as runMCMC's side-by-side driver, so the
+// sampled trace is the same, bit for bit.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct OneChain {
+    Chain chain;
+    McmcOptions opt;
+};
+std::vector<std::unique_ptr<OneChain>> g_chains;
+OneChain& chainOf(int h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h < 0 || h >= static_cast<int>(g_chains.size()) || !g_chains[h]) throw XStrom("bad chain handle");
+    return *g_chains[h];
+}
+}  // namespace
+
+HOST_API int strom_mc3_chain_create(int data_handle, const char* newick, unsigned seed, unsigned chain_index, double heatfactor, unsigned ncateg,
+                                    double gammashape, double pinvar, const double* freqs, const double* rmat, int device, unsigned flags,
+                                    char* err, int errlen) {
+    try {
+        std::unique_ptr<OneChain> oc(new OneChain());
+        McmcOptions& opt = oc->opt;
+        opt.seed = seed; opt.heatfactor = heatfactor; opt.ncateg = ncateg; opt.gammashape = gammashape; opt.pinvar = pinvar;
+        opt.statefreq.assign(freqs, freqs + 4);
+        opt.rmatrix.assign(rmat, rmat + 6);
+        opt.incremental = (flags & 4u) != 0;
+        opt.transientPartials = (flags & 32u) == 0;
+        Lot::defaultBoostCompatible() = (flags & 64u) == 0;
+        setUpChain(oc->chain, dataOf(data_handle), newick, opt, chain_index, device, Lot::SharedPtr(new Lot(seed + 1000003u * (chain_index + 1))));
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_chains.push_back(std::move(oc));
+        return static_cast<int>(g_chains.size()) - 1;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+HOST_API int strom_mc3_chain_step(int h, int iteration, char* err, int errlen) {
+    try {
+        chainOf(h).chain.nextStep(iteration);
+        return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+HOST_API int strom_mc3_chain_stop_tuning(int h) {
+    try {
+        chainOf(h).chain.stopTuning();
+        return 0;
+    } catch (...) { return -1; }
+}
+
+// what a chain shows its swap partner: out[0] = log kernel (lnL + lnPrior), [1] = heating power, [2] = chain index,
+// [3] = number of tuning parameters, [4..] = the tuning parameters.  Returns the number of doubles written (<= cap).
+HOST_API int strom_mc3_chain_offer(int h, double* out, int cap, char* err, int errlen) {
+    try {
+        Chain& ch = chainOf(h).chain;
+        const std::vector<double> lam = ch.getLambdas();
+        if (cap < 4 + static_cast<int>(lam.size())) throw XStrom("offer buffer too small");
+        out[0] = ch.calcLogLikelihood() + ch.calcLogJointPrior();
+        out[1] = ch.getHeatingPower();
+        out[2] = ch.getChainIndex();
+        out[3] = static_cast<double>(lam.size());
+        for (size_t q = 0; q < lam.size(); ++q) out[4 + q] = lam[q];
+        return 4 + static_cast<int>(lam.size());
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+// an accepted swap: this chain takes the partner's heating power, index and tuning parameters (src/strom.hpp:389-399)
+HOST_API int strom_mc3_chain_take(int h, const double* other) {
+    try {
+        Chain& ch = chainOf(h).chain;
+        ch.setHeatingPower(other[1]);
+        ch.setChainIndex(static_cast<unsigned>(other[2]));
+        ch.setLambdas(std::vector<double>(other + 4, other + 4 + static_cast<int>(other[3])));
+        return 0;
+    } catch (...) { return -1; }
+}
+
+HOST_API double strom_mc3_chain_heat(int h) {
+    try {
+        return chainOf(h).chain.getHeatingPower();
+    } catch (...) { return -1.0; }
+}
+
+// the sample row of this chain (15 doubles as in strom_mcmc_ex); evaluates the likelihood once more, as Strom::sample does
+HOST_API int strom_mc3_chain_row(int h, unsigned iteration, double* r, char* err, int errlen) {
+    try {
+        const TraceRow t = traceRowOf(chainOf(h).chain, iteration);
+        r[0] = t.iteration; r[1] = t.lnL; r[2] = t.lnPrior; r[3] = t.TL;
+        for (int k = 0; k < 11; ++k) r[4 + k] = t.params[k];
+        return 0;
+    } catch (const std::exception& e) { return fail(e, err, errlen); }
+}
+
+HOST_API int strom_mc3_chain_free(int h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h < 0 || h >= static_cast<int>(g_chains.size())) return -1;
+    g_chains[h].reset();
+    return 0;
+}
+
+// the swap schedule every process computes for itself (mcmc.hpp::swapSchedule)
+HOST_API int strom_mc3_schedule(unsigned seed, unsigned nchains, unsigned total, int* ci, int* cj, double* logu, unsigned flags) {
+    Lot::defaultBoostCompatible() = (flags & 64u) == 0;
+    std::vector<unsigned> a, b;
+    std::vector<double> u;
+    swapSchedule(seed, nchains, total, a, b, u);
+    for (unsigned t = 0; t < total; ++t) { ci[t] = static_cast<int>(a[t]); cj[t] = static_cast<int>(b[t]); logu[t] = u[t]; }
+    return 0;
+}

@@ -581,6 +581,59 @@ struct SwapMeeting {
     Offer offer[2];                        // [0] = chain i of the pair, [1] = chain j
 };
 
+// One chain of a Metropolis-coupled run as Strom::initChains sets it up (src/strom.hpp:236-285): its own tree, model, Likelihood
+// (engine instance on `device`) and -- unlike the reference -- its own random stream, seeded from (seed, chain).
+inline void setUpChain(Chain& ch, Data::SharedPtr data, const std::string& newick, const McmcOptions& opt, unsigned c, int device,
+                       Lot::SharedPtr lot) {
+    ch.setTreeFromNewick(newick);
+    ch.setLot(lot);
+    Model::SharedPtr model(new Model());
+    model->setExchangeabilitiesAndStateFreqs(opt.rmatrix, opt.statefreq);
+    model->setGammaShape(opt.gammashape);
+    model->setGammaNCateg(opt.ncateg);
+    if (opt.pinvar > 0.0) model->setPinvar(opt.pinvar);
+    Likelihood::SharedPtr lik(new Likelihood());
+    lik->setQuiet(true);
+    lik->setIncremental(opt.incremental);
+    lik->setTransientPartials(opt.transientPartials);
+    lik->setDevices(std::vector<int>(1, device));
+    lik->setData(data);
+    lik->setModel(model);
+    ch.setLikelihood(lik);
+    ch.startTuning();
+    ch.setChainIndex(c);
+    ch.setHeatingPower(1.0 / (1.0 + opt.heatfactor * c));
+    ch.start();
+}
+
+inline TraceRow traceRowOf(Chain& ch, unsigned iteration) {
+    TraceRow r;
+    r.iteration = iteration;
+    r.lnL = ch.calcLogLikelihood();                 // one more full evaluation per sample, as in Strom::sample (:455)
+    r.lnPrior = ch.calcLogJointPrior();
+    r.TL = ch.getTreeManip()->calcTreeLength();
+    const std::vector<double> x = ch.getModel()->getExchangeabilities(), f = ch.getModel()->getStateFreqs();
+    for (int i = 0; i < 6; ++i) r.params[i] = x[i];
+    for (int i = 0; i < 4; ++i) r.params[6 + i] = f[i];
+    r.params[10] = ch.getModel()->getGammaShape();
+    return r;
+}
+
+// The swap schedule of a run whose chains have their own random streams: which two chains, and the log-uniform deviate of the
+// acceptance test, per iteration -- drawn from the master stream in the order the in-turn loop draws them (src/strom.hpp:344-345,
+// :387).  It consumes no chain state, so every process of a one-chain-per-process run computes the same schedule from the seed.
+inline void swapSchedule(unsigned seed, unsigned nchains, unsigned total, std::vector<unsigned>& ci, std::vector<unsigned>& cj,
+                         std::vector<double>& logu) {
+    Lot lot(seed);
+    ci.assign(total, 0); cj.assign(total, 0); logu.assign(total, 0.0);
+    if (nchains < 2) return;
+    for (unsigned t = 0; t < total; ++t) {
+        ci[t] = static_cast<unsigned>(lot.randint(0, static_cast<int>(nchains) - 1));
+        cj[t] = (ci[t] + 1 + static_cast<unsigned>(lot.randint(0, static_cast<int>(nchains) - 2))) % nchains;
+        logu[t] = lot.logUniform();
+    }
+}
+
 // Strom::run's MCMC branch (src/strom.hpp:486-523): initChains, burn-in with tuning, sampling with swaps.
 inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& newick, const McmcOptions& opt) {
     Lot::SharedPtr lot(new Lot(opt.seed));

@@ -468,7 +468,7 @@ def test_every_thread_shape_gives_the_same_bits(engine, oracle, model, monkeypat
     want = full_eval(oracle, pr, m)
     xe = Extra(engine)
     seen = []
-    for shape in ("", "1", "2", "3"):
+    for shape in ("", "1", "2", "3", "4"):
         if shape:
             monkeypatch.setenv("SB200_VARIANT", shape)
         else:

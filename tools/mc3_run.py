@@ -6,4 +6,4 @@ import torch
 from bench import mc3_block
 n = torch.cuda.device_count()
 devs = list(range(n)) if len(sys.argv) < 2 else [int(x) for x in sys.argv[1].split(",")]
-print(json.dumps(mc3_block(devs), indent=1))
+print(json.dumps(mc3_block(devs)[0], indent=1))
