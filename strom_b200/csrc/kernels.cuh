@@ -546,10 +546,14 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             prod = t;
         }
     };
-    // operand A of a chain start, and the scaler of the chain that produced it
+    // operand A of a chain start, and the scaler of the chain that produced it.  A TIP for A is asked for earlier, with
+    // operand B (fetchTipA): it needs no register the current step still uses, and at the end of the step its latency
+    // would sit on the critical path of the next one (every other step of a tips-only launch starts a chain).
+    auto fetchTipA = [&](const DevRec& r) {
+        if ((r.flags & OP_CHAIN_START) && (TIPS || (r.flags & OP_A_TIP))) sX = *byteOffset(tmine, r.aOff);
+    };
     auto startChain = [&](const DevRec& r) {
-        if (TIPS || (r.flags & OP_A_TIP)) sX = *byteOffset(tmine, r.aOff);
-        else fetchPartial(r.aOff, X);
+        if (!TIPS && !(r.flags & OP_A_TIP)) fetchPartial(r.aOff, X);
         if (!TIPS && scalerWarp) {
             const int sa = r.sa;
             if (sa >= 0) {
@@ -594,7 +598,10 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         if (flags & OP_TIPTIP) {
             // both children are tips: copy the precomputed rescaled vector of (stateA, stateB)
             const int combo = sX * 5 + sY;
-            if (more) fetchB(sops[j + 1]);
+            if (more) {
+                fetchB(sops[j + 1]);
+                fetchTipA(sops[j + 1]);
+            }
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
 #pragma unroll
@@ -649,8 +656,11 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             }
             if (!TIPS && scalerWarp && sops[j].sb >= 0) accumulate(pendAcc, pendProd);
             SB200_TICK(2)
-            // next step's operand B is requested now; the rescaling below hides its latency
-            if (more) fetchB(sops[j + 1]);
+            // next step's operand B (and a tip for A) is requested now; the rescaling below hides its latency
+            if (more) {
+                fetchB(sops[j + 1]);
+                fetchTipA(sops[j + 1]);
+            }
             if (flags & OP_RESCALE) {
                 m = rmax(rmax(X[0][0], X[0][1]), rmax(X[0][2], X[0][3]));
 #pragma unroll
@@ -747,6 +757,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         for (int w = tid; w < nc; w += THREADS) SB200_CHECK_REC(sops[w], grp.opStart + chunk0 + w);
         stage(0, sops[0]);
         if (nc > 1) stage(1, sops[1]);
+        fetchTipA(sops[0]);
         if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);       // (a later chunk may begin in mid-chain: A is carried)
         fetchB(sops[0]);
         if (kPrefetch) {
