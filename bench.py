@@ -376,6 +376,28 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
     tr_dev_ms = b0.elapsed_time(b1) / steps
     for Lk in Ls:
         Lk.close()
+    # ... and the stated FP32 variant (float partials / matrices / tables, FP64 scalers and root accumulation): 8 batched chains
+    Lf = [ShardedLikelihood(data, fx["counts"], NC, device=device, single=True) for _ in range(K)]
+    f32_single = [Lk.calc_log_likelihood(ek) for Lk, ek in zip(Lf, eas)]
+    finsts = (C.c_int * K)(*[Lk.inst for Lk in Lf])
+    E.check(E.sb200EvalBatchAsync(K, finsts, bargs), "batched evaluation (f32)")
+    f32_vals = []
+    for Lk in Lf:
+        E.check(E.sb200Finish(Lk.inst, C.byref(res)), "finish")
+        f32_vals.append(res.value)
+    f32_rel = max(abs(a - b) / abs(b) for a, b in zip(f32_vals, single_vals))
+    for _ in range(warmup):
+        E.check(E.sb200ReplayBatchAsync(K, finsts), "replay")
+    with torch.cuda.stream(Lf[0].stream):
+        Lf[0].stream.synchronize()
+        b0.record()
+        for _ in range(steps):
+            E.check(E.sb200ReplayBatchAsync(K, finsts), "replay")
+        b1.record()
+        Lf[0].stream.synchronize()
+    f32_batch_dev_ms = b0.elapsed_time(b1) / steps
+    for Lk in Lf:
+        Lk.close()
     # the C++ Likelihood facade (strom_b200/host/likelihood.hpp): what strom's Chain / Updaters call
     from strom_b200.host import host
     H = host()
@@ -425,6 +447,8 @@ def rbcl738_block(E, device, steps=300, warmup=30, pinvar=0.0):
                                "speedup_e2e_8_batched_vs_cpu_all_threads": (K * 1000.0 / tr_batch_e2e_ms) / allc,
                                "max_rel_diff_vs_materialised": tr_rel,
                                "what": "sb200SetTransientPartials: partials inside a fused chain are not written to HBM; OFF everywhere else in this block"},
+        "f32_batched_chains": {"evals_per_sec_device": K * 1000.0 / f32_batch_dev_ms, "max_rel_diff_vs_f64": f32_rel, "stated_tolerance": 2e-5,
+                               "what": "BEAGLE_FLAG_PRECISION_SINGLE instances, 8 chains as one launch set, every buffer written"},
         "partial_updates_per_sec_device": upd * 1000.0 / dev_ms,
         "roofline": {"bound": "hbm", "achieved": alg.value / (dev_ms / 1000.0) / 1e9, "peak": peaks()[0], "unit": "GB/s",
                      "frac": alg.value / (dev_ms / 1000.0) / 1e9 / peaks()[0],
@@ -475,7 +499,7 @@ def timed_variant(E, tips_h, Pl, ea, local_rank, n, patterns, logl_ref, steps, *
                          "algorithmic_bytes_per_eval": fa.value, "scheduled_bytes_per_eval": fs.value, "traffic": None}}
 
 
-MC3_KW = dict(seed=13579, niter=200, burnin=100, samplefreq=10, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA, freqs=PAUP_PI,
+MC3_KW = dict(seed=13579, niter=400, burnin=200, samplefreq=10, heatfactor=0.5, ncateg=4, gammashape=PAUP_ALPHA, freqs=PAUP_PI,
               rmat=[x / sum(PAUP_R) for x in PAUP_R])
 
 
@@ -494,8 +518,8 @@ def mc3_block(devices, nchains=8):
     from strom_b200.host import host
     H = host()
     hd, newick = mc3_data(H)
-    kw = dict(MC3_KW, nchains=nchains, devices=tuple(devices))
-    H.mcmc(hd, newick, **dict(kw, niter=4, burnin=2), per_chain_streams=True)                  # warm-up (instances, plans)
+    kw = dict(MC3_KW, nchains=nchains, devices=tuple(devices), time_iterations_only=True)      # (set-up of chains / instances not timed)
+    H.mcmc(hd, newick, **dict(kw, niter=4, burnin=2), per_chain_streams=True)                  # warm-up
     tr_turn, sec_turn = H.mcmc(hd, newick, per_chain_streams=True, **kw)
     if len(devices) > 1:
         tr_side, sec_side = H.mcmc(hd, newick, parallel_chains=True, **kw)

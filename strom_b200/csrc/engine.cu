@@ -99,6 +99,25 @@ struct ParamBlockHeader {
     double rates[kMaxCategories];
 };
 
+// The parameter blocks of the instances of a launch set, back to back in ONE pinned host buffer and ONE device buffer, so
+// that a set's parameters go up in one copy instead of one per instance (8 copies cost 30 us before the first kernel of a
+// 320 us set could start).  Shared by the instances that were put into it; freed with the last of them.
+struct ParamArena {
+    int device = 0;
+    unsigned char* h = nullptr;
+    unsigned char* d = nullptr;
+    size_t slotBytes = 0;
+    int slots = 0;
+    cudaEvent_t copied = nullptr;
+    ~ParamArena() {
+        DeviceGuard guard;
+        guard.enter(device);
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        if (copied) cudaEventDestroy(copied);
+    }
+};
+
 struct Engine {
     int device = 0;
     int smCount = 148;
@@ -124,6 +143,8 @@ struct Engine {
     size_t blockBytes = 0, modelOff = 0, midxOff = 0, elenOff = 0;
     int edgeCap = 0, edgeCount = 0;
     cudaEvent_t blockCopied = nullptr;
+    std::shared_ptr<ParamArena> arena;    // set: hBlock / dBlock are slice `arenaSlot` of a launch set's arena (not owned)
+    int arenaSlot = -1;
     bool blockInFlight = false;
     bool blockDirty = true;               // host image newer than the device image
     // schedule
@@ -215,10 +236,13 @@ struct Engine {
         cudaFree(dTips); cudaFree(dPartials); cudaFree(dMats); cudaFree(dPatWeights);
         for (double* p : dScale) cudaFree(p);
         dScale.clear();
-        cudaFree(dSlots); cudaFree(dBlock); cudaFree(dPlan); cudaFree(dTT);
+        cudaFree(dSlots); cudaFree(dPlan); cudaFree(dTT);
+        if (!arena) cudaFree(dBlock);
         freeParkedPlans();
         cudaFree(dBlockSums); cudaFree(dTicket); cudaFree(dOut); cudaFree(dTrace);
-        if (hBlock) cudaFreeHost(hBlock);
+        if (hBlock && !arena) cudaFreeHost(hBlock);
+        arena.reset();
+        arenaSlot = -1;
         if (hSchedStage) cudaFreeHost(hSchedStage);
         if (hOut) cudaFreeHost(hOut);
         if (blockCopied) cudaEventDestroy(blockCopied);
@@ -299,9 +323,25 @@ struct Engine {
     void waitBlockFree() {
         blockDirty = true;
         if (blockInFlight) {
-            CK(cudaEventSynchronize(blockCopied));
+            CK(cudaEventSynchronize(arena ? arena->copied : blockCopied));
             blockInFlight = false;
         }
+    }
+    // the block goes back to buffers of its own (its content is kept)
+    void leaveArena() {
+        if (!arena) return;
+        CK(cudaStreamSynchronize(stream));
+        unsigned char* nh = nullptr;
+        unsigned char* nd = nullptr;
+        CK(cudaMallocHost(&nh, blockBytes));
+        std::memcpy(nh, hBlock, blockBytes);
+        CK(cudaMalloc(&nd, blockBytes));
+        hBlock = nh;
+        dBlock = nd;
+        arena.reset();
+        arenaSlot = -1;
+        blockInFlight = false;
+        blockDirty = true;
     }
 
     double* scaleBuffer(int idx) {
@@ -324,7 +364,7 @@ struct Engine {
     // ---- (a) ---------------------------------------------------------------------------
     void uploadBlock() {
         CK(cudaMemcpyAsync(dBlock, hBlock, blockBytes, cudaMemcpyHostToDevice, stream));
-        CK(cudaEventRecord(blockCopied, stream));
+        CK(cudaEventRecord(arena ? arena->copied : blockCopied, stream));
         blockInFlight = true;
         blockDirty = false;
     }
@@ -353,6 +393,7 @@ struct Engine {
         waitBlockFree();
         if (count > edgeCap) {
             // grow the block, preserving the model part
+            leaveArena();
             std::vector<unsigned char> keep(hBlock, hBlock + midxOff);
             CK(cudaStreamSynchronize(stream));
             cudaFreeHost(hBlock); cudaFree(dBlock);
@@ -961,6 +1002,41 @@ static void fillCmat(const double* evec, const double* ivec, double* cmat) {
             for (int x = 0; x < 4; ++x) cmat[l++] = evec[i * 4 + x] * ivec[x * 4 + j];
 }
 
+// Puts the parameter blocks of the set's instances into slots 0..K-1 of one arena (the first instance's), unless they
+// already are.  Done once per set (it drains the stream); false if the blocks cannot share an arena.
+static bool shareArena(Engine* const* es, int K, const StromEvalArgs* args) {
+    Engine& L = *es[0];
+    for (int z = 0; z < K; ++z)
+        if (es[z]->blockBytes != L.blockBytes || args[z].edgeCount > es[z]->edgeCap) return false;
+    bool ok = L.arena && L.arenaSlot == 0 && L.arena->slots >= K;
+    for (int z = 1; z < K && ok; ++z) ok = es[z]->arena == L.arena && es[z]->arenaSlot == z;
+    if (ok) return true;
+    CK(cudaStreamSynchronize(L.stream));
+    std::shared_ptr<ParamArena> A(new ParamArena());
+    A->device = L.device;
+    A->slotBytes = (L.blockBytes + 255) & ~size_t(255);
+    A->slots = K;
+    CK(cudaMallocHost(&A->h, A->slotBytes * K));
+    CK(cudaMalloc(&A->d, A->slotBytes * K));
+    CK(cudaEventCreateWithFlags(&A->copied, cudaEventDisableTiming));
+    for (int z = 0; z < K; ++z) {
+        Engine& E = *es[z];
+        unsigned char* nh = A->h + A->slotBytes * z;
+        std::memcpy(nh, E.hBlock, E.blockBytes);
+        if (!E.arena) {
+            cudaFreeHost(E.hBlock);
+            cudaFree(E.dBlock);
+        }
+        E.hBlock = nh;
+        E.dBlock = A->d + A->slotBytes * z;
+        E.arena = A;
+        E.arenaSlot = z;
+        E.blockInFlight = false;
+        E.blockDirty = true;
+    }
+    return true;
+}
+
 // One whole evaluation of every instance of the set: parameter blocks up, then ONE set of launches.  Everything is
 // validated before any instance's parameter block is touched or anything is enqueued.
 static int evalSet(Engine* const* es, int K, const StromEvalArgs* args, double* const* deviceOut) {
@@ -998,6 +1074,8 @@ static int evalSet(Engine* const* es, int K, const StromEvalArgs* args, double* 
             if (sc) return sc;
         }
     }
+    static const bool useArena = envInt("SB200_ARENA", 1) != 0;          // tuning aid: one parameter copy per instance
+    const bool oneCopy = K > 1 && useArena && shareArena(es, K, args);
     for (int z = 0; z < K; ++z) {
         Engine& E = *es[z];
         const StromEvalArgs& a = args[z];
@@ -1009,7 +1087,17 @@ static int evalSet(Engine* const* es, int K, const StromEvalArgs* args, double* 
         std::memcpy(m->evals, a.eigenValues, sizeof(double) * 4);
         std::memcpy(m->weights, a.categoryWeights, sizeof(double) * E.C);
         std::memcpy(E.hHeader()->rates, a.categoryRates, sizeof(double) * E.C);
-        E.uploadBlock();
+        if (!oneCopy) E.uploadBlock();
+    }
+    if (oneCopy) {
+        // the K parameter blocks sit back to back in the set's arena: one copy for all of them
+        ParamArena& A = *L.arena;
+        CK(cudaMemcpyAsync(A.d, A.h, A.slotBytes * K, cudaMemcpyHostToDevice, L.stream));
+        CK(cudaEventRecord(A.copied, L.stream));
+        for (int z = 0; z < K; ++z) {
+            es[z]->blockInFlight = true;
+            es[z]->blockDirty = false;
+        }
     }
     launchMatricesSet(es, K);
     int cumIdx[kMaxBatch];

@@ -127,7 +127,7 @@ class HostAPI:
     def mcmc(self, data_handle: int, newick: str, seed: int = 13579, niter: int = 100, burnin: int = 100, samplefreq: int = 1,
              nchains: int = 1, heatfactor: float = 0.5, ncateg: int = 4, gammashape: float = 0.5, freqs=(0.25,) * 4,
              rmat=(1.0 / 6,) * 6, devices=(0,), per_chain_streams: bool = False, parallel_chains: bool = False,
-             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True, transient_partials: bool = True, boost_lot: bool = True):
+             incremental: bool = False, lockstep_chains: bool = False, pinvar: float = 0.0, batch_evaluations: bool = True, transient_partials: bool = True, boost_lot: bool = True, time_iterations_only: bool = False):
         """Returns (trace [rows][15] = iteration, lnL, lnPrior, TL, 6 r, 4 pi, alpha; seconds).
 
         ``parallel_chains``: the heated chains are stepped side by side on host threads (one chain per GPU of
@@ -143,7 +143,7 @@ class HostAPI:
         rows = np.zeros((max_rows, 15))
         sec = C.c_double()
         flags = (1 if per_chain_streams else 0) | (2 if parallel_chains else 0) | (4 if incremental else 0) | \
-            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16) | (0 if transient_partials else 32) | (0 if boost_lot else 64)
+            (8 if lockstep_chains else 0) | (0 if batch_evaluations else 16) | (0 if transient_partials else 32) | (0 if boost_lot else 64) | (128 if time_iterations_only else 0)
         n = self._check(self.lib.strom_mcmc_ex2(data_handle, newick.encode(), seed, niter, burnin, samplefreq, nchains, heatfactor,
                                                 ncateg, gammashape, float(pinvar), f.ctypes.data_as(_DP), r.ctypes.data_as(_DP),
                                                 int(dev.size), dev.ctypes.data_as(_IP), flags, rows.ctypes.data_as(_DP), max_rows,

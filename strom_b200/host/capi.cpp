@@ -392,7 +392,8 @@ HOST_API int strom_mcmc_ex2(int data_handle, const char* newick, unsigned seed, 
         opt.lockstepChains = (flags & 8u) != 0;
         const auto t0 = std::chrono::steady_clock::now();
         const std::vector<TraceRow> tr = runMCMC(dataOf(data_handle), newick, opt);
-        if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        // (flag 128: the iterations alone, without setting up chains, engine instances and data)
+        if (seconds) *seconds = (flags & 128u) ? opt.loopSeconds : std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const int n = std::min<int>(static_cast<int>(tr.size()), max_rows);
         for (int i = 0; i < n; ++i) {
             double* r = rows + static_cast<size_t>(i) * 15;

@@ -560,6 +560,7 @@ struct McmcOptions {
                                              // chains before it is finished on any, so the chains' evaluations overlap on the
                                              // GPU(s) they share (implies perChainStreams; same trace as perChainStreams alone)
     bool transientPartials = true;           // engine builds: Likelihood::setTransientPartials (the facade's default; no effect with `incremental`)
+    mutable double loopSeconds = 0.0;        // out: wall time of the iterations alone (chains, instances and data already set up)
     bool batchEvaluations = true;            // lockstep, engine builds: the evaluations the chains of one GPU begin together go
                                              // to the engine as ONE set of kernel launches (sb200EvalBatchAsync); same values
     bool parallelChains = false;             // every chain runs on its own host thread (implies perChainStreams); only the two
@@ -712,6 +713,8 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         }
     };
     sample(0);
+    const auto loopStart = std::chrono::steady_clock::now();
+    auto stopClock = [&]() { opt.loopSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - loopStart).count(); };
     if (opt.parallelChains && opt.nchains > 1) {
         // Side by side.  The swap schedule (which two chains, and the uniform deviate of the acceptance test) only
         // consumes the master stream, never a chain's state, so it is drawn up front in the order the in-turn loop
@@ -797,6 +800,7 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
             if (e) std::rethrow_exception(e);
         for (const std::vector<TraceRow>& r : rows) trace.insert(trace.end(), r.begin(), r.end());
         std::stable_sort(trace.begin() + 1, trace.end(), [](const TraceRow& x, const TraceRow& y) { return x.iteration < y.iteration; });
+        stopClock();
         return trace;
     }
     // all chains one iteration on: in turn, or (lockstep) update by update with the likelihoods of all chains in flight
@@ -837,6 +841,7 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         if (it % opt.samplefreq == 0) sample(it);
         swapChains();
     }
+    stopClock();
     return trace;
 }
 

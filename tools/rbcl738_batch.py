@@ -22,7 +22,7 @@ for c in range(K):
     if PINV > 0:
         model["rates"], model["probs"] = hostmodel.invariant_gamma_rates(PAUP_ALPHA * (1.0 + 0.1 * c), 4, PINV)
     elen = fx["edge_lengths"] * np.exp(0.2 * rng.standard_normal(fx["edge_lengths"].shape)) if c else fx["edge_lengths"]
-    L = ShardedLikelihood(tips, fx["counts"], len(model["rates"]), device=0, transient_partials=bool(os.environ.get("TRANSIENT")))
+    L = ShardedLikelihood(tips, fx["counts"], len(model["rates"]), device=0, transient_partials=bool(os.environ.get("TRANSIENT")), single=bool(os.environ.get("FP32")))
     Ls.append(L)
     eas.append(EvalArgs(model, fx["ops"], fx["pmatrix_index"], elen, int(fx["parent"]), 0))
 single = [L.calc_log_likelihood(ea) for L, ea in zip(Ls, eas)]
@@ -56,3 +56,15 @@ for _ in range(n_eval):
     batch_eval()
 us = (time.perf_counter() - t0) * 1e6 / n_eval
 print("K=%d fused batch call us/batch %.1f  aggregate evals/s %.0f" % (K, us, K / us * 1e6))
+
+# host side of the fused batch call: enqueue (sb200EvalBatchAsync returns) vs completion (sb200Finish of every chain)
+te = tf = 0.0
+for _ in range(n_eval):
+    t0 = time.perf_counter()
+    E.check(E.sb200EvalBatchAsync(K, insts, args), "batch")
+    t1 = time.perf_counter()
+    for L in Ls:
+        E.check(E.sb200Finish(L.inst, C.byref(out)), "finish")
+    t2 = time.perf_counter()
+    te += t1 - t0; tf += t2 - t1
+print("K=%d enqueue us %.1f  finish-wait us %.1f" % (K, te * 1e6 / n_eval, tf * 1e6 / n_eval))
