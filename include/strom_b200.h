@@ -73,7 +73,8 @@ STROM_API int sb200EvalAsync(int instance, const StromEvalArgs* args, double* de
  * better than -- one.  args[i] belongs to instances[i]; all instances must live on one device and share the category
  * count and the precision; they run on the first instance's stream from this call on.  Lists longer than 8 are cut
  * into sets of 8.  Every scalar is collected with sb200Finish(instances[i]).  Nothing is enqueued if any argument is
- * rejected. */
+ * rejected.  The parameter blocks of a set's instances share one pinned / device arena and go up in one copy.  The
+ * instances of a set must be driven from ONE host thread at a time (as every single instance must). */
 STROM_API int sb200EvalBatchAsync(int count, const int* instances, const StromEvalArgs* args);
 
 /* sb200ReplayAsync for a set of instances that were last evaluated together by sb200EvalBatchAsync. */

@@ -357,7 +357,17 @@ tiptip_tables_kernel(const __grid_constant__ TableBatch<real> B, const int C) {
 //   - multiplies, rescales by the per-pattern maximum over categories and states (in registers; across the
 //     category warps of the narrow shape through shared memory), writes the new partials with 256-bit stores.
 // ONE block barrier per step, placed between the maximum and the rescaling: it publishes the next step's
-// matrix image, retires the previous one and (narrow shape) carries the maxima.
+// matrix image, retires the previous one and carries the maxima of the category warps.
+// Why one barrier is enough (compute-sanitizer's racecheck is not available on the measurement pool, so the argument
+// is written down; the five thread shapes and repeated runs are tested to give identical bits):
+//   * images: step j reads sm[j&1] only BEFORE barrier B_j; image j+1 sits in the other buffer, was staged after
+//     B_{j-1} and is waited for (cp.async.wait_group 0, by every thread for its own copies) before B_j, so it is
+//     complete and visible after B_j; image j+2 is staged into sm[j&1] only AFTER B_j, when nobody reads image j
+//     any more.  The two images of the prologue are waited for and published by a barrier of their own.
+//   * maxima: step j writes smax[j&1] before B_j and reads it after B_j; the next write to the same half is step
+//     j+2's, after B_{j+1}, which every warp reaches only after its step-j reads.
+//   * operation records: written once per chunk between two barriers, read-only afterwards.
+//   * sAcc[tid] is private to its thread.
 // The log of each rescaling maximum is NOT taken per step: the maxima are multiplied into a running
 // product that is folded into a log sum only before it could underflow, chains hand (log sum,
 // product) pairs to their parents, and only the chain ending at the root takes one log per pattern.
