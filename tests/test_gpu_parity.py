@@ -145,10 +145,14 @@ def _shaped_problem(newick, npat, seed):
                 edge_lengths=elen, parent=np.int32(tree.preorder[0].number))
 
 
-@pytest.mark.parametrize("model", ["gtr_g4", "jc"])
-def test_caterpillar_tree_is_one_long_chain(engine, oracle, model):
-    # 700 taxa in a ladder: ONE chain of 698 operations, longer than the 256 operations a block keeps in shared
-    # memory (chunked path), with enough rescaling for the deferred log to fold several times
+@pytest.mark.parametrize("model,shape", [("gtr_g4", ""), ("jc", ""), ("gtr_g4", "1"), ("gtr_g4", "2"), ("gtr_i_g4", "4"), ("gtr_g4", "3")])
+def test_caterpillar_tree_is_one_long_chain(engine, oracle, model, shape, monkeypatch):
+    # 700 taxa in a ladder: ONE chain of 698 operations, longer than the 128 operations a block keeps in shared
+    # memory (chunked path, in every thread shape), with enough rescaling for the deferred log to fold several times
+    if shape:
+        monkeypatch.setenv("SB200_VARIANT", shape)
+    else:
+        monkeypatch.delenv("SB200_VARIANT", raising=False)
     n = 700
     nwk = "1:0.3"
     for t in range(2, n - 1):
