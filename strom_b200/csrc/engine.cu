@@ -211,6 +211,7 @@ struct Engine {
     bool evPending = false;
     bool usePdl = true;
     bool useTipsKernel = true;            // SB200_TIPS_KERNEL=0 (tuning aid): tips-only launches run the general kernel
+    bool useTipTipTables = true;          // precomputed tables for operations on two tips (streaming sizes; SB200_TABLES)
     int forceVariant = -1;                // SB200_VARIANT (tuning aid): every launch of a small instance runs this thread shape
     int wideMinWarps = 0;                 // small instances: a level runs a wide thread shape from this many warps (of that shape) up,
     int wide2MinWarps = 0;                // ... the two-categories-per-thread shape from this many (of ITS warps) up,
@@ -312,6 +313,7 @@ struct Engine {
         usePdl = envInt("SB200_PDL", 1) != 0;                 // tuning aid: plain stream order
         useTipsKernel = envInt("SB200_TIPS_KERNEL", 1) != 0;
         forceVariant = envInt("SB200_VARIANT", -1);
+        useTipTipTables = envInt("SB200_TABLES", bigTiles() ? 1 : 0) != 0;
         wideMinWarps = envInt("SB200_WIDE_MIN_WARPS", 64 * smCount);
         wide2MinWarps = envInt("SB200_WIDE2_MIN_WARPS", 16 * smCount);
         narrowMinWarps = envInt("SB200_NARROW_MIN_WARPS", smCount);
@@ -430,6 +432,11 @@ struct Engine {
     //   * many tiles (streaming sizes): enough blocks for >= 8 waves, so the last partial wave costs little.
     LevelChoice chooseLevel(int chainCount, bool tipsCandidate) const {
         LevelChoice c;
+        if (chainCount == 0) {                           // the planner's question about tip x tip tables (schedule.hpp)
+            c.variant = 0;
+            c.groups = useTipTipTables ? 1 : kNoTipTipTables;
+            return c;
+        }
         if (bigTiles()) {
             c.variant = kVarStream;
             const int tiles = Ppad / varPatterns(C, kVarStream, static_cast<int>(realSize()));

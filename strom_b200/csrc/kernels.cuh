@@ -620,7 +620,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             mfac = static_cast<double>(sm[ib][25 * TTE + combo]);
         } else {
             // factor of operand A (from registers, or a column of P at a chain start with a tip), then operand B
-            if (!TIPS && (flags & OP_A_TIP)) {       // (TIPS: a chain start with a tip for A is a tip x tip operation)
+            if (flags & OP_A_TIP) {                  // (a chain start at a tip; with tables and TIPS that is a tip x tip operation)
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
 #pragma unroll

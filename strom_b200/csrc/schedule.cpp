@@ -17,12 +17,12 @@ static DevOp makeOp(int dest, int a, int ma, int b, int mb, int sa, int sb, int 
 
 // Operations whose two operands are tips produce, per category, one of only 5x5 possible vectors
 // (and rescaling maxima): they get a table computed once per evaluation instead of per pattern.
-static void assignTipTipTables(Schedule& out, int tipCount) {
+static void assignTipTipTables(Schedule& out, int tipCount, bool tables) {
     out.tipTipCount = 0;
     for (DevOp& d : out.ops) {
         if ((d.flags & OP_CHAIN_START) && d.a >= 0 && d.a < tipCount) d.flags |= OP_A_TIP;
         if (d.b < tipCount) d.flags |= OP_B_TIP;
-        if ((d.flags & OP_A_TIP) && (d.flags & OP_B_TIP)) {
+        if (tables && (d.flags & OP_A_TIP) && (d.flags & OP_B_TIP)) {
             d.flags |= OP_TIPTIP;
             d.tt = out.tipTipCount++;
         }
@@ -115,7 +115,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
             out.partialWrites += 1;
             if (accumulate && rescale) out.scalerRows += 2;
         }
-        assignTipTipTables(out, tipCount);
+        assignTipTipTables(out, tipCount, policy(0, true).groups != kNoTipTipTables);
         return BEAGLE_SUCCESS;
     }
 
@@ -295,7 +295,7 @@ int buildSchedule(const BeagleOperation* ops, int count, int tipCount, int parti
         out.levels.push_back(L);
     }
     for (int o = 0; o < count; ++o) out.opChain[o] = chainNewId[out.opChain[o]];
-    assignTipTipTables(out, tipCount);
+    assignTipTipTables(out, tipCount, policy(0, true).groups != kNoTipTipTables);
     for (Level& L : out.levels) {
         bool tips = L.groupCount > 0;
         for (int g = L.groupStart; g < L.groupStart + L.groupCount && tips; ++g)

@@ -76,6 +76,10 @@ struct LevelChoice {
     int groups;
 };
 typedef std::function<LevelChoice(int chainCount, bool tipsCandidate)> LevelPolicy;
+// Asked with chainCount == 0 the policy says whether operations on two tips get a precomputed (stateA, stateB) table
+// (any answer but groups == kNoTipTipTables), or are computed per pattern from the two tip columns like any other operation
+// (small instances: the kernel that builds the tables is 8 us on the critical path of a 90 us evaluation).
+constexpr int kNoTipTipTables = -12345;
 
 struct Group {
     int opStart;
