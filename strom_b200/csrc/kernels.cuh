@@ -95,15 +95,20 @@ __host__ __device__ constexpr int varWarps(int C, int V, int realBytes) { return
 __host__ __device__ constexpr int varThreads(int C, int V, int realBytes) { return 32 * varWarps(C, V, realBytes); }
 __host__ __device__ constexpr int varPatterns(int C, int V, int realBytes) { return 32 * varTP(C, V, realBytes); }   // patterns per block
 #ifndef SB200_REG_BUDGET
-#define SB200_REG_BUDGET 80
+#define SB200_REG_BUDGET 96
 #endif
 #ifndef SB200_REG_BUDGET_MOST
 #define SB200_REG_BUDGET_MOST 96
 #endif
+#ifndef SB200_REG_BUDGET_TIPS
+#define SB200_REG_BUDGET_TIPS 80
+#endif
 __host__ __device__ constexpr int varBlocksPerSm(int C, int V, bool tips, int realBytes) {
-    // registers per thread the kernel is compiled for: 64 for the tips-only variants; otherwise 96 where a thread carries
-    // three or four FP64 categories (stream / wide: no spills, 5 resident blocks of 4 warps), 80 for the others
-    const int regs = tips ? 64 : (realBytes == 8 && varCPT(C, V, realBytes) >= 3) ? SB200_REG_BUDGET_MOST : SB200_REG_BUDGET;
+    // registers per thread the kernel is compiled for: 80 for the tips-only variants, 96 otherwise (no spills with four FP64
+    // categories per thread; 5 resident blocks of 4 warps).  Measured, rbcl738 single / 8 batched chains / 250k patterns:
+    // 64 + 80 registers 85.6 us / 318 us / 7.36 ms, 80 + 96 (kept) 81.2 / 306 / 7.20, 80 + 112 80.2 / 308 / 7.22, 128 80.2 / 317 / 7.35:
+    // the launches are bound by latency, not by occupancy, and a wider register window lets ptxas overlap more of a step
+    const int regs = tips ? SB200_REG_BUDGET_TIPS : (realBytes == 8 && varCPT(C, V, realBytes) >= 3) ? SB200_REG_BUDGET_MOST : SB200_REG_BUDGET;
     const int byRegs = 65536 / (regs * varThreads(C, V, realBytes));
     return byRegs < 1 ? 1 : byRegs > 16 ? 16 : byRegs;
 }
