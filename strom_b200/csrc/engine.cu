@@ -124,6 +124,7 @@ struct Engine {
     bool fp32 = false;
     int nTips = 0, nPartials = 0, nCompact = 0, P = 0, nEigen = 0, nMat = 0, C = 0, nScale = 0;
     int Ppad = 0;                         // pattern axis padded to whole thread-block tiles in every buffer
+    bool streaming = false;               // P x C large enough for the streaming thread shape on every launch (bigTiles)
     long long tipStride = 0;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     int batchHint = 1;                    // evaluations launched side by side with this one (shapes the plan's launches)
@@ -277,6 +278,8 @@ struct Engine {
         CK(cudaEventCreateWithFlags(&schedCopied, cudaEventDisableTiming));
         // pattern axis padded to a whole number of thread-block tiles of every kernel that walks it: the pruning shapes
         // hold 32 .. 256 patterns per block, the root kernel 128
+        streaming = static_cast<long long>(P) * C >= (1LL << 18);
+        if (const char* f = std::getenv("SB200_FORCE_BIG")) streaming = (f[0] == '1');   // tuning aid
         {
             const int unit = bigTiles() ? 256 : 128;
             Ppad = ((P + unit - 1) / unit) * unit;
@@ -415,11 +418,7 @@ struct Engine {
     // ---- (b) ---------------------------------------------------------------------------
     // Streaming sizes run one thread shape (kVarStream) on every launch; small instances choose per launch between the
     // wide and the narrow shape (kernels.cuh).  Fixed at creation: it sets the pattern padding.
-    bool bigTiles() const {
-        bool big = static_cast<long long>(P) * C >= (1LL << 18);
-        if (const char* f = std::getenv("SB200_FORCE_BIG")) big = (f[0] == '1');   // tuning aid
-        return big;
-    }
+    bool bigTiles() const { return streaming; }
     int blocksPerSm(int V, bool tips) const { return varBlocksPerSm(C, V, tips && useTipsKernel, static_cast<int>(realSize())); }
 
     // Shape and group count of a launch.  Every block pays a fixed set-up (operation words, first images and
@@ -835,7 +834,7 @@ static void launchPartialsSetT(Engine* const* es, int K, const int* cumIdx) {
     int tilesOf[kVarCount];
     for (int v = 0; v < kVarCount; ++v) tilesOf[v] = L.Ppad / varPatterns(C, v, sizeof(real));
     tilesOf[kVarQuad] = L.Ppad / kQuadPatterns;
-    const int traceLevel = envInt("SB200_TRACE_LEVEL", -1);   // tuning aid (needs -DSB200_TRACE)
+    static const int traceLevel = envInt("SB200_TRACE_LEVEL", -1);   // tuning aid (needs -DSB200_TRACE)
     for (size_t l = 0; l < maxLevels; ++l) {
         // the instances' launches number l, grouped by (thread shape, tips-only): normally ONE launch
         bool done[kMaxBatch] = {false};
