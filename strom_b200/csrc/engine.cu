@@ -340,7 +340,11 @@ struct Engine {
         unsigned char* nd = nullptr;
         CK(cudaMallocHost(&nh, blockBytes));
         std::memcpy(nh, hBlock, blockBytes);
-        CK(cudaMalloc(&nd, blockBytes));
+        const cudaError_t e = cudaMalloc(&nd, blockBytes);
+        if (e != cudaSuccess) {
+            cudaFreeHost(nh);
+            throw CudaFail{e};
+        }
         hBlock = nh;
         dBlock = nd;
         arena.reset();
