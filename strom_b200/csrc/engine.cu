@@ -1148,7 +1148,7 @@ extern "C" BeagleResourceList* beagleGetResourceList(void) {
         if (cudaGetDeviceProperties(&prop, i) == cudaSuccess)
             std::snprintf(g_resNames[i], sizeof(g_resNames[i]), "%s", prop.name);
         else
-            std::snprintf(g_resNames[i], sizeof(g_resNames[i]), "%s %d", g_resName, i);
+            std::snprintf(g_resNames[i], sizeof(g_resNames[i]), "%.200s %d", g_resName, i);
         g_res[i].name = g_resNames[i];
         g_res[i].description = g_resDesc;
         g_res[i].supportFlags = BEAGLE_FLAG_PRECISION_DOUBLE | BEAGLE_FLAG_PRECISION_SINGLE | BEAGLE_FLAG_SCALING_MANUAL |
