@@ -677,21 +677,9 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
         ch.start();
     }
     std::vector<TraceRow> trace;
-    auto rowOf = [](Chain& ch, unsigned iteration) {
-        TraceRow r;
-        r.iteration = iteration;
-        r.lnL = ch.calcLogLikelihood();                 // one more full evaluation per sample, as in Strom::sample (:455)
-        r.lnPrior = ch.calcLogJointPrior();
-        r.TL = ch.getTreeManip()->calcTreeLength();
-        const std::vector<double> x = ch.getModel()->getExchangeabilities(), f = ch.getModel()->getStateFreqs();
-        for (int i = 0; i < 6; ++i) r.params[i] = x[i];
-        for (int i = 0; i < 4; ++i) r.params[6 + i] = f[i];
-        r.params[10] = ch.getModel()->getGammaShape();
-        return r;
-    };
     auto sample = [&](unsigned iteration) {
         for (Chain& ch : chains)
-            if (ch.getHeatingPower() == 1.0) trace.push_back(rowOf(ch, iteration));
+            if (ch.getHeatingPower() == 1.0) trace.push_back(traceRowOf(ch, iteration));
     };
     auto swapChains = [&]() {
         if (opt.nchains == 1) return;
@@ -785,7 +773,7 @@ inline std::vector<TraceRow> runMCMC(Data::SharedPtr data, const std::string& ne
                 ch.stopTuning();
                 for (unsigned it = 1; it <= opt.niter; ++it) {
                     ch.nextStep(static_cast<int>(it));
-                    if (it % opt.samplefreq == 0 && ch.getHeatingPower() == 1.0) rows[c].push_back(rowOf(ch, it));
+                    if (it % opt.samplefreq == 0 && ch.getHeatingPower() == 1.0) rows[c].push_back(traceRowOf(ch, it));
                     propose(c, opt.burnin + it - 1);
                 }
             } catch (...) {
