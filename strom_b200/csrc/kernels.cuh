@@ -91,8 +91,15 @@ __host__ __device__ constexpr int varTP(int C, int V, int realBytes) {
          : V == kVarStream ? (SB200_STREAM_WARPS / varNCW(C, V, realBytes) > 0 ? SB200_STREAM_WARPS / varNCW(C, V, realBytes) : 1)
                            : (SB200_WIDE_WARPS / varNCW(C, V, realBytes) > 0 ? SB200_WIDE_WARPS / varNCW(C, V, realBytes) : 1);
 }
-__host__ __device__ constexpr int varWarps(int C, int V, int realBytes) { return varNCW(C, V, realBytes) * varTP(C, V, realBytes); }
-__host__ __device__ constexpr int varThreads(int C, int V, int realBytes) { return 32 * varWarps(C, V, realBytes); }
+__host__ __device__ constexpr int varWarps(int C, int V, int realBytes) { return varNCW(C, V, realBytes) * varTP(C, V, realBytes); }   // compute warps
+// Narrow shape: one more warp per block that does no arithmetic.  It stages the matrix images of the steps ahead and keeps
+// the log-scalers of the block's 32 patterns, so that the category warps -- whose instruction stream IS the duration of a
+// step at the top of a small tree -- carry neither (SB200_HELPER_WARP=0: the category warps do both, as in the other shapes).
+#ifndef SB200_HELPER_WARP
+#define SB200_HELPER_WARP 1
+#endif
+__host__ __device__ constexpr int varHelperWarps(int V) { return (V == kVarNarrow && SB200_HELPER_WARP) ? 1 : 0; }
+__host__ __device__ constexpr int varThreads(int C, int V, int realBytes) { return 32 * (varWarps(C, V, realBytes) + varHelperWarps(V)); }
 __host__ __device__ constexpr int varPatterns(int C, int V, int realBytes) { return 32 * varTP(C, V, realBytes); }   // patterns per block
 #ifndef SB200_REG_BUDGET
 #define SB200_REG_BUDGET 96
@@ -464,13 +471,16 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     constexpr int TTS = ttStride(C, sizeof(real));       // reals per tip x tip table
     constexpr int NTT = TTS / CHUNK;                     // 16-byte chunks per table
     constexpr int IMG = TTS > 2 * MSZ ? TTS : 2 * MSZ;   // shared image of one step: two matrices OR one table
-    constexpr int NSTG = (IMG / CHUNK + THREADS - 1) / THREADS;   // staging chunks per thread
+    constexpr bool kHelper = varHelperWarps(V) > 0;      // the block's last warp stages the images and keeps the log-scalers
+    constexpr int STAGERS = kHelper ? 32 : THREADS;      // threads that stage
+    constexpr int NSTG = (IMG / CHUNK + STAGERS - 1) / STAGERS;   // staging chunks per staging thread
     constexpr bool kSingleWarp = THREADS == 32;
+    static_assert(!kHelper || TP == 1, "the helper warp keeps the scalers of ONE pattern sub-tile");
     constexpr bool kPrefetch = V == kVarStream && kPrefetchAhead > 0 && !TIPS;   // (small instances live in L2 anyway)
     __shared__ __align__(16) real sm[2][IMG];
     __shared__ DevRec sops[kOpChunk];
     __shared__ double sAcc[THREADS];                     // log part of the running scaler (touched rarely)
-    __shared__ real smax[2][NCW > 1 ? THREADS : 1];      // narrow shape: per-warp maxima of a step, double-buffered
+    __shared__ real smax[2][(NCW > 1 || kHelper) ? THREADS : 1];   // per-warp maxima of a step, double-buffered
 
     const int z = blockIdx.z;
     pdlLaunchDependents();
@@ -479,10 +489,11 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int kb = (warp % NCW) * CPT;                   // first category of this thread
-    const int sp = warp / NCW;                           // pattern sub-tile of this warp
+    const bool helper = kHelper && warp >= NCW * TP;     // (warp-uniform)
+    const int kb = helper ? 0 : (warp % NCW) * CPT;      // first category of this thread
+    const int sp = helper ? 0 : warp / NCW;              // pattern sub-tile of this warp
     constexpr bool kEven = NCW * CPT == C;               // otherwise the last category warp repeats category C-1 in its spare slots
-    const bool scalerWarp = NCW == 1 || kb == 0;         // the warp that keeps a pattern's log-scalers
+    const bool scalerWarp = kHelper ? helper : (NCW == 1 || kb == 0);   // the warp that keeps a pattern's log-scalers
     const Group grp = A.groups[B.groupBase[z] + blockIdx.y];
     const int nOps = grp.opEnd - grp.opStart;
     const int Ppad = A.Ppad;
@@ -498,6 +509,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
 
     auto blockSync = [&]() {
         if (kSingleWarp) __syncwarp();
+        else if (kHelper) asm volatile("bar.sync 0, %0;" ::"n"(THREADS) : "memory");   // (the helper warp arrives from its own loop)
         else __syncthreads();
     };
     // ---- helpers ---------------------------------------------------------------------------
@@ -508,13 +520,13 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             const real* src = A.ttTables + static_cast<size_t>(w.w) * TTS;
 #pragma unroll
             for (int s = 0; s < NSTG; ++s) {
-                const int c = tid + s * THREADS;
+                const int c = (kHelper ? lane : tid) + s * STAGERS;
                 if (c < NTT) cpAsync16(&sm[buf][c * CHUNK], src + c * CHUNK);
             }
         } else {
 #pragma unroll
             for (int s = 0; s < NSTG; ++s) {
-                const int c = tid + s * THREADS;
+                const int c = (kHelper ? lane : tid) + s * STAGERS;
                 if (c < 2 * NCH) {
                     const int o = c >= NCH ? 1 : 0;
                     cpAsync16(&sm[buf][c * CHUNK], mats + static_cast<size_t>(o ? w.z : w.y) * MSZ + (c - o * NCH) * CHUNK);
@@ -564,12 +576,16 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
     // operand A of a chain start, and the scaler of the chain that produced it.  A TIP for A is asked for earlier, with
     // operand B (fetchTipA): it needs no register the current step still uses, and at the end of the step its latency
     // would sit on the critical path of the next one (every other step of a tips-only launch starts a chain).
-    auto fetchTipA = [&](const DevRec& r) {
+    // (each in two parts: what the arithmetic warps do, and what the warp that keeps the scalers does -- the same warp
+    // unless the shape has a helper warp)
+    auto tipAOperand = [&](const DevRec& r) {
         if ((r.flags & OP_CHAIN_START) && (TIPS || (r.flags & OP_A_TIP))) sX = *byteOffset(tmine, r.aOff);
     };
-    auto startChain = [&](const DevRec& r) {
+    auto startChainOperand = [&](const DevRec& r) {
         if (!TIPS && !(r.flags & OP_A_TIP)) fetchPartial(r.aOff, X);
-        if (!TIPS && scalerWarp) {
+    };
+    auto startChainScaler = [&](const DevRec& r) {
+        if (!TIPS) {
             const int sa = r.sa;
             if (sa >= 0) {
                 const double a = accMine[static_cast<size_t>(sa) * Ppad];
@@ -579,16 +595,29 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         }
     };
     // operand B (and its chain's scaler) of an operation, one step ahead of its use
-    auto fetchB = [&](const DevRec& r) {
+    auto fetchBOperand = [&](const DevRec& r) {
         if (TIPS || (r.flags & OP_B_TIP)) sY = *byteOffset(tmine, r.bOff);
         else fetchPartial(r.bOff, Y);
-        if (!TIPS && scalerWarp) {
+    };
+    auto fetchBScaler = [&](const DevRec& r) {
+        if (!TIPS) {
             const int sb = r.sb;
             if (sb >= 0) {
                 pendAcc = accMine[static_cast<size_t>(sb) * Ppad];
                 pendProd = prodMine[static_cast<size_t>(sb) * Ppad];
             }
         }
+    };
+    const bool inlineScalers = !kHelper && scalerWarp;   // the arithmetic warps keep the scalers themselves
+    // the forms the arithmetic warps use inside a step
+    auto fetchTipA = [&](const DevRec& r) { tipAOperand(r); };
+    auto startChain = [&](const DevRec& r) {
+        startChainOperand(r);
+        if (inlineScalers) startChainScaler(r);
+    };
+    auto fetchB = [&](const DevRec& r) {
+        fetchBOperand(r);
+        if (inlineScalers) fetchBScaler(r);
     };
 
 #ifdef SB200_TRACE
@@ -599,6 +628,65 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
 #else
 #define SB200_TICK(slot)
 #endif
+    // the running scaler after operation j: times this step's maximum; a chain end hands it on
+    auto scalerTail = [&](const int flags, const int j, const double mfac) {
+        // deferred log: multiply the maxima, fold into the log sum only before an underflow
+        {
+            const double t = prod * mfac;
+            if (t < 1e-200) {
+                sAcc[tid] += foldedLog(prod, mfac);
+                prod = 1.0;
+            } else {
+                prod = t;
+            }
+        }
+        if (flags & (OP_STORE_S | OP_CHAIN_END)) {
+            // a chain end hands its subtree log-scaler to the parent chain (and resets); incremental plans keep
+            // every node's (OP_STORE_S: store and carry on)
+            const int sOut = sops[j].sOut;
+            double a = sAcc[tid];
+            if (sOut >= 0) {
+                if (prod < 1e-100) {                     // keep a parent's product of two stored factors normal
+                    a += foldedLog(prod, 1.0);
+                    prod = 1.0;
+                    if (!(flags & OP_CHAIN_END)) sAcc[tid] = a;
+                }
+                accMine[static_cast<size_t>(sOut) * Ppad] = a;
+                prodMine[static_cast<size_t>(sOut) * Ppad] = prod;
+            }
+            if (flags & OP_CHAIN_END) {
+                if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr) {
+                    const double total = scalerTotal(a, prod);
+                    double* c = A.cum + pat;
+                    if (A.cumMode) *c = total;
+                    else *c += total;
+                }
+                sAcc[tid] = 0.0;
+                prod = 1.0;
+            }
+        }
+    };
+    // ---- the helper warp's step (narrow shape): image j+2 on its way, then the scalers of operation j -------------
+    // Same barrier, same order of scaler operations as the inline form below: the pending scaler of operand B, the
+    // request for the next one, this step's maximum (taken from the category warps' exchange), the chain end, the
+    // scaler of a chain start.
+    auto helperStep = [&](const int j, const int nc) {
+        const bool more = j + 1 < nc;
+        const int flags = sops[j].flags;
+        const int ib = j & 1;
+        if (more) cpAsyncWaitAll();   // image j+1 has landed
+        blockSync();
+        if (j + 2 < nc) stage(j & 1, sops[j + 2]);
+        if (!TIPS && !(flags & OP_TIPTIP) && sops[j].sb >= 0) accumulate(pendAcc, pendProd);
+        if (more) fetchBScaler(sops[j + 1]);
+        real m = smax[ib][lane];
+#pragma unroll
+        for (int w = 1; w < NCW; ++w) m = rmax(m, smax[ib][w * 32 + lane]);
+        if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) m = (m == real(0)) ? real(1) : m;
+        scalerTail(flags, j, static_cast<double>(m));
+        if (more && (sops[j + 1].flags & OP_CHAIN_START)) startChainScaler(sops[j + 1]);
+    };
+
     // ---- one step: operation j of the chunk ------------------------------------------------------------
     // On entry image j is visible to the whole block and image j+1 is on its way.
     auto step = [&](const int j, const int nc) {
@@ -623,6 +711,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                 for (int i = 0; i < 4; ++i) X[c][i] = sm[ib][combo * TTE + kcat(c) * 4 + i];
             }
             mfac = static_cast<double>(sm[ib][25 * TTE + combo]);
+            if (kHelper) smax[ib][tid] = sm[ib][25 * TTE + combo];
         } else {
             // factor of operand A (from registers, or a column of P at a chain start with a tip), then operand B
             if (flags & OP_A_TIP) {                  // (a chain start at a tip; with tables and TIPS that is a tip x tip operation)
@@ -669,7 +758,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                     }
                 }
             }
-            if (!TIPS && scalerWarp && sops[j].sb >= 0) accumulate(pendAcc, pendProd);
+            if (!TIPS && inlineScalers && sops[j].sb >= 0) accumulate(pendAcc, pendProd);
             SB200_TICK(2)
             // next step's operand B (and a tip for A) is requested now; the rescaling below hides its latency
             if (more) {
@@ -680,15 +769,17 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
                 m = rmax(rmax(X[0][0], X[0][1]), rmax(X[0][2], X[0][3]));
 #pragma unroll
                 for (int c = 1; c < CPT; ++c) m = rmax(m, rmax(rmax(X[c][0], X[c][1]), rmax(X[c][2], X[c][3])));
-                if (NCW > 1) smax[ib][tid] = m;
+                if (NCW > 1 || kHelper) smax[ib][tid] = m;
+            } else if (kHelper) {
+                smax[ib][tid] = real(1);
             }
             mfac = 1.0;
         }
         SB200_TICK(3)
-        if (more) cpAsyncWaitAll();   // (my part of) image j+1 has landed
+        if (!kHelper && more) cpAsyncWaitAll();   // (my part of) image j+1 has landed
         blockSync();                  // image j+1 and this step's maxima visible; everyone is done with image j
         SB200_TICK(4)
-        if (j + 2 < nc) stage(j & 1, sops[j + 2]);
+        if (!kHelper && j + 2 < nc) stage(j & 1, sops[j + 2]);
         if (!(flags & OP_TIPTIP) && (flags & OP_RESCALE)) {
             if (NCW > 1) {
                 m = smax[ib][(sp * NCW) * 32 + lane];
@@ -717,43 +808,7 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
             for (int c = 0; c < CPT; ++c)
                 if (kEven || kb + c < C) st4Stream(dest + catOff(c), X[c]);
         }
-        if (scalerWarp) {
-            // deferred log: multiply the maxima, fold into the log sum only before an underflow
-            {
-                const double t = prod * mfac;
-                if (t < 1e-200) {
-                    sAcc[tid] += foldedLog(prod, mfac);
-                    prod = 1.0;
-                } else {
-                    prod = t;
-                }
-            }
-            if (flags & (OP_STORE_S | OP_CHAIN_END)) {
-                // a chain end hands its subtree log-scaler to the parent chain (and resets); incremental plans keep
-                // every node's (OP_STORE_S: store and carry on)
-                const int sOut = sops[j].sOut;
-                double a = sAcc[tid];
-                if (sOut >= 0) {
-                    if (prod < 1e-100) {                     // keep a parent's product of two stored factors normal
-                        a += foldedLog(prod, 1.0);
-                        prod = 1.0;
-                        if (!(flags & OP_CHAIN_END)) sAcc[tid] = a;
-                    }
-                    accMine[static_cast<size_t>(sOut) * Ppad] = a;
-                    prodMine[static_cast<size_t>(sOut) * Ppad] = prod;
-                }
-                if (flags & OP_CHAIN_END) {
-                    if ((flags & OP_ADD_TO_CUM) && A.cum != nullptr) {
-                        const double total = scalerTotal(a, prod);
-                        double* c = A.cum + pat;
-                        if (A.cumMode) *c = total;
-                        else *c += total;
-                    }
-                    sAcc[tid] = 0.0;
-                    prod = 1.0;
-                }
-            }
-        }
+        if (inlineScalers) scalerTail(flags, j, mfac);
         if (more && (sops[j + 1].flags & OP_CHAIN_START)) startChain(sops[j + 1]);
         SB200_TICK(6)
     };
@@ -770,11 +825,18 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         blockSync();
         if (chunk0 == 0) pdlWait();   // the plan is in shared memory; everything below reads what earlier kernels wrote
         for (int w = tid; w < nc; w += THREADS) SB200_CHECK_REC(sops[w], grp.opStart + chunk0 + w);
-        stage(0, sops[0]);
-        if (nc > 1) stage(1, sops[1]);
-        fetchTipA(sops[0]);
-        if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);       // (a later chunk may begin in mid-chain: A is carried)
-        fetchB(sops[0]);
+        if (!kHelper || helper) {
+            stage(0, sops[0]);
+            if (nc > 1) stage(1, sops[1]);
+        }
+        if (kHelper && helper) {
+            if (sops[0].flags & OP_CHAIN_START) startChainScaler(sops[0]);
+            fetchBScaler(sops[0]);
+        } else {
+            fetchTipA(sops[0]);
+            if (sops[0].flags & OP_CHAIN_START) startChain(sops[0]);       // (a later chunk may begin in mid-chain: A is carried)
+            fetchB(sops[0]);
+        }
         if (kPrefetch) {
 #pragma unroll
             for (int a = 1; a <= kPrefetchAhead; ++a)
@@ -782,8 +844,13 @@ prune_chains_kernel(const __grid_constant__ PruneBatch<real> B) {
         }
         cpAsyncWaitAll();
         blockSync();                  // images 0 and 1 visible
+        if (kHelper && helper) {
 #pragma unroll 1
-        for (int j = 0; j < nc; ++j) step(j, nc);
+            for (int j = 0; j < nc; ++j) helperStep(j, nc);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < nc; ++j) step(j, nc);
+        }
     }
 }
 
