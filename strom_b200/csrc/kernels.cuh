@@ -57,7 +57,9 @@ __host__ __device__ constexpr int ttStride(int C, int realBytes) { return 25 * t
 //               (the lower levels of one rbcl738 evaluation);
 //   kVarNarrow  one category per thread (a warp per category): C times the warps and a C times shorter dependent
 //               instruction stream per step, for launches with few chains, where a step is bound by the latency of
-//               one warp's instructions;
+//               one warp's instructions; a HELPER warp per block takes everything that is not arithmetic off the
+//               category warps: it stages the matrix images and keeps the patterns' log-scalers (it reads the
+//               step's maxima from the category warps' exchange);
 //   kVarQuad    one STATE of one category of one pattern per thread (prune_quad_kernel: a warp = 8 patterns x 4 states
 //               of a category, a block = C such warps): below one warp per SM (tiny data sets).
 // ------------------------------------------------------------------------------------------
@@ -380,6 +382,10 @@ tiptip_tables_kernel(const __grid_constant__ TableBatch<real> B, const int C) {
 //     j+2's, after B_{j+1}, which every warp reaches only after its step-j reads.
 //   * operation records: written once per chunk between two barriers, read-only afterwards.
 //   * sAcc[tid] is private to its thread.
+//   * helper warp (narrow shape): it is the only stager, waits for its own copies before B_j and stages image j+2 after
+//     B_j like every thread above; it reads smax[j&1] after B_j like the category warps; the scaler slots and the
+//     cumulative buffer of a pattern are touched by its lane alone.  It arrives at the same barriers from its own loop
+//     (bar.sync 0 with the block's thread count).
 // The log of each rescaling maximum is NOT taken per step: the maxima are multiplied into a running
 // product that is folded into a log sum only before it could underflow, chains hand (log sum,
 // product) pairs to their parents, and only the chain ending at the root takes one log per pattern.
